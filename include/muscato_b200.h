@@ -1,0 +1,169 @@
+/* muscato_b200.h -- C ABI of the B200-native screen -> group -> confirm -> combine hot path.
+ *
+ * The reference (kshedden/muscato) has no FFI: its boundary is process level
+ * (executables + config.json + files in TempDir).  This header is the thin layer a
+ * cgo shim or the stage-compatible C++ executables bind.  Each
+ * entry point names the reference code it replaces (file:line under the reference
+ * tree).  Plain C, opaque handle, caller-owned inputs (borrowed for the call),
+ * library-owned outputs released with msc_free, int return codes (0 = ok), no
+ * exceptions across the boundary.  A context is bound to one CUDA device and is not
+ * thread-safe (callers serialise).  There is NO CPU fallback: without a usable
+ * sm_100 device msc_create fails with MSC_ERR_CUDA.
+ */
+#ifndef MUSCATO_B200_H
+#define MUSCATO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSC_MAX_WINDOWS 32
+#define MSC_MAX_WINDOW_WIDTH 32
+#define MSC_MAX_READ_LENGTH 1024
+
+enum {
+  MSC_OK = 0,
+  MSC_ERR_CONFIG = 1,   /* invalid / unsupported configuration */
+  MSC_ERR_INPUT = 2,    /* malformed input buffers */
+  MSC_ERR_CUDA = 3,     /* CUDA runtime failure (message in msc_last_error) */
+  MSC_ERR_STATE = 4,    /* call order violated (e.g. screen before set_reads) */
+  MSC_ERR_NOMEM = 5,
+  MSC_ERR_IO = 6
+};
+
+enum { MSC_MATCH_FIRST = 0, MSC_MATCH_BEST = 1 };
+
+/* The hot-path subset of utils.Config (utils/config.go:10-101) plus device selection.
+ * BloomSize / NumHash are accepted by the stage executables and ignored: the
+ * rolling-hash Bloom screen (cmd/muscato_screen/main.go:86-253) is replaced by an
+ * exact key table behind a blocked Bloom front. */
+typedef struct msc_config {
+  int32_t n_windows;                  /* len(Config.Windows), 1..MSC_MAX_WINDOWS */
+  int32_t windows[MSC_MAX_WINDOWS];   /* Config.Windows (left end of each window) */
+  int32_t window_width;               /* Config.WindowWidth, 1..MSC_MAX_WINDOW_WIDTH */
+  int32_t max_read_length;            /* Config.MaxReadLength, <= MSC_MAX_READ_LENGTH */
+  double  pmatch;                     /* Config.PMatch; nmiss = int((1-PMatch)*float64(L)), confirm main.go:198 */
+  int32_t min_dinuc;                  /* Config.MinDinuc (utils/entropy.go) */
+  int32_t mmtol;                      /* Config.MMTol (cmd/muscato_combine_windows/main.go:36-60) */
+  int64_t max_matches;                /* Config.MaxMatches (cmd/muscato_confirm/main.go:233-242, 424-448) */
+  int32_t match_mode;                 /* MSC_MATCH_FIRST / MSC_MATCH_BEST */
+  int32_t device;                     /* CUDA device ordinal */
+  int32_t bloom_bits_per_key;         /* 0 = default; tuning only, never changes results */
+  int32_t keep_ascii;                 /* keep device copies of the ASCII inputs (needed by msc_rebuild) */
+  int32_t reserved[8];
+} msc_config;
+
+/* One confirmed alignment: the fields of an rmatch/matches.txt line
+ * (cmd/muscato_confirm/main.go:221-230) as integers.  The text columns are
+ * read = reads[read_id], target = targets[gene_id][pos : pos+len(read)]. */
+typedef struct msc_match {
+  uint32_t read_id;   /* index into the reads passed to msc_set_reads (reads_sorted order) */
+  uint32_t gene_id;   /* 0-based target line index (cmd/muscato_screen/main.go:440-452) */
+  uint32_t pos;       /* mpos - len(mlft): start of the read within the target */
+  uint32_t nx;        /* mismatch count */
+} msc_match;
+
+typedef struct msc_stats {
+  uint64_t n_reads, n_keys, n_key_groups, table_slots, bloom_bytes;
+  uint64_t n_targets, target_bases, positions_probed;
+  uint64_t n_candidates, n_pairs, n_pass, n_matches_pre, n_matches;
+  uint64_t n_overflow_groups;         /* (window,key) groups that hit MaxMatches */
+  uint64_t h2d_bytes, d2h_bytes;
+  uint64_t kernel_launches;           /* kernels launched by this library since msc_reset_stats */
+  float ms_pack_reads, ms_build, ms_pack_targets, ms_scan, ms_expand, ms_confirm, ms_combine;
+  float ms_scan_kernel;               /* the scan kernel alone (CUDA events on the launch stream) */
+  float reserved_f[8];
+} msc_stats;
+
+typedef struct msc_ctx msc_ctx;
+
+/* Library / build identification (no GPU needed).  msc_struct_size lets a binding verify
+ * its mirror of the structs: which = 0 msc_config, 1 msc_match, 2 msc_stats, 3 msc_key_rec,
+ * 4 msc_cand_rec. */
+const char* msc_version(void);
+uint64_t msc_struct_size(int which);
+
+/* Create / destroy a context on config.device.  Validates the configuration like
+ * checkArgs (cmd/muscato/main.go:833-904) does for the fields it owns.  On failure
+ * returns NULL and, if err/errlen are given, writes a message there. */
+msc_ctx* msc_create(const msc_config* config, char* err, uint64_t errlen);
+void msc_destroy(msc_ctx* ctx);
+const char* msc_last_error(const msc_ctx* ctx);
+
+/* Unique reads in reads_sorted.txt order (first field of each line,
+ * cmd/muscato_screen/main.go:165-172; cmd/muscato_window_reads/main.go:100-101):
+ * read i is ascii[offs[i] .. offs[i+1]).  Alphabet A,C,G,T,X (any other byte is
+ * treated as X).  Uploads, 2-bit packs on the device and builds the window-key
+ * table: replaces buildBloom (cmd/muscato_screen/main.go:116-207), muscato_window_reads
+ * (cmd/muscato_window_reads/main.go:94-141) and sortWindows (cmd/muscato/main.go:237-304). */
+int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint64_t n_reads);
+
+/* Targets in GeneFileName order (gene id = index, cmd/muscato_screen/main.go:440-452):
+ * target g is ascii[offs[g] .. offs[g+1]).  Total length < 2^32 - 4096 bases per call
+ * (shard larger databases by target range).  Uploads and 2-bit packs on the device. */
+int msc_set_targets(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint64_t n_targets);
+
+/* Re-run the device-side pack/build from the resident ASCII copies (keep_ascii=1);
+ * what: 1 = reads (+ key table), 2 = targets, 3 = both.  Used to time the hot path
+ * with inputs already in HBM. */
+int msc_rebuild(msc_ctx* ctx, int what);
+
+/* Streaming scan of the packed targets against the key table, compacting
+ * (key group, target position) candidates: replaces search/processSeq/checkWin/harvest
+ * (cmd/muscato_screen/main.go:220-480). */
+int msc_screen(msc_ctx* ctx);
+
+/* Expand candidates x reads of the key group into pairs (replaces sortBloom,
+ * cmd/muscato/main.go:318-385, and the merge join cmd/muscato_confirm/main.go:375-416),
+ * count mismatches, apply the fit / mismatch rules and MaxMatches
+ * (searchpairs, cmd/muscato_confirm/main.go:171-250, 424-448), de-duplicate across
+ * windows (sort -u, cmd/muscato/main.go:453-463).  Leaves per-read best mismatch
+ * counts in a device array (msc_best_device). */
+int msc_confirm(msc_ctx* ctx);
+
+/* Device pointer to uint32 best_nx[n_reads] (MSC_NO_MATCH = no match; positive as int32
+ * too, so a signed MIN works) valid between msc_confirm and msc_combine.  With targets
+ * sharded over several GPUs the host min-all-reduces this array across ranks (NCCL)
+ * before msc_combine. */
+#define MSC_NO_MATCH 0x7F7F7F7Fu
+void* msc_best_device(msc_ctx* ctx);
+
+/* Keep matches with nx <= best[read] + MMTol and group them by read:
+ * replaces writebest (cmd/muscato_combine_windows/main.go:36-60). */
+int msc_combine(msc_ctx* ctx);
+
+/* Device pointer to the n surviving matches (msc_match layout, grouped by read_id) left by
+ * msc_combine; valid until the next call that changes the context.  Lets the host gather
+ * the compacted matches of all ranks over NCCL without a host round trip. */
+void* msc_matches_device(msc_ctx* ctx, uint64_t* n);
+
+/* Copy the surviving matches to the host, ordered by (read_id, gene_id, pos).
+ * *out is owned by the library: release with msc_free. */
+int msc_fetch_matches(msc_ctx* ctx, msc_match** out, uint64_t* n);
+
+/* Convenience: msc_screen + msc_confirm + msc_combine. */
+int msc_run(msc_ctx* ctx);
+
+int msc_get_stats(const msc_ctx* ctx, msc_stats* out);
+void msc_reset_stats(msc_ctx* ctx);
+void msc_free(void* p);
+
+/* Parity-debugging taps (SURVEY.md App. B checkpoints).  Each returns a library-owned
+ * array released with msc_free.
+ *   msc_dump_keys: every valid (window, read) key the table holds -- the content of
+ *     win_<k>_sorted (cmd/muscato_window_reads/main.go:120-126) as (window, read_id) pairs.
+ *   msc_dump_candidates: (gene_id, window start p, read_id, window) for every candidate x
+ *     group member whose window k-mer matches exactly -- smatch_<k> joined with
+ *     win_<k>_sorted on the k-mer (cmd/muscato_confirm/main.go:382-393), before the fit
+ *     and mismatch rules. */
+typedef struct msc_key_rec { uint32_t window; uint32_t read_id; } msc_key_rec;
+typedef struct msc_cand_rec { uint32_t gene_id; uint32_t p; uint32_t read_id; uint32_t window; } msc_cand_rec;
+int msc_dump_keys(msc_ctx* ctx, msc_key_rec** out, uint64_t* n);
+int msc_dump_candidates(msc_ctx* ctx, msc_cand_rec** out, uint64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUSCATO_B200_H */

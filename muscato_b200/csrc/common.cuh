@@ -1,0 +1,134 @@
+// common.cuh -- shared device helpers for the muscato_b200 hot path (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace msc {
+
+// ---------------------------------------------------------------------------
+// 2-bit sequence layout.
+//   base i of a stream lives in 64-bit word i>>5 at bits [2*(i&31), 2*(i&31)+2).
+//   codes: A=0 C=1 T=2 G=3 ((ascii>>1)&3); any other byte is "X": code 0 plus a bit in
+//   the X plane, which uses the same spacing (bit 2*(i&31) of word i>>5) so that the
+//   same funnel shifts apply to both planes.
+// ---------------------------------------------------------------------------
+constexpr uint64_t kEvenBits = 0x5555555555555555ull;
+
+__host__ __device__ __forceinline__ uint64_t low_bases_mask(int n) {  // n in [0,32]
+  return n >= 32 ? ~0ull : ((1ull << (2 * n)) - 1ull);
+}
+
+// 32 bases starting at base index `base` (reads word wi and wi+1: buffers are padded).
+__device__ __forceinline__ uint64_t extract32(const uint64_t* __restrict__ w, uint64_t base) {
+  const uint64_t wi = base >> 5;
+  const unsigned sh = (unsigned)(base & 31u) * 2u;
+  const uint64_t lo = __ldg(w + wi);
+  if (sh == 0) return lo;
+  const uint64_t hi = __ldg(w + wi + 1);
+  return (lo >> sh) | (hi << (64u - sh));
+}
+
+// ---------------------------------------------------------------------------
+// Window-key fingerprint.  A W<=32 window is 2W bits (key) plus its X mask (xm, same
+// spacing).  fp is a bijective mix of key when xm==0; windows containing X fold the
+// mask in.  fp only has to be free of false negatives: the confirm kernel re-checks
+// the window bases exactly (cmd/muscato_confirm/main.go:382-393 requires byte equality).
+// fp==0 is reserved for "empty slot".
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t fmix64(uint64_t z) {
+  z ^= z >> 33;
+  z *= 0xff51afd7ed558ccdull;
+  z ^= z >> 33;
+  z *= 0xc4ceb9fe1a85ec53ull;
+  z ^= z >> 33;
+  return z;
+}
+
+__host__ __device__ __forceinline__ uint64_t key_fp(uint64_t key, uint64_t xm) {
+  uint64_t z = fmix64((key ^ (xm * 0xD6E8FEB86659FD93ull)) + 0x9E3779B97F4A7C15ull);
+  return z ? z : 1ull;
+}
+
+// Blocked Bloom front: one 64-bit word per key (a single 8-byte load per probed target
+// position), 2 bits in each 32-bit half.
+__host__ __device__ __forceinline__ uint32_t bloom_mask_lo(uint64_t fp) {
+  return (1u << (unsigned)(fp & 31u)) | (1u << (unsigned)((fp >> 5) & 31u));
+}
+__host__ __device__ __forceinline__ uint32_t bloom_mask_hi(uint64_t fp) {
+  return (1u << (unsigned)((fp >> 10) & 31u)) | (1u << (unsigned)((fp >> 15) & 31u));
+}
+__host__ __device__ __forceinline__ uint64_t bloom_index(uint64_t fp, int lg_words) {
+  return fp >> (64 - lg_words);
+}
+__host__ __device__ __forceinline__ uint64_t table_home(uint64_t fp, int lg_slots) {
+  return (fp * 0x9E3779B97F4A7C15ull) >> (64 - lg_slots);
+}
+
+// Open-addressing lookup (linear probing).  Returns slot or -1.
+__device__ __forceinline__ int64_t table_find(const uint64_t* __restrict__ tab_fp, int lg_slots, uint64_t fp) {
+  const uint64_t mask = (1ull << lg_slots) - 1ull;
+  uint64_t s = table_home(fp, lg_slots);
+  while (true) {
+    const uint64_t cur = __ldg(tab_fp + s);
+    if (cur == fp) return (int64_t)s;
+    if (cur == 0) return -1;
+    s = (s + 1) & mask;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// PTX wrappers: mbarrier + 1-D bulk async copy (TMA engine; SASS: UBLKCP / SYNCS).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Warp-aggregated append: every calling lane (any divergent subset) reserves one slot.
+__device__ __forceinline__ unsigned long long warp_agg_inc(unsigned long long* counter) {
+  const unsigned active = __activemask();
+  const int leader = __ffs(active) - 1;
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned long long base = 0;
+  if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(active));
+  base = __shfl_sync(active, base, leader);
+  return base + (unsigned long long)__popc(active & ((1u << lane) - 1u));
+}
+
+// First index i in [lo, hi) with a[i] > v  (a ascending).
+template <typename T>
+__device__ __forceinline__ uint64_t upper_bound_dev(const T* __restrict__ a, uint64_t lo, uint64_t hi, T v) {
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) <= v) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+}  // namespace msc

@@ -1,0 +1,190 @@
+// confirm.cuh -- kernels (3) and (4): segmented expansion of candidates into
+// (candidate, read) pairs and the XOR+popcount confirm.
+//
+// (3) replaces sortBloom (cmd/muscato/main.go:318-385) and the merge join of
+//     cmd/muscato_confirm/main.go:375-416: every candidate already carries its key-group
+//     (table slot), so grouping is a prefix sum over the group sizes; pair i is located by
+//     a binary search in that prefix array (load-balanced: one thread per pair, however
+//     skewed the groups are).
+// (4) replaces searchpairs/cdiff (cmd/muscato_confirm/main.go:151-250): full-read mismatch
+//     count on packed words, the fit rule (:200-203), the position-0 rule of the screen
+//     (cmd/muscato_screen/main.go:294-316, the literal 100), nmiss = int((1-PMatch)*L) from a
+//     host-computed float64 table (:198), and exact cross-window de-duplication (the
+//     `sort -u` of cmd/muscato/main.go:453-463): a pair is emitted only through the lowest
+//     window index that delivers it.
+#pragma once
+#include "build.cuh"
+#include "common.cuh"
+
+namespace msc {
+
+__global__ void __launch_bounds__(256) cand_sizes_kernel(const uint2* __restrict__ cand, uint64_t n_cand,
+                                                         const uint32_t* __restrict__ tab_cnt,
+                                                         uint32_t* __restrict__ sizes) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_cand) sizes[i] = __ldg(tab_cnt + cand[i].x);
+}
+
+struct ConfirmArgs {
+  // candidates and their pair prefix
+  const uint2* cand;
+  const uint64_t* pstart;  // n_cand + 1
+  uint64_t n_cand;
+  uint64_t n_pairs;
+  // key table
+  const uint32_t* tab_start;
+  const uint32_t* items;
+  uint32_t* pass_cnt;  // per slot: pairs that passed (MaxMatches pre-check)
+  // reads
+  const uint64_t* rd_words;
+  const uint64_t* rd_x;
+  const uint32_t* len_flags;
+  const uint32_t* validmask;
+  // targets
+  const uint64_t* tg_words;
+  const uint64_t* tg_x;
+  const uint32_t* xsum;
+  const uint32_t* tg_off;  // n_targets + 1 (base offsets in the concatenated stream)
+  uint64_t n_targets;
+  // rules
+  const int32_t* nmiss;  // [MRL + 1]
+  // outputs
+  uint4* matches;  // (read, gene, pos, nx)
+  unsigned long long match_cap;
+  unsigned long long* n_match;
+  unsigned long long* n_pass;
+  uint32_t* best;  // per read min nx
+  int mode;        // 0 = confirm, 1 = dump exact-key candidates as (gene, p, read, window)
+};
+
+__device__ __forceinline__ bool tg_range_has_x(const uint32_t* __restrict__ xsum, uint64_t w0, uint64_t w1) {
+  // any X summary bit set for words w0..w1 (inclusive)
+  for (uint64_t u = w0 >> 5; u <= (w1 >> 5); u++) {
+    uint32_t v = __ldg(xsum + u);
+    if (!v) continue;
+    const uint64_t lo = u << 5;
+    if (w0 > lo) v &= ~0u << (unsigned)(w0 - lo);
+    if (w1 < lo + 31) v &= ~0u >> (unsigned)(lo + 31 - w1);
+    if (v) return true;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(256) confirm_pairs_kernel(const WinCfg cfg, const ConfirmArgs a) {
+  __shared__ uint64_t s_clo, s_chi;
+  const uint64_t first = (uint64_t)blockIdx.x * blockDim.x;
+  if (threadIdx.x == 0) {
+    const uint64_t last = min(first + blockDim.x, a.n_pairs) - 1;
+    s_clo = upper_bound_dev<uint64_t>(a.pstart, 0, a.n_cand, first) - 1;
+    s_chi = upper_bound_dev<uint64_t>(a.pstart, 0, a.n_cand, last) - 1;
+  }
+  __syncthreads();
+  const uint64_t i = first + threadIdx.x;
+  if (i >= a.n_pairs) return;
+  const uint64_t c = upper_bound_dev<uint64_t>(a.pstart, s_clo, s_chi + 1, i) - 1;
+  const uint2 cd = __ldg(a.cand + c);
+  const uint32_t slot = cd.x;
+  const uint64_t gpos = cd.y;
+  const uint32_t item = __ldg(a.items + __ldg(a.tab_start + slot) + (uint32_t)(i - __ldg(a.pstart + c)));
+  const uint32_t r = item / (uint32_t)cfg.nwin;
+  const int k = (int)(item - r * (uint32_t)cfg.nwin);
+  const int W = cfg.W;
+  const int q1 = cfg.windows[k], q2 = q1 + W;
+
+  // Gene of this candidate and window start p inside it.
+  const uint64_t g = upper_bound_dev<uint32_t>(a.tg_off, 0, a.n_targets + 1, (uint32_t)gpos) - 1;
+  const uint32_t goff = __ldg(a.tg_off + g);
+  const int64_t glen = (int64_t)__ldg(a.tg_off + g + 1) - (int64_t)goff;
+  const int64_t p = (int64_t)gpos - (int64_t)goff;
+  if (p + W > glen) return;        // the W-mer straddles a target boundary: not a window of any target
+  const int64_t pos = p - q1;      // jw = jx - q1 >= 0 (cmd/muscato_screen/main.go:345, :355)
+  if (pos < 0) return;
+
+  const uint32_t lf = __ldg(a.len_flags + r);
+  const int L = (int)(lf & 0x7fffffffu);
+  const bool rx = lf >> 31;
+  const uint64_t* row = a.rd_words + (uint64_t)r * cfg.S;
+  const uint64_t* xrow = a.rd_x + (uint64_t)r * cfg.S;
+  const uint64_t kmask = low_bases_mask(W);
+  const uint64_t gstart = gpos - (uint64_t)q1;  // global base index of the read's first base
+  const bool tx = tg_range_has_x(a.xsum, gstart >> 5, ((gstart + (uint64_t)L) >> 5) + 1);
+  const bool anyx = rx | tx;
+
+  // Exact key equality for the window that produced this pair (merge join on the k-mer bytes,
+  // cmd/muscato_confirm/main.go:382-393): rejects fingerprint collisions.
+  {
+    const uint64_t rk = extract32(row, (uint64_t)q1) & kmask;
+    const uint64_t tk = extract32(a.tg_words, gpos) & kmask;
+    if (rk != tk) return;
+    if (anyx) {
+      const uint64_t rxm = rx ? (extract32(xrow, (uint64_t)q1) & kmask) : 0ull;
+      const uint64_t txm = tx ? (extract32(a.tg_x, gpos) & kmask) : 0ull;
+      if (rxm != txm) return;
+    }
+  }
+  if (a.mode == 1) {
+    const unsigned long long at = warp_agg_inc(a.n_match);
+    if (at < a.match_cap) a.matches[at] = make_uint4((uint32_t)g, (uint32_t)p, r, (uint32_t)k);
+    return;
+  }
+
+  // Fit rule (cmd/muscato_confirm/main.go:200-203) on the candidate's clipped right tail.
+  const int64_t lim0 = min((int64_t)(100 - W), glen);  // position-0 record: right = t[W : min(100-q2, len)]
+  if (p == 0) {
+    if ((int64_t)L > lim0) return;  // len(srgt) = L - W <= min(100 - W, len) - W
+  } else {
+    const int64_t mr = min(p + W + (int64_t)cfg.MRL - q2, glen) - (p + W);
+    if ((int64_t)(L - q2) > mr) return;
+  }
+
+  // Full-read mismatch count: nx = cdiff(left tails) + cdiff(right tails) (+0 inside the window).
+  int nx = 0;
+  const int nwords = (L + 31) >> 5;
+  for (int w = 0; w < nwords; w++) {
+    const uint64_t ra = __ldg(row + w);
+    const uint64_t tb = extract32(a.tg_words, gstart + 32ull * w);
+    uint64_t x = ra ^ tb;
+    uint64_t m = (x | (x >> 1)) & kEvenBits;
+    if (anyx) {
+      const uint64_t xa = rx ? __ldg(xrow + w) : 0ull;
+      const uint64_t xb = tx ? extract32(a.tg_x, gstart + 32ull * w) : 0ull;
+      m = (m & ~(xa | xb)) | (xa ^ xb);  // X==X matches, X vs base mismatches (cdiff compares bytes)
+    }
+    m &= low_bases_mask(min(32, L - 32 * w));
+    nx += __popcll(m);
+  }
+  if (nx > __ldg(a.nmiss + L)) return;
+
+  // The pair passes through window k.
+  atomicAdd(a.pass_cnt + slot, 1u);
+  {
+    const unsigned long long np = warp_agg_inc(a.n_pass);
+    (void)np;
+  }
+
+  // Cross-window de-duplication: emit only through the lowest window index that delivers
+  // this (read, gene, pos).  Window k' delivers it iff it is valid for the read, its k-mer
+  // matches exactly, and -- when it would sit at target position 0 -- the literal-100 rule holds.
+  uint32_t vm = __ldg(a.validmask + r) & ((1u << k) - 1u);
+  while (vm) {
+    const int k2 = __ffs(vm) - 1;
+    vm &= vm - 1;
+    const int q1b = cfg.windows[k2];
+    if (pos + q1b == 0 && (int64_t)L > lim0) continue;
+    const uint64_t rk = extract32(row, (uint64_t)q1b) & kmask;
+    const uint64_t tk = extract32(a.tg_words, gstart + (uint64_t)q1b) & kmask;
+    if (rk != tk) continue;
+    if (anyx) {
+      const uint64_t rxm = rx ? (extract32(xrow, (uint64_t)q1b) & kmask) : 0ull;
+      const uint64_t txm = tx ? (extract32(a.tg_x, gstart + (uint64_t)q1b) & kmask) : 0ull;
+      if (rxm != txm) continue;
+    }
+    return;  // an earlier window owns this pair
+  }
+
+  atomicMin(a.best + r, (uint32_t)nx);
+  const unsigned long long at = warp_agg_inc(a.n_match);
+  if (at < a.match_cap) a.matches[at] = make_uint4(r, (uint32_t)g, (uint32_t)pos, (uint32_t)nx);
+}
+
+}  // namespace msc

@@ -1,0 +1,172 @@
+"""Host-side handle on the CUDA hot path: a thin object over the C ABI
+(include/muscato_b200.h).  All computation happens in libmuscato_b200.so on the GPU."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _capi
+from .config import Config
+
+MATCH_DTYPE = np.dtype([("read_id", "<u4"), ("gene_id", "<u4"), ("pos", "<u4"), ("nx", "<u4")])
+KEY_DTYPE = np.dtype([("window", "<u4"), ("read_id", "<u4")])
+CAND_DTYPE = np.dtype([("gene_id", "<u4"), ("p", "<u4"), ("read_id", "<u4"), ("window", "<u4")])
+
+SeqInput = Union[Sequence[bytes], Tuple[np.ndarray, np.ndarray]]
+
+
+class MuscatoError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"muscato_b200 error {code}: {msg}")
+        self.code = code
+
+
+def concat_sequences(seqs: Iterable[bytes]) -> Tuple[np.ndarray, np.ndarray]:
+    """list of byte strings -> (ascii uint8 array, uint64 offsets[n+1])."""
+    seqs = list(seqs)
+    offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    if seqs:
+        offs[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+    ascii_ = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    return ascii_, offs
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ holder so torch can view a library-owned device buffer."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class HotPath:
+    def __init__(self, cfg: Config, device: int = 0, keep_ascii: bool = False, bloom_bits_per_key: int = 0):
+        self._lib = _capi.load()
+        self.cfg = cfg
+        mc = cfg.to_msc(device=device, keep_ascii=keep_ascii, bloom_bits_per_key=bloom_bits_per_key)
+        err = C.create_string_buffer(512)
+        self._ctx = self._lib.msc_create(C.byref(mc), err, 512)
+        if not self._ctx:
+            raise MuscatoError(-1, err.value.decode(errors="replace"))
+        self.n_reads = 0
+        self.n_targets = 0
+        self._keep = []
+
+    # -- lifecycle -------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.msc_destroy(self._ctx)
+            self._ctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise MuscatoError(rc, self._lib.msc_last_error(self._ctx).decode(errors="replace"))
+
+    @staticmethod
+    def _as_arrays(seqs: SeqInput) -> Tuple[np.ndarray, np.ndarray]:
+        if isinstance(seqs, tuple) and len(seqs) == 2 and isinstance(seqs[0], np.ndarray):
+            a, o = seqs
+            return np.ascontiguousarray(a, dtype=np.uint8), np.ascontiguousarray(o, dtype=np.uint64)
+        return concat_sequences(seqs)
+
+    # -- the path -------------------------------------------------------------------
+    def set_reads(self, seqs: SeqInput):
+        a, o = self._as_arrays(seqs)
+        self.n_reads = len(o) - 1
+        self._check(self._lib.msc_set_reads(self._ctx, a.ctypes.data, o.ctypes.data, self.n_reads))
+
+    def set_targets(self, seqs: SeqInput):
+        a, o = self._as_arrays(seqs)
+        self.n_targets = len(o) - 1
+        self._check(self._lib.msc_set_targets(self._ctx, a.ctypes.data, o.ctypes.data, self.n_targets))
+
+    def set_reads_ptr(self, ascii_ptr: int, offs_ptr: int, n: int):
+        """Raw-pointer variant (e.g. pinned host buffers owned by the caller)."""
+        self.n_reads = n
+        self._check(self._lib.msc_set_reads(self._ctx, ascii_ptr, offs_ptr, n))
+
+    def set_targets_ptr(self, ascii_ptr: int, offs_ptr: int, n: int):
+        self.n_targets = n
+        self._check(self._lib.msc_set_targets(self._ctx, ascii_ptr, offs_ptr, n))
+
+    def rebuild(self, what: int = 3):
+        self._check(self._lib.msc_rebuild(self._ctx, what))
+
+    def screen(self):
+        self._check(self._lib.msc_screen(self._ctx))
+
+    def confirm(self):
+        self._check(self._lib.msc_confirm(self._ctx))
+
+    def combine(self):
+        self._check(self._lib.msc_combine(self._ctx))
+
+    def run(self):
+        self._check(self._lib.msc_run(self._ctx))
+
+    def best_device(self) -> _DevArray:
+        ptr = self._lib.msc_best_device(self._ctx)
+        if not ptr:
+            raise MuscatoError(_capi.MSC_ERR_STATE, "best array not available (run confirm first)")
+        return _DevArray(ptr, self.n_reads, "<i4")
+
+    def matches_device(self):
+        """(holder, n): device view of the combined matches as int32[n*4] (read, gene, pos, nx)."""
+        n = C.c_uint64(0)
+        ptr = self._lib.msc_matches_device(self._ctx, C.byref(n))
+        if not ptr:
+            raise MuscatoError(_capi.MSC_ERR_STATE, "matches not available (run combine first)")
+        return _DevArray(ptr, int(n.value) * 4, "<i4"), int(n.value)
+
+    def fetch(self) -> np.ndarray:
+        out = C.POINTER(_capi.msc_match)()
+        n = C.c_uint64(0)
+        self._check(self._lib.msc_fetch_matches(self._ctx, C.byref(out), C.byref(n)))
+        try:
+            if n.value == 0:
+                return np.zeros(0, dtype=MATCH_DTYPE)
+            buf = C.string_at(out, n.value * C.sizeof(_capi.msc_match))
+            return np.frombuffer(buf, dtype=MATCH_DTYPE).copy()
+        finally:
+            self._lib.msc_free(out)
+
+    def dump_keys(self) -> np.ndarray:
+        out = C.POINTER(_capi.msc_key_rec)()
+        n = C.c_uint64(0)
+        self._check(self._lib.msc_dump_keys(self._ctx, C.byref(out), C.byref(n)))
+        try:
+            buf = C.string_at(out, n.value * C.sizeof(_capi.msc_key_rec)) if n.value else b""
+            return np.frombuffer(buf, dtype=KEY_DTYPE).copy()
+        finally:
+            self._lib.msc_free(out)
+
+    def dump_candidates(self) -> np.ndarray:
+        out = C.POINTER(_capi.msc_cand_rec)()
+        n = C.c_uint64(0)
+        self._check(self._lib.msc_dump_candidates(self._ctx, C.byref(out), C.byref(n)))
+        try:
+            buf = C.string_at(out, n.value * C.sizeof(_capi.msc_cand_rec)) if n.value else b""
+            return np.frombuffer(buf, dtype=CAND_DTYPE).copy()
+        finally:
+            self._lib.msc_free(out)
+
+    def stats(self) -> dict:
+        st = _capi.msc_stats()
+        self._check(self._lib.msc_get_stats(self._ctx, C.byref(st)))
+        return st.as_dict()
+
+    def reset_stats(self):
+        self._lib.msc_reset_stats(self._ctx)

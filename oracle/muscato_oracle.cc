@@ -30,6 +30,7 @@
 //   prep_targets [-rev] <in.txt|in.fasta> <seq_out> <ids_out>
 //   pipeline <config.json>     whole muscato run (steps 1..12 of cmd/muscato/main.go:1005-1058)
 //   upstream <config.json>     prepReads + windowReads + sortWindows only
+//   windows  <config.json>     windowReads + sortWindows on an existing TempDir/reads_sorted.txt
 //   hotpath  <config.json>     screen + sortBloom + confirm + combineWindows only (timed)
 //   epilogue <config.json>     sortByGeneId + joinGeneNames + joinReadNames + nonmatch
 #include <algorithm>
@@ -522,7 +523,7 @@ struct Screen {
   const Config& c;
   int nh, W;
   std::vector<std::vector<uint32_t>> tables;  // genTables :86-101
-  std::vector<std::vector<uint64_t>> smp;     // one bit array per window :549-552
+  std::vector<uint64_t*> smp;                 // one bit array per window :549-552 (calloc: lazily zeroed pages, like Go's make)
   std::vector<FILE*> outs;                    // bmatch_k (harvest :369-403)
   std::vector<std::mutex> out_mu;
   std::atomic<uint64_t> bases{0}, recs{0};
@@ -546,8 +547,13 @@ struct Screen {
         }
       }
     }
-    smp.assign(c.Windows.size(), std::vector<uint64_t>((c.BloomSize + 63) / 64, 0));
+    for (size_t k = 0; k < c.Windows.size(); k++) {
+      uint64_t* p = (uint64_t*)calloc((c.BloomSize + 63) / 64 + 1, sizeof(uint64_t));
+      if (!p) die("cannot allocate Bloom bit array");
+      smp.push_back(p);
+    }
   }
+  ~Screen() { for (auto* p : smp) free(p); }
 
   static inline uint32_t rotl(uint32_t x, unsigned r) { r &= 31; return r ? (x << r) | (x >> (32 - r)) : x; }
 
@@ -563,21 +569,26 @@ struct Screen {
   }
   bool get_bit(size_t k, uint64_t x) const { return (smp[k][x >> 6] >> (x & 63)) & 1; }
 
-  // buildBloom :116-207
+  // buildBloom :116-207.  The reference feeds one worker goroutine per window (:136-162); here the
+  // read scan is done once per window thread, which sets the same bits.
   void build_bloom() {
-    LineReader rd(tmp(c, "reads_sorted.txt"));
-    std::string line;
-    while (rd.next(line)) {
-      auto f = fields(line);
-      const std::string& seq = f[0];
-      for (size_t k = 0; k < c.Windows.size(); k++) {
-        int q1 = c.Windows[k], q2 = q1 + W;
-        if (q2 > (int)seq.size()) continue;                               // :177-179
-        if (count_dinuc(seq.data() + q1, W) < c.MinDinuc) continue;       // :183-185
-        for (int j = 0; j < nh; j++)                                      // :150-159
-          set_bit(k, (uint64_t)hash_full(j, seq.data() + q1, W) % c.BloomSize);
-      }
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < c.Windows.size(); k++) {
+      th.emplace_back([this, k] {
+        LineReader rd(tmp(c, "reads_sorted.txt"));
+        std::string line;
+        const int q1 = c.Windows[k], q2 = q1 + W;
+        while (rd.next(line)) {
+          size_t e = 0;
+          while (e < line.size() && !is_space(line[e])) e++;  // bytes.Fields(line)[0] :172
+          if (q2 > (int)e) continue;                                      // :177-179
+          if (count_dinuc(line.data() + q1, W) < c.MinDinuc) continue;    // :183-185
+          for (int j = 0; j < nh; j++)                                    // :150-159
+            set_bit(k, (uint64_t)hash_full(j, line.data() + q1, W) % c.BloomSize);
+        }
+      });
     }
+    for (auto& t : th) t.join();
   }
 
   // checkWin :220-253
@@ -1023,6 +1034,9 @@ int main(int argc, char** argv) {
     nonmatch(c);
   } else if (cmd == "upstream") {
     upstream(c);
+  } else if (cmd == "windows") {  // windowReads + sortWindows on an existing TempDir/reads_sorted.txt
+    window_reads(c);
+    sort_windows(c);
   } else if (cmd == "hotpath") {
     hotpath(c, true);
   } else if (cmd == "epilogue") {

@@ -1,0 +1,118 @@
+"""Test-side helpers: building and running the CPU oracle (oracle/ is test infrastructure and
+is only ever touched from tests/, smoke() and bench.py's baseline legs)."""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+from typing import Dict, List, Optional
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_BIN = os.path.join(ORACLE_DIR, "_build", "muscato_oracle")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def build_oracle() -> str:
+    src = os.path.join(ORACLE_DIR, "muscato_oracle.cc")
+    if not os.path.exists(ORACLE_BIN) or os.path.getmtime(ORACLE_BIN) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
+    return ORACLE_BIN
+
+
+def run_oracle(args: List[str], **kw) -> subprocess.CompletedProcess:
+    return subprocess.run([build_oracle()] + args, capture_output=True, text=True, **kw)
+
+
+def oracle_prep_targets(src: str, seq_out: str, ids_out: str, rev: bool = False) -> None:
+    a = ["prep_targets"] + (["-rev"] if rev else []) + [src, seq_out, ids_out]
+    r = run_oracle(a)
+    assert r.returncode == 0, r.stderr
+
+
+def oracle_pipeline(workdir: str, fastq: str, genes_seq: str, genes_ids: str, cfg: Dict,
+                    sub: str = "pipeline") -> Dict[str, str]:
+    """Run the oracle on prepared targets; returns paths of its outputs."""
+    tmp = os.path.join(workdir, "tmp")
+    os.makedirs(tmp, exist_ok=True)
+    c = dict(cfg)
+    c.update(ReadFileName=fastq, GeneFileName=genes_seq, GeneIdFileName=genes_ids,
+             ResultsFileName=os.path.join(workdir, "result.txt"), TempDir=tmp, SortPar=2, SortMem="5%")
+    c.setdefault("Threads", 4)
+    cpath = os.path.join(workdir, "oracle_config.json")
+    with open(cpath, "w") as f:
+        json.dump(c, f)
+    r = run_oracle([sub, cpath])
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    return {
+        "config": cpath,
+        "tmp": tmp,
+        "results": c["ResultsFileName"],
+        "nonmatch": os.path.join(workdir, "result.nonmatch.txt.fastq"),
+        "matches": os.path.join(tmp, "matches.txt"),
+        "reads_sorted": os.path.join(tmp, "reads_sorted.txt"),
+        "stdout": r.stdout,
+    }
+
+
+def read_bytes(path: str) -> bytes:
+    with open(path, "rb") as f:
+        return f.read()
+
+
+def read_lines(path: str) -> List[bytes]:
+    d = read_bytes(path)
+    lines = d.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    return lines
+
+
+def oracle_window_keys(tmp: str, reads: List[bytes], k: int) -> set:
+    """win_<k>_sorted lines mapped back to read ids: {(k, read_id)}."""
+    idx = {r: i for i, r in enumerate(reads)}
+    out = set()
+    for ln in read_lines(os.path.join(tmp, f"win_{k}_sorted.txt")):
+        key, left, right = ln.split(b"\t")
+        out.add((k, idx[left + key + right]))
+    return out
+
+
+def oracle_candidates(tmp: str, k: int) -> set:
+    """{(k, gene, p)} for smatch_<k> lines whose k-mer is a key of win_<k>_sorted
+    (the merge join of cmd/muscato_confirm/main.go:375-416 drops every other line)."""
+    keys = {ln.split(b"\t")[0] for ln in read_lines(os.path.join(tmp, f"win_{k}_sorted.txt"))}
+    out = set()
+    for ln in read_lines(os.path.join(tmp, f"smatch_{k}.txt")):
+        f = ln.split(b"\t")
+        if f[0] in keys:
+            out.add((k, int(f[3]), int(f[4])))
+    return out
+
+
+def random_dna(rng: np.random.Generator, n: int, alphabet: bytes = b"ACGT") -> bytes:
+    a = np.frombuffer(alphabet, dtype=np.uint8)
+    return a[rng.integers(0, len(a), size=n)].tobytes()
+
+
+def write_case(workdir: str, raw_reads: List[bytes], names: Optional[List[bytes]], genes: List[bytes],
+               gene_names: Optional[List[bytes]] = None):
+    """Write reads.fastq + prepped target files (plain text) for the oracle."""
+    os.makedirs(workdir, exist_ok=True)
+    fq = os.path.join(workdir, "reads.fastq")
+    with open(fq, "wb") as f:
+        for i, r in enumerate(raw_reads):
+            nm = names[i] if names else b"@read_%d" % i
+            f.write(nm + b"\n" + r + b"\n+\n" + b"F" * len(r) + b"\n")
+    gs = os.path.join(workdir, "genes_seq.txt")
+    gi = os.path.join(workdir, "genes_ids.txt")
+    with open(gs, "wb") as f:
+        for g in genes:
+            f.write(g + b"\n")
+    with open(gi, "wb") as f:
+        for i, g in enumerate(genes):
+            nm = gene_names[i] if gene_names else b"gene_%d" % i
+            f.write(b"%011d\t%s\t%d\n" % (i, nm, len(g)))
+    return fq, gs, gi

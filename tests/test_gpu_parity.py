@@ -1,0 +1,230 @@
+"""Parity tests proper: the CUDA hot path (through the C ABI) against the CPU oracle and the
+reference's golden fixtures.  Integer/byte work: the bar is bit-exact."""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from muscato_b200 import formats, gendat
+from muscato_b200.config import Config
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(cfg: Config, **kw):
+    from muscato_b200.engine import HotPath
+    return HotPath(cfg, device=0, **kw)
+
+
+def run_cuda(cfg: Config, reads, targets, taps=False):
+    with _engine(cfg) as hp:
+        hp.set_reads(reads)
+        hp.set_targets(targets)
+        hp.screen()
+        keys = cands = None
+        if taps:
+            keys = hp.dump_keys()
+            cands = hp.dump_candidates()
+        hp.confirm()
+        hp.combine()
+        m = hp.fetch()
+        st = hp.stats()
+    return m, st, keys, cands
+
+
+def check_against_oracle(tmp_path, raw_reads, names, genes, cfgd, gene_names=None, taps=True):
+    """Full comparison of one case: window keys, candidates, matches.txt, results.txt, non-match fastq."""
+    work = str(tmp_path)
+    fq, gs, gi = helpers.write_case(work, raw_reads, names, genes, gene_names)
+    out = helpers.oracle_pipeline(work, fq, gs, gi, cfgd)
+    cfg = Config(**{k: v for k, v in cfgd.items() if k in Config.__dataclass_fields__}).apply_defaults()
+    seqs, counts, rnames = formats.prep_reads_uniqify(helpers.read_bytes(fq), cfg.MinReadLength, cfg.MaxReadLength)
+    # host mirror of prepReads must agree with the oracle's reads_sorted
+    o_seqs, o_counts, o_names = formats.load_reads_sorted(out["reads_sorted"])
+    assert (seqs, counts, rnames) == (o_seqs, o_counts, o_names)
+    targets = formats.load_targets(gs)
+    gnames, glens = formats.load_gene_ids(gi)
+    m, st, keys, cands = run_cuda(cfg, seqs, targets, taps=taps)
+    if taps:
+        want_keys = set()
+        want_cands = set()
+        for k in range(len(cfg.Windows)):
+            want_keys |= helpers.oracle_window_keys(out["tmp"], seqs, k)
+            want_cands |= helpers.oracle_candidates(out["tmp"], k)
+        got_keys = {(int(r["window"]), int(r["read_id"])) for r in keys}
+        assert got_keys == want_keys
+        got_cands = {(int(r["window"]), int(r["gene_id"]), int(r["p"])) for r in cands}
+        assert got_cands == want_cands
+    assert formats.matches_lines(m, seqs, targets) == helpers.read_lines(out["matches"])
+    res = b"".join(ln + b"\n" for ln in formats.results_lines(m, seqs, counts, rnames, targets, gnames, glens))
+    assert res == helpers.read_bytes(out["results"])
+    assert formats.nonmatch_fastq(m, seqs, counts, rnames) == helpers.read_bytes(out["nonmatch"])
+    return m, st
+
+
+@pytest.mark.parametrize("case", ["00", "01", "02", "03", "04"])
+def test_golden_fixture_through_cuda(case, tmp_path, oracle_bin):
+    """tests/tests.toml "muscato 0..4" of the reference: result.txt and the non-match fastq, byte for byte."""
+    src = os.path.join(helpers.GOLDEN, "muscato", case)
+    cfgd = json.load(open(os.path.join(src, "config.json")))
+    seq, ids = str(tmp_path / "genes_seq.txt"), str(tmp_path / "genes_ids.txt")
+    helpers.oracle_prep_targets(os.path.join(src, "genes.txt"), seq, ids, rev=(case == "04"))
+    cfg = Config(**{k: v for k, v in cfgd.items() if k in Config.__dataclass_fields__}).apply_defaults()
+    seqs, counts, rnames = formats.prep_reads_uniqify(helpers.read_bytes(os.path.join(src, "reads.fastq")),
+                                                      cfg.MinReadLength, cfg.MaxReadLength)
+    targets = formats.load_targets(seq)
+    gnames, glens = formats.load_gene_ids(ids)
+    m, _, _, _ = run_cuda(cfg, seqs, targets)
+    res = b"".join(ln + b"\n" for ln in formats.results_lines(m, seqs, counts, rnames, targets, gnames, glens))
+    assert res == helpers.read_bytes(os.path.join(src, "result_e.txt"))
+    assert formats.nonmatch_fastq(m, seqs, counts, rnames) == helpers.read_bytes(os.path.join(src, "result.nonmatch_e.txt"))
+
+
+def _planted_case(rng, n_genes, gene_len, n_reads, read_lens, sub_rate, alphabet=b"ACGT", x_rate=0.0,
+                  dup_frac=0.1, edge_frac=0.2):
+    """Random genes; reads sampled from them (with substitutions), some from position 0 and the
+    target end, some duplicated, some pure noise."""
+    genes = [helpers.random_dna(rng, int(gl), alphabet) for gl in (gene_len if hasattr(gene_len, "__len__") else [gene_len] * n_genes)]
+    if x_rate > 0:
+        gs = []
+        for g in genes:
+            a = np.frombuffer(g, dtype=np.uint8).copy()
+            a[rng.random(len(a)) < x_rate] = ord("N")  # prep_targets would turn this into X
+            gs.append(bytes(a).replace(b"N", b"X"))
+        genes = gs
+    reads = []
+    for i in range(n_reads):
+        L = int(rng.choice(read_lens))
+        u = rng.random()
+        if u < 0.15:
+            reads.append(helpers.random_dna(rng, L, alphabet))
+            continue
+        g = genes[int(rng.integers(0, len(genes)))]
+        if len(g) < L:
+            reads.append(helpers.random_dna(rng, L, alphabet))
+            continue
+        v = rng.random()
+        if v < edge_frac / 2:
+            p = 0
+        elif v < edge_frac:
+            p = len(g) - L
+        else:
+            p = int(rng.integers(0, len(g) - L + 1))
+        a = np.frombuffer(g[p:p + L], dtype=np.uint8).copy()
+        mut = rng.random(L) < sub_rate
+        a[mut] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=int(mut.sum()))]
+        if x_rate > 0:
+            a[rng.random(L) < x_rate] = ord("N")
+        reads.append(bytes(a))
+    ndup = int(dup_frac * n_reads)
+    for _ in range(ndup):
+        reads.append(reads[int(rng.integers(0, len(reads)))])
+    return reads, genes
+
+
+CASES = [
+    # name, W, Windows, MRL, PMatch, MinDinuc, MMTol, read_lens, gene_len, sub_rate, x_rate
+    ("w4_exact", 4, [0, 5], 300, 1.0, 1, 1, [10, 12], 40, 0.0, 0.0),
+    ("w5_mm", 5, [0, 7, 14], 30, 0.9, 0, 0, [20, 24, 30], 80, 0.05, 0.0),
+    ("w8_mm_tol", 8, [0, 10, 20], 120, 0.93, 3, 2, [40, 60, 110], 300, 0.04, 0.0),
+    ("w15_q1", 15, [0, 20, 40], 100, 0.97, 5, 1, [100, 90, 85, 86], 400, 0.02, 0.0),   # L > 100-W at target position 0
+    ("w15_x", 15, [0, 20], 100, 0.95, 2, 1, [100, 64, 33], 300, 0.02, 0.02),           # X in reads and targets
+    ("w32_long", 32, [0, 40, 100], 200, 0.96, 4, 3, [200, 150, 133], 700, 0.02, 0.0),
+    ("w20_unsorted_windows", 20, [30, 0, 10, 10], 150, 0.98, 0, 0, [150, 64, 45], 500, 0.01, 0.0),
+    ("w7_lowcomplex", 7, [0, 7, 3], 64, 0.9, 0, 5, [64, 32, 21], 150, 0.03, 0.0),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_random_cases_vs_oracle(case, tmp_path, oracle_bin):
+    name, W, wins, mrl, pm, mind, mmtol, rlens, glen, sub, xr = case
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    alphabet = b"AC" if "lowcomplex" in name else b"ACGT"
+    n_genes = 30
+    glens = [glen] * (n_genes - 4) + [W - 1, W, W + 3, max(W + 1, 20)]  # targets shorter than / equal to W
+    reads, genes = _planted_case(rng, n_genes, glens, 300, rlens, sub, alphabet=alphabet, x_rate=xr)
+    cfgd = dict(Windows=wins, WindowWidth=W, MaxReadLength=mrl, PMatch=pm, MinDinuc=mind, MMTol=mmtol,
+                BloomSize=4000000, NumHash=8, MinReadLength=0, MaxMatches=1000000, MaxConfirmProcs=3, MatchMode="best")
+    m, st = check_against_oracle(tmp_path, reads, None, genes, cfgd)
+    if sub == 0.0 or pm < 1:
+        assert len(m) > 0
+
+
+def test_truncated_and_short_reads(tmp_path, oracle_bin):
+    """MaxReadLength truncation / MinReadLength skipping happen upstream (prep_reads) -- the host mirror
+    must feed the device exactly what the oracle's reads_sorted holds."""
+    rng = np.random.default_rng(11)
+    reads, genes = _planted_case(rng, 20, 200, 200, [30, 50, 80, 120], 0.02)
+    cfgd = dict(Windows=[0, 12, 25], WindowWidth=10, MaxReadLength=60, MinReadLength=40, PMatch=0.95, MinDinuc=2,
+                MMTol=1, BloomSize=2000000, NumHash=6, MaxMatches=1000000, MatchMode="best")
+    check_against_oracle(tmp_path, reads, None, genes, cfgd)
+
+
+def test_names_with_spaces_and_duplicates(tmp_path, oracle_bin):
+    rng = np.random.default_rng(5)
+    reads, genes = _planted_case(rng, 10, 120, 60, [40], 0.01, dup_frac=0.5)
+    names = [b"@SRR%d.%d some comment length=%d" % (i % 7, i, len(r)) for i, r in enumerate(reads)]
+    gnames = [b">chr%d description here" % i for i in range(len(genes))]
+    cfgd = dict(Windows=[0, 15], WindowWidth=12, MaxReadLength=40, PMatch=0.95, MinDinuc=0, MMTol=0,
+                BloomSize=1000000, NumHash=6, MaxMatches=1000000, MatchMode="best")
+    check_against_oracle(tmp_path, reads, names, genes, cfgd, gene_names=gnames)
+
+
+def test_gendat_medium_vs_oracle(tmp_path, oracle_bin):
+    """muscato_gendat-shaped data with the README flags (Windows=0,20 WindowWidth=15 MaxReadLength=100)."""
+    syn = gendat.generate(20000, 100, 400, 2000, seed=1, rev=True, mutated_fraction=0.5)
+    work = str(tmp_path)
+    fq, gs, gi = os.path.join(work, "reads.fastq"), os.path.join(work, "genes_seq.txt"), os.path.join(work, "genes_ids.txt")
+    gendat.write_oracle_inputs(syn, fq, gs, gi)
+    cfgd = dict(Windows=[0, 20], WindowWidth=15, MaxReadLength=100, PMatch=0.97, MinDinuc=5, MMTol=1,
+                BloomSize=40000000, NumHash=20, MaxMatches=1000000, MatchMode="best")
+    out = helpers.oracle_pipeline(work, fq, gs, gi, cfgd)
+    cfg = Config(**cfgd).apply_defaults()
+    seqs, counts, rnames = formats.load_reads_sorted(out["reads_sorted"])
+    assert seqs == syn.reads_list()
+    targets = syn.targets_list()
+    with _engine(cfg) as hp:
+        hp.set_reads((syn.read_ascii, syn.read_offs))
+        hp.set_targets((syn.target_ascii, syn.target_offs))
+        hp.run()
+        m = hp.fetch()
+    assert len(m) > 5000
+    assert formats.matches_lines(m, seqs, targets) == helpers.read_lines(out["matches"])
+    gnames, glens = formats.load_gene_ids(gi)
+    res = b"".join(ln + b"\n" for ln in formats.results_lines(m, seqs, counts, rnames, targets, gnames, glens))
+    assert res == helpers.read_bytes(out["results"])
+    assert formats.nonmatch_fastq(m, seqs, counts, rnames) == helpers.read_bytes(out["nonmatch"])
+
+
+def test_empty_inputs():
+    cfg = Config(Windows=[0, 5], WindowWidth=4, MaxReadLength=50).apply_defaults()
+    with _engine(cfg) as hp:
+        hp.set_reads([])
+        hp.set_targets([b"ACGTACGTACGT"])
+        hp.run()
+        assert len(hp.fetch()) == 0
+    with _engine(cfg) as hp:
+        hp.set_reads([b"ACGTACGTAC"])
+        hp.set_targets([])
+        hp.run()
+        assert len(hp.fetch()) == 0
+    with _engine(cfg) as hp:
+        hp.set_reads([b"ACG", b""])       # shorter than every window
+        hp.set_targets([b"ACGTACGTACGT", b""])
+        hp.run()
+        assert len(hp.fetch()) == 0
+
+
+def test_input_validation_errors():
+    from muscato_b200.engine import MuscatoError
+    cfg = Config(Windows=[0], WindowWidth=4, MaxReadLength=8).apply_defaults()
+    with _engine(cfg) as hp:
+        with pytest.raises(MuscatoError):
+            hp.set_reads([b"ACGTACGTACGT"])  # longer than MaxReadLength
+        with pytest.raises(MuscatoError):
+            hp.screen()                      # nothing set
+    with pytest.raises(MuscatoError):
+        _engine(Config(Windows=[0], WindowWidth=40, MaxReadLength=100).apply_defaults())

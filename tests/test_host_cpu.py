@@ -1,0 +1,136 @@
+"""CPU-only checks: host-side mirrors, the .sz codec, and that the C-ABI library loads and
+exports every symbol include/muscato_b200.h declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from muscato_b200 import _capi, build, formats, gendat, sz
+from muscato_b200.config import Config
+from tests import helpers
+
+
+def test_nmiss_float64_truncation_table():
+    """int((1-PMatch)*float64(L)), cmd/muscato_confirm/main.go:198."""
+    table = {
+        0.99: [0, 0, 1, 1, 2, 3], 0.98: [1, 1, 2, 3, 4, 6], 0.97: [1, 2, 3, 4, 6, 9],
+        0.96: [2, 3, 4, 6, 8, 12], 0.95: [2, 3, 5, 7, 10, 15], 0.93: [3, 5, 6, 10, 13, 20],
+        0.9: [4, 7, 9, 14, 19, 29],
+    }
+    for p, want in table.items():
+        cfg = Config(Windows=[0], WindowWidth=4, MaxReadLength=300, PMatch=p)
+        assert [cfg.nmiss(L) for L in (50, 75, 100, 150, 200, 300)] == want
+
+
+def test_config_defaults_and_mandatory_fields():
+    with pytest.raises(ValueError):
+        Config(WindowWidth=4, MaxReadLength=10).apply_defaults()
+    c = Config(Windows=[0, 5], WindowWidth=4, MaxReadLength=10).apply_defaults()
+    assert (c.BloomSize, c.NumHash, c.PMatch, c.MaxMatches, c.MaxConfirmProcs, c.MatchMode, c.SortPar, c.SortMem) == \
+        (4000000000, 20, 1.0, 1000000, 3, "best", 8, "50%")
+    assert (c.MinDinuc, c.MMTol, c.MinReadLength) == (0, 0, 0)
+    m = c.to_msc(device=0)
+    assert m.n_windows == 2 and list(m.windows)[:2] == [0, 5] and m.window_width == 4 and m.match_mode == _capi.MSC_MATCH_BEST
+
+
+def test_config_from_fixture_json():
+    c = Config.from_json(os.path.join(helpers.GOLDEN, "muscato", "00", "config.json"))
+    assert c.Windows == [0, 5] and c.WindowWidth == 4 and c.MMTol == 1 and c.MaxMatches == 1000
+
+
+def test_sz_reads_reference_fixture_and_round_trips():
+    d = sz.read_file(os.path.join(helpers.GOLDEN, "prep_targets", "06", "genes.txt.sz"))
+    assert d == b"gene1\tATACGATCTACGATCA\ngene2\tTTAATTAATTAA\ngene3\tATTAGGCC\n"
+    rng = np.random.default_rng(0)
+    blob = helpers.random_dna(rng, 200000) + b"\n"
+    assert sz.decompress(sz.compress(blob)) == blob
+    assert sz.compress(b"")[:10] == b"\xff\x06\x00\x00sNaPpY"
+    assert sz.crc32c(b"123456789") == 0xE3069283
+    bad = bytearray(sz.compress(b"hello world\n"))
+    bad[-1] ^= 1
+    with pytest.raises(ValueError):
+        sz.decompress(bytes(bad))
+
+
+def test_prep_reads_mirror_matches_oracle(tmp_path, oracle_bin):
+    rng = np.random.default_rng(3)
+    raw = [helpers.random_dna(rng, int(rng.integers(5, 40)), b"ACGTN") for _ in range(200)]
+    raw += raw[:30]
+    names = [b"@r%d extra" % i for i in range(len(raw))]
+    genes = [helpers.random_dna(rng, 80) for _ in range(3)]
+    fq, gs, gi = helpers.write_case(str(tmp_path), raw, names, genes)
+    cfgd = dict(Windows=[0], WindowWidth=4, MaxReadLength=30, MinReadLength=8, PMatch=1.0, BloomSize=100000, NumHash=4)
+    out = helpers.oracle_pipeline(str(tmp_path), fq, gs, gi, cfgd, sub="upstream")
+    got = formats.prep_reads_uniqify(helpers.read_bytes(fq), 8, 30)
+    assert got == formats.load_reads_sorted(out["reads_sorted"])
+
+
+def test_nonmatch_name_rule():
+    assert formats.nonmatch_name("data/x/result.txt") == "data/x/result.nonmatch.txt.fastq"
+    assert formats.nonmatch_name("results") == "nonmatch.results.fastq"
+
+
+def test_gendat_plants_reads_like_reference():
+    syn = gendat.generate(500, 50, 40, 300, seed=7)
+    reads = set(syn.reads_list())
+    tg = syn.targets_list()
+    planted = 0
+    for i in range(20):  # i < NumGene/2: read i%10 at offset i%10 (cmd/muscato_gendat/main.go:122-125)
+        j = i % 10
+        planted += tg[i][j:j + 50] in reads
+    assert planted == 20
+    syn_r = gendat.generate(500, 50, 40, 300, seed=7, rev=True)
+    assert syn_r.n_targets == 80
+    t0, t1 = syn_r.targets_list()[:2]
+    comp = {65: 84, 84: 65, 71: 67, 67: 71}
+    assert bytes(comp[c] for c in reversed(t0)) == t1
+
+
+def _header_functions():
+    hdr = open(os.path.join(helpers.ROOT, "include", "muscato_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(msc_[a-z_]+)\s*\(", hdr)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    build.build()
+    lib = ctypes.CDLL(build.LIB_PATH)
+    declared = _header_functions()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/muscato_b200.h but not exported"
+    assert sorted(_capi.EXPORTED_SYMBOLS) == declared
+    lib.msc_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.msc_version()
+
+
+def test_struct_layouts_match_the_library():
+    lib = _capi.load()
+    for which, st in enumerate([_capi.msc_config, _capi.msc_match, _capi.msc_stats, _capi.msc_key_rec,
+                                _capi.msc_cand_rec]):
+        assert lib.msc_struct_size(which) == ctypes.sizeof(st), st.__name__
+    assert ctypes.sizeof(_capi.msc_match) == 16
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    """Without a usable device msc_create must fail with a message (no CPU path exists)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from muscato_b200.engine import HotPath, MuscatoError
+    with pytest.raises(MuscatoError) as ei:
+        HotPath(Config(Windows=[0], WindowWidth=4, MaxReadLength=10).apply_defaults())
+    assert "CUDA" in str(ei.value) or "device" in str(ei.value)
+
+
+def test_product_never_touches_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's baseline legs may reference oracle/."""
+    pkg = os.path.join(helpers.ROOT, "muscato_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h", ".cpp")):
+                txt = open(os.path.join(root, f), errors="replace").read()
+                assert "oracle/" not in txt.replace("write_oracle_inputs", "") or f == "gendat.py", f
+                assert "muscato_oracle" not in txt, f
