@@ -79,7 +79,7 @@ struct msc_ctx {
   // candidates / pairs
   uint64_t n_cand = 0, n_pairs = 0;
   bool have_cand = false;
-  DevBuf cand, sizes, pstart;
+  DevBuf cand, cinfo, sizes, pstart, block_first;
   // matches
   uint64_t n_match_pre = 0, n_match = 0;
   bool have_confirm = false, have_combine = false;
@@ -261,6 +261,8 @@ int run_confirm_kernel(msc_ctx* ctx, int mode, DevBuf& outbuf, uint64_t* n_out) 
     if (ctx->n_pairs) {
       ConfirmArgs a{};
       a.cand = ctx->cand.as<uint2>();
+      a.cinfo = ctx->cinfo.as<uint2>();
+      a.block_first = ctx->block_first.as<uint32_t>();
       a.pstart = ctx->pstart.as<uint64_t>();
       a.n_cand = ctx->n_cand;
       a.n_pairs = ctx->n_pairs;
@@ -385,7 +387,7 @@ void msc_destroy(msc_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->rd_ascii, &ctx->rd_offs, &ctx->rd_words, &ctx->rd_x,  &ctx->len_flags, &ctx->validmask,
                     &ctx->tab_fp,   &ctx->tab_cnt, &ctx->tab_start, &ctx->tab_fill, &ctx->bloom, &ctx->items,
                     &ctx->tg_ascii, &ctx->tg_off,  &ctx->tg_words, &ctx->tg_x,  &ctx->xsum,      &ctx->cand,
-                    &ctx->sizes,    &ctx->pstart,  &ctx->match_pre, &ctx->best, &ctx->rcount,    &ctx->rstart,
+                    &ctx->sizes,    &ctx->pstart, &ctx->cinfo, &ctx->block_first,  &ctx->match_pre, &ctx->best, &ctx->rcount,    &ctx->rstart,
                     &ctx->rfill,    &ctx->match_out, &ctx->counters, &ctx->tile_sums, &ctx->nmiss};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -551,11 +553,12 @@ int msc_screen(msc_ctx* ctx) {
 
 static int expand_candidates(msc_ctx* ctx) {
   CK(ctx->sizes.reserve((ctx->n_cand + 1) * sizeof(uint32_t)));
+  CK(ctx->cinfo.reserve((ctx->n_cand + 1) * sizeof(uint2)));
   CK(ctx->pstart.reserve((ctx->n_cand + 2) * sizeof(uint64_t)));
   if (ctx->n_cand) {
-    cand_sizes_kernel<<<grid_for(ctx->n_cand, 256), 256, 0, ctx->stream>>>(ctx->cand.as<uint2>(), ctx->n_cand,
-                                                                          ctx->tab_cnt.as<uint32_t>(),
-                                                                          ctx->sizes.as<uint32_t>());
+    cand_prepare_kernel<<<grid_for(ctx->n_cand, 256), 256, 0, ctx->stream>>>(
+        ctx->cand.as<uint2>(), ctx->n_cand, ctx->tab_cnt.as<uint32_t>(), ctx->tg_off.as<uint32_t>(), ctx->n_targets,
+        ctx->win.W, ctx->cinfo.as<uint2>(), ctx->sizes.as<uint32_t>());
     LAUNCH_CHECK();
   }
   if (int rc = device_exclusive_scan<uint64_t>(ctx, ctx->sizes.as<uint32_t>(), ctx->n_cand, ctx->pstart.as<uint64_t>(), true))
@@ -563,6 +566,13 @@ static int expand_candidates(msc_ctx* ctx) {
   if (int rc = fetch_counters(ctx)) return rc;
   ctx->n_pairs = ctx->h_counters[C_SCANTOTAL];
   ctx->st.n_pairs = ctx->n_pairs;
+  const uint64_t n_blocks = (ctx->n_pairs + 255) / 256;
+  CK(ctx->block_first.reserve((n_blocks + 2) * sizeof(uint32_t)));
+  if (ctx->n_pairs) {
+    pair_block_starts_kernel<<<grid_for(n_blocks + 1, 256), 256, 0, ctx->stream>>>(
+        ctx->pstart.as<uint64_t>(), ctx->n_cand, ctx->n_pairs, n_blocks, ctx->block_first.as<uint32_t>());
+    LAUNCH_CHECK();
+  }
   return MSC_OK;
 }
 
@@ -664,12 +674,17 @@ int msc_fetch_matches(msc_ctx* ctx, msc_match** out, uint64_t* n) {
       return ctx->fail(MSC_ERR_CUDA, "D2H of matches failed: %s", cudaGetErrorString(e));
     }
     ctx->st.d2h_bytes += ctx->n_match * sizeof(msc_match);
-    // The device groups by read; order inside a read group is made deterministic here.
-    std::sort(h, h + ctx->n_match, [](const msc_match& a, const msc_match& b) {
-      if (a.read_id != b.read_id) return a.read_id < b.read_id;
-      if (a.gene_id != b.gene_id) return a.gene_id < b.gene_id;
-      return a.pos < b.pos;
-    });
+    // The device groups by read (counting sort on read_id); order inside a read group is made
+    // deterministic here.  Groups are short, so this is a linear pass in practice.
+    auto by_gene_pos = [](const msc_match& a, const msc_match& b) {
+      return a.gene_id != b.gene_id ? a.gene_id < b.gene_id : a.pos < b.pos;
+    };
+    for (uint64_t i = 0; i < ctx->n_match;) {
+      uint64_t j = i + 1;
+      while (j < ctx->n_match && h[j].read_id == h[i].read_id) j++;
+      if (j - i > 1) std::sort(h + i, h + j, by_gene_pos);
+      i = j;
+    }
   }
   *out = h;
   return MSC_OK;

@@ -18,16 +18,43 @@
 
 namespace msc {
 
-__global__ void __launch_bounds__(256) cand_sizes_kernel(const uint2* __restrict__ cand, uint64_t n_cand,
-                                                         const uint32_t* __restrict__ tab_cnt,
-                                                         uint32_t* __restrict__ sizes) {
+// Per candidate: locate its gene once (binary search in the target offsets), store
+// (gene, window start p inside the gene) and the number of (read, window) items of its key
+// group.  A W-mer that straddles a target boundary is not a window of any target
+// (processSeq only rolls inside one target, cmd/muscato_screen/main.go:319): size 0.
+__global__ void __launch_bounds__(256) cand_prepare_kernel(const uint2* __restrict__ cand, uint64_t n_cand,
+                                                           const uint32_t* __restrict__ tab_cnt,
+                                                           const uint32_t* __restrict__ tg_off, uint64_t n_targets,
+                                                           int W, uint2* __restrict__ cinfo,
+                                                           uint32_t* __restrict__ sizes) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_cand) sizes[i] = __ldg(tab_cnt + cand[i].x);
+  if (i >= n_cand) return;
+  const uint2 cd = cand[i];
+  const uint64_t g = upper_bound_dev<uint32_t>(tg_off, 0, n_targets + 1, cd.y) - 1;
+  const uint32_t goff = __ldg(tg_off + g);
+  const uint32_t gend = __ldg(tg_off + g + 1);
+  const uint32_t p = cd.y - goff;
+  cinfo[i] = make_uint2((uint32_t)g, p);
+  sizes[i] = ((uint64_t)cd.y + (uint64_t)W <= (uint64_t)gend) ? __ldg(tab_cnt + cd.x) : 0u;
+}
+
+// First candidate of every 256-pair block of the confirm kernel (one parallel binary search
+// per block instead of a serial one inside the block).
+__global__ void __launch_bounds__(256) pair_block_starts_kernel(const uint64_t* __restrict__ pstart, uint64_t n_cand,
+                                                                uint64_t n_pairs, uint64_t n_blocks,
+                                                                uint32_t* __restrict__ block_first) {
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > n_blocks) return;
+  const uint64_t last = n_pairs ? n_pairs - 1 : 0;
+  const uint64_t first = b * 256ull < last ? b * 256ull : last;
+  block_first[b] = (uint32_t)(upper_bound_dev<uint64_t>(pstart, 0, n_cand, first) - 1);
 }
 
 struct ConfirmArgs {
   // candidates and their pair prefix
   const uint2* cand;
+  const uint2* cinfo;          // (gene, p) per candidate
+  const uint32_t* block_first; // first candidate of each 256-pair block (+1 sentinel entry)
   const uint64_t* pstart;  // n_cand + 1
   uint64_t n_cand;
   uint64_t n_pairs;
@@ -71,18 +98,12 @@ __device__ __forceinline__ bool tg_range_has_x(const uint32_t* __restrict__ xsum
 }
 
 __global__ void __launch_bounds__(256) confirm_pairs_kernel(const WinCfg cfg, const ConfirmArgs a) {
-  __shared__ uint64_t s_clo, s_chi;
-  const uint64_t first = (uint64_t)blockIdx.x * blockDim.x;
-  if (threadIdx.x == 0) {
-    const uint64_t last = min(first + blockDim.x, a.n_pairs) - 1;
-    s_clo = upper_bound_dev<uint64_t>(a.pstart, 0, a.n_cand, first) - 1;
-    s_chi = upper_bound_dev<uint64_t>(a.pstart, 0, a.n_cand, last) - 1;
-  }
-  __syncthreads();
-  const uint64_t i = first + threadIdx.x;
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n_pairs) return;
-  const uint64_t c = upper_bound_dev<uint64_t>(a.pstart, s_clo, s_chi + 1, i) - 1;
+  const uint64_t clo = __ldg(a.block_first + blockIdx.x), chi = __ldg(a.block_first + blockIdx.x + 1);
+  const uint64_t c = upper_bound_dev<uint64_t>(a.pstart, clo, chi + 1, i) - 1;
   const uint2 cd = __ldg(a.cand + c);
+  const uint2 ci = __ldg(a.cinfo + c);
   const uint32_t slot = cd.x;
   const uint64_t gpos = cd.y;
   const uint32_t item = __ldg(a.items + __ldg(a.tab_start + slot) + (uint32_t)(i - __ldg(a.pstart + c)));
@@ -91,12 +112,10 @@ __global__ void __launch_bounds__(256) confirm_pairs_kernel(const WinCfg cfg, co
   const int W = cfg.W;
   const int q1 = cfg.windows[k], q2 = q1 + W;
 
-  // Gene of this candidate and window start p inside it.
-  const uint64_t g = upper_bound_dev<uint32_t>(a.tg_off, 0, a.n_targets + 1, (uint32_t)gpos) - 1;
-  const uint32_t goff = __ldg(a.tg_off + g);
-  const int64_t glen = (int64_t)__ldg(a.tg_off + g + 1) - (int64_t)goff;
-  const int64_t p = (int64_t)gpos - (int64_t)goff;
-  if (p + W > glen) return;        // the W-mer straddles a target boundary: not a window of any target
+  // Gene of this candidate and window start p inside it (cand_prepare_kernel).
+  const uint64_t g = ci.x;
+  const int64_t p = (int64_t)ci.y;
+  const int64_t glen = (int64_t)__ldg(a.tg_off + g + 1) - (int64_t)__ldg(a.tg_off + g);
   const int64_t pos = p - q1;      // jw = jx - q1 >= 0 (cmd/muscato_screen/main.go:345, :355)
   if (pos < 0) return;
 

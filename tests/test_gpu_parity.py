@@ -228,3 +228,28 @@ def test_input_validation_errors():
             hp.screen()                      # nothing set
     with pytest.raises(MuscatoError):
         _engine(Config(Windows=[0], WindowWidth=40, MaxReadLength=100).apply_defaults())
+
+
+@pytest.mark.parametrize("case", ["00", "03", "04"])
+def test_cli_files_drop_in(case, tmp_path, oracle_bin):
+    """The stage-compatible driver: config.json + .sz inputs in, matches.txt.sz / result.txt /
+    non-match fastq out, compared with the reference's expected files."""
+    from muscato_b200 import cli, sz
+    src = os.path.join(helpers.GOLDEN, "muscato", case)
+    cfgd = json.load(open(os.path.join(src, "config.json")))
+    seq, ids = str(tmp_path / "genes_seq.txt"), str(tmp_path / "genes_ids.txt")
+    helpers.oracle_prep_targets(os.path.join(src, "genes.txt"), seq, ids, rev=(case == "04"))
+    sz.write_file(str(tmp_path / "genes.txt.sz"), helpers.read_bytes(seq))
+    sz.write_file(str(tmp_path / "genes_ids.txt.sz"), helpers.read_bytes(ids))
+    out = helpers.oracle_pipeline(str(tmp_path / "oracle"), os.path.join(src, "reads.fastq"), seq, ids, cfgd)
+    cfgd.update(ReadFileName=os.path.join(src, "reads.fastq"), GeneFileName=str(tmp_path / "genes.txt.sz"),
+                GeneIdFileName=str(tmp_path / "genes_ids.txt.sz"), ResultsFileName=str(tmp_path / "result.txt"),
+                TempDir=str(tmp_path / "tmp"))
+    cpath = str(tmp_path / "config.json")
+    json.dump(cfgd, open(cpath, "w"))
+    cli.run(cpath, device=0, from_fastq=True)
+    assert helpers.read_bytes(str(tmp_path / "result.txt")) == helpers.read_bytes(os.path.join(src, "result_e.txt"))
+    assert helpers.read_bytes(str(tmp_path / "result.nonmatch.txt.fastq")) == \
+        helpers.read_bytes(os.path.join(src, "result.nonmatch_e.txt"))
+    assert sz.read_file(str(tmp_path / "tmp" / "matches.txt.sz")) == helpers.read_bytes(out["matches"])
+    assert sz.read_file(str(tmp_path / "tmp" / "reads_sorted.txt.sz")) == helpers.read_bytes(out["reads_sorted"])
