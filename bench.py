@@ -257,9 +257,14 @@ def run_ours(args, rank, local_rank, world):
     hp.set_targets_ptr(tg_a.data_ptr(), tg_o.data_ptr(), n_tg)
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_mode = os.environ.get("MSC_BENCH_FLUSH", "write")
 
     def flush_l2(i):
-        flush_buf.fill_(i & 0xFF)
+        # evict the previous step's working set: write a buffer twice the size of L2
+        if flush_mode != "none":
+            flush_buf.fill_(i & 0xFF)
+        if flush_mode == "write+read":
+            flush_buf.view(torch.int64).sum()
         torch.cuda.synchronize()
 
     def exchange_best():
@@ -269,7 +274,12 @@ def run_ours(args, rank, local_rank, world):
             torch.cuda.synchronize()
 
     def step_resident():
-        hp.rebuild(3)   # device pack of reads + key table + Bloom, device pack of targets
+        if world == 1:
+            # device pack of reads + key table + Bloom, device pack of targets, scan, expansion,
+            # confirm, combine: one enqueue, one synchronisation
+            hp.rebuild_and_run(3)
+            return
+        hp.rebuild(3)
         hp.screen()
         hp.confirm()
         exchange_best()
@@ -278,10 +288,13 @@ def run_ours(args, rank, local_rank, world):
     def step_e2e():
         hp.set_reads_ptr(rd_a.data_ptr(), rd_o.data_ptr(), n_reads)
         hp.set_targets_ptr(tg_a.data_ptr(), tg_o.data_ptr(), n_tg)
-        hp.screen()
-        hp.confirm()
-        exchange_best()
-        hp.combine()
+        if world == 1:
+            hp.run()
+        else:
+            hp.screen()
+            hp.confirm()
+            exchange_best()
+            hp.combine()
         if world > 1:
             holder, n = hp.matches_device()
             local = torch.as_tensor(holder, device=dev) if n else torch.zeros(0, dtype=torch.int32, device=dev)

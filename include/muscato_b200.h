@@ -143,8 +143,13 @@ void* msc_matches_device(msc_ctx* ctx, uint64_t* n);
  * *out is owned by the library: release with msc_free. */
 int msc_fetch_matches(msc_ctx* ctx, msc_match** out, uint64_t* n);
 
-/* Convenience: msc_screen + msc_confirm + msc_combine. */
+/* msc_screen + msc_confirm + msc_combine enqueued back to back on the context's stream with a
+ * single host synchronisation at the end (intermediate counts stay on the device). */
 int msc_run(msc_ctx* ctx);
+
+/* msc_rebuild(what) followed by msc_run, again with a single synchronisation: one full pass of
+ * the hot path over inputs that are already resident in HBM (keep_ascii=1). */
+int msc_rebuild_and_run(msc_ctx* ctx, int what);
 
 int msc_get_stats(const msc_ctx* ctx, msc_stats* out);
 void msc_reset_stats(msc_ctx* ctx);

@@ -82,6 +82,7 @@ _SIGS = [
     ("msc_matches_device", C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),
     ("msc_fetch_matches", C.c_int, [C.c_void_p, C.POINTER(C.POINTER(msc_match)), C.POINTER(C.c_uint64)]),
     ("msc_run", C.c_int, [C.c_void_p]),
+    ("msc_rebuild_and_run", C.c_int, [C.c_void_p, C.c_int]),
     ("msc_get_stats", C.c_int, [C.c_void_p, C.POINTER(msc_stats)]),
     ("msc_reset_stats", None, [C.c_void_p]),
     ("msc_free", None, [C.c_void_p]),

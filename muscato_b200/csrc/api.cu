@@ -1,7 +1,15 @@
 // api.cu -- context management and the C ABI of include/muscato_b200.h.
-// One context = one CUDA device + one stream.  There is deliberately no CPU fallback:
-// every entry point that computes anything launches the sm_100a kernels in this directory
-// and fails with MSC_ERR_CUDA when that is impossible.
+//
+// One context = one CUDA device + one stream.  There is deliberately no CPU fallback: every
+// entry point that computes anything launches the sm_100a kernels in this directory and fails
+// with MSC_ERR_CUDA when that is impossible.
+//
+// Execution model: every stage is *enqueued* on the context's stream without a host round
+// trip -- element counts produced by one kernel (candidates, pairs, matches) stay in a device
+// counter block that the next kernels read, and launches use persistent / grid-stride grids
+// whose shape does not depend on those counts.  A call synchronises once, at its end, to read
+// the counter block (one 128-byte D2H) and to check that the bounded output buffers were large
+// enough; if one was not, it is grown and the enqueue is repeated.
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -31,6 +39,7 @@ struct DevBuf {
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
+    bytes += 64;  // slack for 16-byte rounded fills and read-past-the-end word loads
     size_t want = bytes + bytes / 8 + 256;
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) {
@@ -50,7 +59,17 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-enum Counter { C_NKEYS = 0, C_NGROUPS, C_NCAND, C_BLOOMPASS, C_NMATCH, C_NPASS, C_SCANTOTAL, C_NOVER, C_COUNT };
+// Device counter block (unsigned long long each).
+enum Counter {
+  C_NKEYS = 0, C_NGROUPS, C_NDUP, C_SCRATCH, C_NCAND, C_BLOOMPASS, C_NMATCH, C_NPASS, C_NOVER, C_NOUT, C_NPAIRS,
+  C_COUNT = 16  // groups that are cleared together start at even indices (16-byte aligned)
+};
+
+// Stage boundary events.
+enum Ev {
+  EV_PACKR0 = 0, EV_PACKR1, EV_BUILD1, EV_PACKT0, EV_PACKT1, EV_SCAN0, EV_SCAN1, EV_EXPAND1, EV_CONFIRM1, EV_COMB0,
+  EV_COMB1, EV_COUNT
+};
 
 }  // namespace
 
@@ -59,19 +78,20 @@ struct msc_ctx {
   WinCfg win{};
   int device = 0;
   int sm_count = 148;
+  int scan_grid = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[EV_COUNT] = {};
   std::string err;
   msc_stats st{};
 
   // reads
-  uint64_t n_reads = 0, rd_ascii_bytes = 0;
+  uint64_t n_reads = 0;
   bool have_reads = false;
   DevBuf rd_ascii, rd_offs, rd_words, rd_x, len_flags, validmask;
   // key table
   int lg_slots = 0, lg_bloom = 0;
-  uint64_t n_keys = 0, n_groups = 0;
-  DevBuf tab_fp, tab_cnt, tab_start, tab_fill, bloom, items;
+  uint64_t n_keys = 0, n_groups = 0, n_dup = 0;
+  DevBuf tab_fp, tab_item0, tab_cnt, tab_start, tab_fill, bloom, items, dup_slot, fps;
   // targets
   uint64_t n_targets = 0, n_bases = 0, n_words_alloc = 0, n_tiles = 0;
   bool have_targets = false;
@@ -87,6 +107,29 @@ struct msc_ctx {
   // misc
   DevBuf counters, tile_sums, nmiss;
   unsigned long long* h_counters = nullptr;  // pinned mirror
+  // MSC_TRACE=1: an event after every launch, per-launch device times printed at each sync
+  bool trace = false;
+  std::vector<std::pair<const char*, cudaEvent_t>> trace_ev;
+  size_t trace_used = 0;
+  void trace_mark(const char* what) {
+    if (trace_used == trace_ev.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      trace_ev.emplace_back(what, e);
+    }
+    trace_ev[trace_used].first = what;
+    cudaEventRecord(trace_ev[trace_used].second, stream);
+    trace_used++;
+  }
+  void trace_dump() {
+    for (size_t i = 1; i < trace_used; i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, trace_ev[i - 1].second, trace_ev[i].second);
+      fprintf(stderr, "[msc trace] %8.1f us  %s\n", ms * 1000.f, trace_ev[i].first);
+    }
+    if (trace_used) fprintf(stderr, "[msc trace] ---- sync\n");
+    trace_used = 0;
+  }
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -97,6 +140,13 @@ struct msc_ctx {
     err = buf;
     return code;
   }
+  unsigned long long* ctr(int which) const { return counters.as<unsigned long long>() + which; }
+  uint64_t cand_cap() const { return cand.cap / sizeof(uint2); }
+  uint64_t match_cap() const { return match_pre.cap / sizeof(uint4); }
+  uint64_t block_cap() const {
+    const uint64_t n = block_first.cap / sizeof(uint32_t);
+    return n >= 2 ? n - 2 : 0;
+  }
 };
 
 #define CK(call)                                                                                         \
@@ -106,15 +156,24 @@ struct msc_ctx {
       return ctx->fail(MSC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
-#define LAUNCH_CHECK()                 \
-  do {                                 \
-    ctx->st.kernel_launches++;         \
-    CK(cudaGetLastError());            \
+#define LAUNCH_CHECK()                                       \
+  do {                                                       \
+    ctx->st.kernel_launches++;                               \
+    CK(cudaGetLastError());                                  \
+    if (ctx->trace) ctx->trace_mark(__FILE__ ":" MSC_STR(__LINE__)); \
+  } while (0)
+#define MSC_STR2(x) #x
+#define MSC_STR(x) MSC_STR2(x)
+
+#define RC(call)           \
+  do {                     \
+    int rc__ = (call);     \
+    if (rc__) return rc__; \
   } while (0)
 
 namespace {
 
-inline unsigned grid_for(uint64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+inline unsigned grid_for(uint64_t n, int block) { return (unsigned)std::max<uint64_t>(1, (n + block - 1) / block); }
 
 int ceil_log2(uint64_t v) {
   int l = 0;
@@ -122,39 +181,51 @@ int ceil_log2(uint64_t v) {
   return l;
 }
 
-// Exclusive scan of uint32 in[n] -> OutT out[n] (+ out[n] = total when write_end).
-// The grand total is also left in counters[C_SCANTOTAL].
+// Exclusive scan of uint32 in[] -> OutT out[] (+ out[n] = total when write_end).  The element
+// count is n_host, or the device counter *n_ptr clamped to n_host.  The grand total goes to
+// *total (a device counter).  Three launches, no host involvement.
 template <typename OutT>
-int device_exclusive_scan(msc_ctx* ctx, const uint32_t* in, uint64_t n, OutT* out, bool write_end) {
-  unsigned long long* total = ctx->counters.as<unsigned long long>() + C_SCANTOTAL;
-  if (n == 0) {
-    CK(cudaMemsetAsync(total, 0, sizeof(unsigned long long), ctx->stream));
-    if (write_end) CK(cudaMemsetAsync(out, 0, sizeof(OutT), ctx->stream));
-    return MSC_OK;
-  }
-  const uint64_t ntiles = (n + kScanTile - 1) / kScanTile;
-  CK(ctx->tile_sums.reserve(ntiles * sizeof(uint64_t)));
-  scan_tile_sums<<<(unsigned)ntiles, kScanThreads, 0, ctx->stream>>>(in, n, ctx->tile_sums.as<uint64_t>());
+int enqueue_exclusive_scan(msc_ctx* ctx, const uint32_t* in, const unsigned long long* n_ptr, uint64_t n_host, OutT* out,
+                           bool write_end, unsigned long long* total) {
+  const uint64_t max_tiles = std::max<uint64_t>(1, (n_host + kScanTile - 1) / kScanTile);
+  CK(ctx->tile_sums.reserve(max_tiles * sizeof(uint64_t)));
+  const unsigned grid = (unsigned)std::min<uint64_t>(max_tiles, (uint64_t)ctx->sm_count * 8);
+  scan_tile_sums<<<grid, kScanThreads, 0, ctx->stream>>>(in, n_ptr, n_host, ctx->tile_sums.as<uint64_t>());
   LAUNCH_CHECK();
-  scan_tile_offsets<<<1, kScanThreads, 0, ctx->stream>>>(ctx->tile_sums.as<uint64_t>(), ntiles,
+  scan_tile_offsets<<<1, kScanThreads, 0, ctx->stream>>>(ctx->tile_sums.as<uint64_t>(), n_ptr, n_host,
                                                          reinterpret_cast<uint64_t*>(total));
   LAUNCH_CHECK();
-  scan_apply<OutT><<<(unsigned)ntiles, kScanThreads, 0, ctx->stream>>>(in, n, ctx->tile_sums.as<uint64_t>(), out,
-                                                                       write_end ? 1 : 0);
+  scan_apply<OutT><<<grid, kScanThreads, 0, ctx->stream>>>(in, n_ptr, n_host, ctx->tile_sums.as<uint64_t>(), out,
+                                                           write_end ? 1 : 0);
   LAUNCH_CHECK();
   return MSC_OK;
 }
 
-int fetch_counters(msc_ctx* ctx) {
+// Fill several buffers in one launch.  Sizes are rounded up to 16 bytes: every DevBuf is
+// over-allocated by at least 256 bytes, so the round-up stays inside the allocation.
+struct Filler {
+  FillJob job{};
+  void add(void* p, size_t bytes, unsigned int value = 0) {
+    job.ptr[job.n] = p;
+    job.bytes[job.n] = (bytes + 15) & ~(size_t)15;
+    job.value[job.n] = value;
+    job.n++;
+  }
+};
+
+int enqueue_fill(msc_ctx* ctx, const Filler& f) {
+  if (f.job.n == 0) return MSC_OK;
+  fill_buffers_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, ctx->stream>>>(f.job);
+  LAUNCH_CHECK();
+  return MSC_OK;
+}
+
+int sync_counters(msc_ctx* ctx) {
   CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                      ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->st.d2h_bytes += C_COUNT * sizeof(unsigned long long);
-  return MSC_OK;
-}
-
-int zero_counter(msc_ctx* ctx, int which) {
-  CK(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + which, 0, sizeof(unsigned long long), ctx->stream));
+  if (ctx->trace) ctx->trace_dump();
   return MSC_OK;
 }
 
@@ -167,136 +238,349 @@ float elapsed(msc_ctx* ctx, int a, int b) {
   return ms;
 }
 
-// ---- reads: device-side pack + key table build (from the resident ASCII copy) -------------
-int build_reads_device(msc_ctx* ctx) {
+// ---- enqueue: reads pack + key table build (from the resident ASCII copy) ------------------
+int enqueue_build_reads(msc_ctx* ctx) {
   const uint64_t U = ctx->n_reads;
   const int S = ctx->win.S;
-  const uint64_t nw = U * (uint64_t)S;
-  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  CK(cudaMemsetAsync(ctx->len_flags.p, 0, (U + 1) * sizeof(uint32_t), ctx->stream));
-  if (nw) {
-    pack_reads_kernel<<<grid_for(nw, 256), 256, 0, ctx->stream>>>(
-        ctx->rd_ascii.as<uint8_t>(), ctx->rd_offs.as<uint64_t>(), U, S, ctx->rd_words.as<uint64_t>(),
+  CK(cudaEventRecord(ctx->ev[EV_PACKR0], ctx->stream));
+  if (ctx->trace) ctx->trace_mark("start build_reads");
+  const uint64_t slots = 1ull << ctx->lg_slots;
+  const uint64_t bwords = 1ull << ctx->lg_bloom;
+  {
+    Filler f;
+    f.add(ctx->len_flags.p, (U + 1) * sizeof(uint32_t));
+    f.add(ctx->counters.p, C_COUNT * sizeof(unsigned long long));
+    RC(enqueue_fill(ctx, f));
+  }
+  if (U) {
+    const int rpb = std::max(1, 256 / S);  // whole reads per block
+    const size_t smem = (size_t)rpb * (size_t)ctx->win.MRL + 64;
+    pack_reads_kernel<<<grid_for(U, rpb), 256, smem, ctx->stream>>>(
+        ctx->rd_ascii.as<uint8_t>(), ctx->rd_offs.as<uint64_t>(), U, S, rpb, ctx->rd_words.as<uint64_t>(),
         ctx->rd_x.as<uint64_t>(), ctx->len_flags.as<uint32_t>());
     LAUNCH_CHECK();
   }
-  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CK(cudaEventRecord(ctx->ev[EV_PACKR1], ctx->stream));
 
-  const uint64_t slots = 1ull << ctx->lg_slots;
-  const uint64_t bwords = 1ull << ctx->lg_bloom;
-  CK(cudaMemsetAsync(ctx->tab_fp.p, 0, slots * sizeof(uint64_t), ctx->stream));
-  CK(cudaMemsetAsync(ctx->tab_cnt.p, 0, slots * sizeof(uint32_t), ctx->stream));
-  CK(cudaMemsetAsync(ctx->tab_fill.p, 0, slots * sizeof(uint32_t), ctx->stream));
-  CK(cudaMemsetAsync(ctx->bloom.p, 0, bwords * sizeof(uint64_t), ctx->stream));
-  CK(cudaMemsetAsync(ctx->validmask.p, 0, (U + 1) * sizeof(uint32_t), ctx->stream));
-  if (int rc = zero_counter(ctx, C_NKEYS)) return rc;
-  if (int rc = zero_counter(ctx, C_NGROUPS)) return rc;
+  const uint64_t n_items = U * (uint64_t)ctx->win.nwin;
+  if (U) {
+    window_keys_kernel<<<grid_for(U, 256), 256, 0, ctx->stream>>>(
+        ctx->win, ctx->rd_words.as<uint64_t>(), ctx->rd_x.as<uint64_t>(), ctx->len_flags.as<uint32_t>(), U,
+        ctx->validmask.as<uint32_t>(), ctx->fps.as<uint64_t>(), ctx->ctr(C_NKEYS));
+    LAUNCH_CHECK();
+  }
+  {
+    Filler f;
+    f.add(ctx->tab_fp.p, slots * sizeof(uint64_t));
+    f.add(ctx->tab_cnt.p, slots * sizeof(uint32_t));
+    f.add(ctx->tab_fill.p, slots * sizeof(uint32_t));
+    f.add(ctx->bloom.p, bwords * sizeof(uint64_t));
+    RC(enqueue_fill(ctx, f));
+  }
   if (U) {
     BuildArgs a{};
-    a.rd_words = ctx->rd_words.as<uint64_t>();
-    a.rd_x = ctx->rd_x.as<uint64_t>();
-    a.len_flags = ctx->len_flags.as<uint32_t>();
-    a.n_reads = U;
+    a.n_items = n_items;
+    a.fps = ctx->fps.as<uint64_t>();
     a.tab_fp = ctx->tab_fp.as<uint64_t>();
+    a.tab_item0 = ctx->tab_item0.as<uint32_t>();
     a.tab_cnt = ctx->tab_cnt.as<uint32_t>();
     a.lg_slots = ctx->lg_slots;
     a.bloom = ctx->bloom.as<unsigned long long>();
     a.lg_bloom = ctx->lg_bloom;
-    a.validmask = ctx->validmask.as<uint32_t>();
-    a.n_keys = ctx->counters.as<unsigned long long>() + C_NKEYS;
-    a.n_groups = ctx->counters.as<unsigned long long>() + C_NGROUPS;
-    build_insert_kernel<<<grid_for(U, 256), 256, 0, ctx->stream>>>(ctx->win, a);
+    a.dup_slot = ctx->dup_slot.as<uint32_t>();
+    a.n_groups = ctx->ctr(C_NGROUPS);
+    a.n_dup = ctx->ctr(C_NDUP);
+    build_insert_kernel<<<grid_for(n_items, 256), 256, 0, ctx->stream>>>(a);
     LAUNCH_CHECK();
   }
-  if (int rc = device_exclusive_scan<uint32_t>(ctx, ctx->tab_cnt.as<uint32_t>(), slots, ctx->tab_start.as<uint32_t>(),
-                                               true))
-    return rc;
+  RC(enqueue_exclusive_scan<uint32_t>(ctx, ctx->tab_cnt.as<uint32_t>(), nullptr, slots, ctx->tab_start.as<uint32_t>(),
+                                      true, ctx->ctr(C_SCRATCH)));
   if (U) {
-    build_fill_kernel<<<grid_for(U, 256), 256, 0, ctx->stream>>>(
-        ctx->win, ctx->rd_words.as<uint64_t>(), ctx->rd_x.as<uint64_t>(), ctx->len_flags.as<uint32_t>(),
-        ctx->validmask.as<uint32_t>(), U, ctx->tab_fp.as<uint64_t>(), ctx->tab_start.as<uint32_t>(),
-        ctx->tab_fill.as<uint32_t>(), ctx->lg_slots, ctx->items.as<uint32_t>());
+    build_fill_kernel<<<grid_for(n_items, 256), 256, 0, ctx->stream>>>(
+        ctx->dup_slot.as<uint32_t>(), n_items, ctx->tab_start.as<uint32_t>(), ctx->tab_fill.as<uint32_t>(),
+        ctx->items.as<uint32_t>());
     LAUNCH_CHECK();
   }
-  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-  if (int rc = fetch_counters(ctx)) return rc;
-  ctx->n_keys = ctx->h_counters[C_NKEYS];
-  ctx->n_groups = ctx->h_counters[C_NGROUPS];
-  ctx->st.n_reads = U;
-  ctx->st.n_keys = ctx->n_keys;
-  ctx->st.n_key_groups = ctx->n_groups;
-  ctx->st.table_slots = slots;
-  ctx->st.bloom_bytes = bwords * sizeof(uint64_t);
-  ctx->st.ms_pack_reads += elapsed(ctx, 0, 1);
-  ctx->st.ms_build += elapsed(ctx, 1, 2);
+  CK(cudaEventRecord(ctx->ev[EV_BUILD1], ctx->stream));
   ctx->have_cand = ctx->have_confirm = ctx->have_combine = false;
   return MSC_OK;
 }
 
-int pack_targets_device(msc_ctx* ctx) {
-  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  CK(cudaMemsetAsync(ctx->tg_x.p, 0, ctx->n_words_alloc * sizeof(uint64_t), ctx->stream));
-  CK(cudaMemsetAsync(ctx->xsum.p, 0, (ctx->n_words_alloc / 32 + 4) * sizeof(uint32_t), ctx->stream));
+void account_build_reads(msc_ctx* ctx) {
+  ctx->n_keys = ctx->h_counters[C_NKEYS];
+  ctx->n_groups = ctx->h_counters[C_NGROUPS];
+  ctx->n_dup = ctx->h_counters[C_NDUP];
+  ctx->st.n_reads = ctx->n_reads;
+  ctx->st.n_keys = ctx->n_keys;
+  ctx->st.n_key_groups = ctx->n_groups;
+  ctx->st.table_slots = 1ull << ctx->lg_slots;
+  ctx->st.bloom_bytes = (1ull << ctx->lg_bloom) * sizeof(uint64_t);
+  ctx->st.ms_pack_reads += elapsed(ctx, EV_PACKR0, EV_PACKR1);
+  ctx->st.ms_build += elapsed(ctx, EV_PACKR1, EV_BUILD1);
+}
+
+int enqueue_pack_targets(msc_ctx* ctx) {
+  CK(cudaEventRecord(ctx->ev[EV_PACKT0], ctx->stream));
+  {
+    Filler f;
+    f.add(ctx->tg_x.p, ctx->n_words_alloc * sizeof(uint64_t));
+    f.add(ctx->xsum.p, (ctx->n_words_alloc / 32 + 4) * sizeof(uint32_t));
+    RC(enqueue_fill(ctx, f));
+  }
   pack_targets_kernel<<<grid_for(ctx->n_words_alloc, 256), 256, 0, ctx->stream>>>(
       ctx->tg_ascii.as<uint8_t>(), ctx->n_bases, ctx->tg_words.as<uint64_t>(), ctx->n_words_alloc,
       ctx->tg_x.as<uint64_t>(), ctx->xsum.as<uint32_t>());
   LAUNCH_CHECK();
-  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  ctx->st.ms_pack_targets += elapsed(ctx, 0, 1);
-  ctx->st.n_targets = ctx->n_targets;
-  ctx->st.target_bases = ctx->n_bases;
+  CK(cudaEventRecord(ctx->ev[EV_PACKT1], ctx->stream));
   ctx->have_cand = ctx->have_confirm = ctx->have_combine = false;
   return MSC_OK;
 }
 
-int run_confirm_kernel(msc_ctx* ctx, int mode, DevBuf& outbuf, uint64_t* n_out) {
-  // Runs the pair kernel; grows outbuf and re-runs if the output did not fit.
-  for (int attempt = 0; attempt < 3; attempt++) {
-    const uint64_t cap = outbuf.cap / sizeof(uint4);
-    if (int rc = zero_counter(ctx, C_NMATCH)) return rc;
-    if (int rc = zero_counter(ctx, C_NPASS)) return rc;
-    CK(cudaMemsetAsync(ctx->best.p, 0x7f, (ctx->n_reads + 1) * sizeof(uint32_t), ctx->stream));  // MSC_NO_MATCH
-    CK(cudaMemsetAsync(ctx->tab_fill.p, 0, (1ull << ctx->lg_slots) * sizeof(uint32_t), ctx->stream));
-    if (ctx->n_pairs) {
-      ConfirmArgs a{};
-      a.cand = ctx->cand.as<uint2>();
-      a.cinfo = ctx->cinfo.as<uint2>();
-      a.block_first = ctx->block_first.as<uint32_t>();
-      a.pstart = ctx->pstart.as<uint64_t>();
-      a.n_cand = ctx->n_cand;
-      a.n_pairs = ctx->n_pairs;
-      a.tab_start = ctx->tab_start.as<uint32_t>();
-      a.items = ctx->items.as<uint32_t>();
-      a.pass_cnt = ctx->tab_fill.as<uint32_t>();
-      a.rd_words = ctx->rd_words.as<uint64_t>();
-      a.rd_x = ctx->rd_x.as<uint64_t>();
-      a.len_flags = ctx->len_flags.as<uint32_t>();
-      a.validmask = ctx->validmask.as<uint32_t>();
-      a.tg_words = ctx->tg_words.as<uint64_t>();
-      a.tg_x = ctx->tg_x.as<uint64_t>();
-      a.xsum = ctx->xsum.as<uint32_t>();
-      a.tg_off = ctx->tg_off.as<uint32_t>();
-      a.n_targets = ctx->n_targets;
-      a.nmiss = ctx->nmiss.as<int32_t>();
-      a.matches = outbuf.as<uint4>();
-      a.match_cap = cap;
-      a.n_match = ctx->counters.as<unsigned long long>() + C_NMATCH;
-      a.n_pass = ctx->counters.as<unsigned long long>() + C_NPASS;
-      a.best = ctx->best.as<uint32_t>();
-      a.mode = mode;
-      confirm_pairs_kernel<<<grid_for(ctx->n_pairs, 256), 256, 0, ctx->stream>>>(ctx->win, a);
-      LAUNCH_CHECK();
-    }
-    if (int rc = fetch_counters(ctx)) return rc;
-    const uint64_t n = ctx->h_counters[C_NMATCH];
-    if (n <= cap) {
-      *n_out = n;
-      return MSC_OK;
-    }
-    CK(outbuf.reserve(n * sizeof(uint4)));
+void account_pack_targets(msc_ctx* ctx) {
+  ctx->st.ms_pack_targets += elapsed(ctx, EV_PACKT0, EV_PACKT1);
+  ctx->st.n_targets = ctx->n_targets;
+  ctx->st.target_bases = ctx->n_bases;
+}
+
+// ---- enqueue: scan ---------------------------------------------------------------------------
+int enqueue_scan(msc_ctx* ctx) {
+  if (ctx->cand.cap == 0) CK(ctx->cand.reserve(std::max<uint64_t>(1u << 20, ctx->n_bases / 16) * sizeof(uint2)));
+  if (ctx->scan_grid == 0) {
+    int blocks_per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_targets_kernel, kScanBlock, 0));
+    ctx->scan_grid = ctx->sm_count * std::max(1, blocks_per_sm);
   }
-  return ctx->fail(MSC_ERR_NOMEM, "match buffer kept overflowing");
+  {
+    Filler f;
+    f.add(ctx->ctr(C_NCAND), 2 * sizeof(unsigned long long));  // C_NCAND, C_BLOOMPASS
+    RC(enqueue_fill(ctx, f));
+  }
+  CK(cudaEventRecord(ctx->ev[EV_SCAN0], ctx->stream));
+  if (ctx->n_tiles && ctx->n_reads) {
+    ScanArgs a{};
+    a.tg_words = ctx->tg_words.as<uint64_t>();
+    a.tg_x = ctx->tg_x.as<uint64_t>();
+    a.xsum = ctx->xsum.as<uint32_t>();
+    a.n_bases = ctx->n_bases;
+    a.n_tiles = ctx->n_tiles;
+    a.bloom = ctx->bloom.as<uint2>();
+    a.lg_bloom = ctx->lg_bloom;
+    a.tab_fp = ctx->tab_fp.as<uint64_t>();
+    a.lg_slots = ctx->lg_slots;
+    a.cand = ctx->cand.as<uint2>();
+    a.cand_cap = ctx->cand_cap();
+    a.n_cand = ctx->ctr(C_NCAND);
+    a.n_bloom_pass = ctx->ctr(C_BLOOMPASS);
+    a.W = ctx->win.W;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ctx->n_tiles, (uint64_t)ctx->scan_grid));
+    scan_targets_kernel<<<grid, kScanBlock, 0, ctx->stream>>>(a);
+    LAUNCH_CHECK();
+  }
+  CK(cudaEventRecord(ctx->ev[EV_SCAN1], ctx->stream));
+  return MSC_OK;
+}
+
+// ---- enqueue: expansion + pair kernel -------------------------------------------------------
+int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
+  const uint64_t ccap = ctx->cand_cap();
+  CK(ctx->sizes.reserve((ccap + 1) * sizeof(uint32_t)));
+  CK(ctx->cinfo.reserve((ccap + 1) * sizeof(uint2)));
+  CK(ctx->pstart.reserve((ccap + 2) * sizeof(uint64_t)));
+  if (ctx->block_first.cap == 0) CK(ctx->block_first.reserve(((size_t)(1u << 16) + 2) * sizeof(uint32_t)));
+  if (outbuf.cap == 0) CK(outbuf.reserve((size_t)(1u << 20) * sizeof(uint4)));
+  const unsigned pgrid = (unsigned)ctx->sm_count * 8;
+  cand_prepare_kernel<<<pgrid, 256, 0, ctx->stream>>>(ctx->cand.as<uint2>(), ctx->ctr(C_NCAND), ccap,
+                                                      ctx->tab_cnt.as<uint32_t>(), ctx->tg_off.as<uint32_t>(),
+                                                      ctx->n_targets, ctx->win.W, ctx->cinfo.as<uint2>(),
+                                                      ctx->sizes.as<uint32_t>());
+  LAUNCH_CHECK();
+  RC(enqueue_exclusive_scan<uint64_t>(ctx, ctx->sizes.as<uint32_t>(), ctx->ctr(C_NCAND), ccap, ctx->pstart.as<uint64_t>(),
+                                      true, ctx->ctr(C_NPAIRS)));
+  pair_block_starts_kernel<<<pgrid, 256, 0, ctx->stream>>>(ctx->pstart.as<uint64_t>(), ctx->ctr(C_NCAND), ccap,
+                                                           ctx->ctr(C_NPAIRS), ctx->block_cap(),
+                                                           ctx->block_first.as<uint32_t>());
+  LAUNCH_CHECK();
+  CK(cudaEventRecord(ctx->ev[EV_EXPAND1], ctx->stream));
+
+  {
+    Filler f;
+    f.add(ctx->ctr(C_NMATCH), 4 * sizeof(unsigned long long));  // C_NMATCH, C_NPASS, C_NOVER, C_NOUT
+    f.add(ctx->best.p, (ctx->n_reads + 1) * sizeof(uint32_t), MSC_NO_MATCH);
+    f.add(ctx->tab_fill.p, (1ull << ctx->lg_slots) * sizeof(uint32_t));
+    RC(enqueue_fill(ctx, f));
+  }
+  ConfirmArgs a{};
+  a.cand = ctx->cand.as<uint2>();
+  a.cinfo = ctx->cinfo.as<uint2>();
+  a.block_first = ctx->block_first.as<uint32_t>();
+  a.pstart = ctx->pstart.as<uint64_t>();
+  a.n_pairs_ptr = ctx->ctr(C_NPAIRS);
+  a.block_cap = ctx->block_cap();
+  a.tab_item0 = ctx->tab_item0.as<uint32_t>();
+  a.tab_start = ctx->tab_start.as<uint32_t>();
+  a.items = ctx->items.as<uint32_t>();
+  a.pass_cnt = ctx->tab_fill.as<uint32_t>();
+  a.rd_words = ctx->rd_words.as<uint64_t>();
+  a.rd_x = ctx->rd_x.as<uint64_t>();
+  a.len_flags = ctx->len_flags.as<uint32_t>();
+  a.validmask = ctx->validmask.as<uint32_t>();
+  a.tg_words = ctx->tg_words.as<uint64_t>();
+  a.tg_x = ctx->tg_x.as<uint64_t>();
+  a.xsum = ctx->xsum.as<uint32_t>();
+  a.tg_off = ctx->tg_off.as<uint32_t>();
+  a.n_targets = ctx->n_targets;
+  a.nmiss = ctx->nmiss.as<int32_t>();
+  a.matches = outbuf.as<uint4>();
+  a.match_cap = outbuf.cap / sizeof(uint4);
+  a.n_match = ctx->ctr(C_NMATCH);
+  a.n_pass = ctx->ctr(C_NPASS);
+  a.best = ctx->best.as<uint32_t>();
+  a.mode = mode;
+  confirm_pairs_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->win, a);
+  LAUNCH_CHECK();
+  if (mode == 0) {
+    // MaxMatches pre-check (cmd/muscato_confirm/main.go:233-242, :424-448): truncation can only
+    // happen in a key group with more than MaxMatches passing pairs.
+    const uint64_t slots = 1ull << ctx->lg_slots;
+    overflow_count_kernel<<<grid_for(slots, 256), 256, 0, ctx->stream>>>(
+        ctx->tab_fill.as<uint32_t>(), slots, (unsigned long long)ctx->cfg.max_matches, ctx->ctr(C_NPASS),
+        ctx->ctr(C_NOVER));
+    LAUNCH_CHECK();
+  }
+  CK(cudaEventRecord(ctx->ev[EV_CONFIRM1], ctx->stream));
+  return MSC_OK;
+}
+
+int enqueue_combine(msc_ctx* ctx) {
+  const uint64_t U = ctx->n_reads, mcap = ctx->match_cap();
+  CK(ctx->rcount.reserve((U + 1) * sizeof(uint32_t)));
+  CK(ctx->rstart.reserve((U + 2) * sizeof(uint32_t)));
+  CK(ctx->rfill.reserve((U + 1) * sizeof(uint32_t)));
+  CK(ctx->match_out.reserve((mcap + 1) * sizeof(uint4)));
+  CK(cudaEventRecord(ctx->ev[EV_COMB0], ctx->stream));
+  {
+    Filler f;
+    f.add(ctx->rcount.p, (U + 1) * sizeof(uint32_t));
+    f.add(ctx->rfill.p, (U + 1) * sizeof(uint32_t));
+    RC(enqueue_fill(ctx, f));
+  }
+  const unsigned g = (unsigned)ctx->sm_count * 8;
+  combine_count_kernel<<<g, 256, 0, ctx->stream>>>(ctx->match_pre.as<uint4>(), ctx->ctr(C_NMATCH), mcap,
+                                                   ctx->best.as<uint32_t>(), (uint32_t)ctx->cfg.mmtol,
+                                                   ctx->rcount.as<uint32_t>());
+  LAUNCH_CHECK();
+  RC(enqueue_exclusive_scan<uint32_t>(ctx, ctx->rcount.as<uint32_t>(), nullptr, U, ctx->rstart.as<uint32_t>(), true,
+                                      ctx->ctr(C_NOUT)));
+  combine_scatter_kernel<<<g, 256, 0, ctx->stream>>>(ctx->match_pre.as<uint4>(), ctx->ctr(C_NMATCH), mcap,
+                                                     ctx->best.as<uint32_t>(), (uint32_t)ctx->cfg.mmtol,
+                                                     ctx->rstart.as<uint32_t>(), ctx->rfill.as<uint32_t>(),
+                                                     ctx->match_out.as<uint4>());
+  LAUNCH_CHECK();
+  CK(cudaEventRecord(ctx->ev[EV_COMB1], ctx->stream));
+  return MSC_OK;
+}
+
+// ---- completion: read the counter block, grow buffers that were too small --------------------
+// finish_* return MSC_OK, an error, or NEED_RETRY when a buffer was grown and the caller must
+// enqueue again.
+enum { NEED_RETRY = -1 };
+
+int finish_scan(msc_ctx* ctx) {
+  const float ms = elapsed(ctx, EV_SCAN0, EV_SCAN1);
+  ctx->st.ms_scan += ms;
+  ctx->st.ms_scan_kernel = ms;
+  ctx->n_cand = ctx->h_counters[C_NCAND];
+  if (ctx->n_cand > ctx->cand_cap()) {
+    CK(ctx->cand.reserve(ctx->n_cand * sizeof(uint2)));
+    ctx->have_cand = false;
+    return NEED_RETRY;
+  }
+  ctx->st.n_candidates = ctx->n_cand;
+  ctx->st.positions_probed = ctx->n_bases;
+  ctx->st.reserved_f[0] = (float)ctx->h_counters[C_BLOOMPASS];
+  ctx->have_cand = true;
+  ctx->have_confirm = ctx->have_combine = false;
+  return MSC_OK;
+}
+
+int finish_pairs(msc_ctx* ctx, DevBuf& outbuf, uint64_t* n_out) {
+  ctx->n_pairs = ctx->h_counters[C_NPAIRS];
+  const uint64_t n_blocks = (ctx->n_pairs + 255) / 256;
+  bool retry = false;
+  if (n_blocks > ctx->block_cap()) {
+    CK(ctx->block_first.reserve((n_blocks + 2) * sizeof(uint32_t)));
+    retry = true;
+  }
+  const uint64_t n = ctx->h_counters[C_NMATCH];
+  if (n > outbuf.cap / sizeof(uint4)) {
+    CK(outbuf.reserve(n * sizeof(uint4)));
+    retry = true;
+  }
+  if (retry) return NEED_RETRY;
+  *n_out = n;
+  return MSC_OK;
+}
+
+int finish_confirm(msc_ctx* ctx) {
+  RC(finish_pairs(ctx, ctx->match_pre, &ctx->n_match_pre));
+  ctx->st.ms_expand += elapsed(ctx, EV_SCAN1, EV_EXPAND1);
+  ctx->st.ms_confirm += elapsed(ctx, EV_EXPAND1, EV_CONFIRM1);
+  ctx->st.n_pairs = ctx->n_pairs;
+  ctx->st.n_pass = ctx->h_counters[C_NPASS];
+  ctx->st.n_matches_pre = ctx->n_match_pre;
+  ctx->st.n_overflow_groups = ctx->h_counters[C_NOVER];
+  if (ctx->st.n_overflow_groups)
+    return ctx->fail(MSC_ERR_CONFIG,
+                     "%llu key group(s) exceed MaxMatches=%lld passing pairs; the order-dependent truncation of "
+                     "cmd/muscato_confirm/main.go:424-448 is not implemented yet -- raise MaxMatches",
+                     (unsigned long long)ctx->st.n_overflow_groups, (long long)ctx->cfg.max_matches);
+  ctx->have_confirm = true;
+  ctx->have_combine = false;
+  return MSC_OK;
+}
+
+int finish_combine(msc_ctx* ctx) {
+  ctx->n_match = ctx->h_counters[C_NOUT];
+  ctx->st.n_matches = ctx->n_match;
+  ctx->st.ms_combine += elapsed(ctx, EV_COMB0, EV_COMB1);
+  ctx->have_combine = true;
+  return MSC_OK;
+}
+
+// The expand stage is timed from EV_SCAN1; when it is enqueued on its own (msc_confirm after
+// msc_screen) that boundary is re-recorded.
+int mark_expand_start(msc_ctx* ctx) {
+  CK(cudaEventRecord(ctx->ev[EV_SCAN1], ctx->stream));
+  return MSC_OK;
+}
+
+// [rebuild +] screen [+ confirm + combine] with a single synchronisation; repeated from the
+// scan when a buffer had to grow.
+int run_pipeline(msc_ctx* ctx, int rebuild_what, bool do_scan, bool do_confirm, bool do_combine) {
+  for (int attempt = 0; attempt < 5; attempt++) {
+    if (attempt == 0) {
+      if (rebuild_what & 1) RC(enqueue_build_reads(ctx));
+      if (rebuild_what & 2) RC(enqueue_pack_targets(ctx));
+    }
+    if (do_scan) RC(enqueue_scan(ctx));
+    if (do_confirm) {
+      if (!do_scan) RC(mark_expand_start(ctx));
+      RC(enqueue_pairs(ctx, 0, ctx->match_pre));
+    }
+    if (do_combine) RC(enqueue_combine(ctx));
+    RC(sync_counters(ctx));
+    if (attempt == 0) {
+      if (rebuild_what & 1) account_build_reads(ctx);
+      if (rebuild_what & 2) account_pack_targets(ctx);
+    }
+    int rc = MSC_OK;
+    if (do_scan) rc = finish_scan(ctx);
+    if (rc == MSC_OK && do_confirm) rc = finish_confirm(ctx);
+    if (rc == MSC_OK && do_combine) rc = finish_combine(ctx);
+    if (rc != NEED_RETRY) return rc;
+    if (!ctx->have_cand) do_scan = true;  // the candidate buffer was grown: scan again
+  }
+  return ctx->fail(MSC_ERR_NOMEM, "output buffers kept overflowing");
 }
 
 }  // namespace
@@ -304,7 +588,7 @@ int run_confirm_kernel(msc_ctx* ctx, int mode, DevBuf& outbuf, uint64_t* n_out) 
 // ===========================================================================================
 extern "C" {
 
-const char* msc_version(void) { return "muscato_b200 0.1 (sm_100a)"; }
+const char* msc_version(void) { return "muscato_b200 0.2 (sm_100a)"; }
 
 uint64_t msc_struct_size(int which) {
   switch (which) {
@@ -352,6 +636,7 @@ msc_ctx* msc_create(const msc_config* config, char* errbuf, uint64_t errlen) {
   ctx->cfg = c;
   ctx->device = c.device;
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->trace = getenv("MSC_TRACE") && atoi(getenv("MSC_TRACE")) > 0;
   ctx->win.nwin = c.n_windows;
   ctx->win.W = c.window_width;
   ctx->win.MRL = c.max_read_length;
@@ -359,7 +644,7 @@ msc_ctx* msc_create(const msc_config* config, char* errbuf, uint64_t errlen) {
   ctx->win.min_dinuc = c.min_dinuc;
   for (int k = 0; k < c.n_windows; k++) ctx->win.windows[k] = c.windows[k];
   bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
-  for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+  for (int i = 0; ok && i < EV_COUNT; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
   ok = ok && ctx->counters.reserve(C_COUNT * sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaMallocHost(&ctx->h_counters, C_COUNT * sizeof(unsigned long long)) == cudaSuccess;
   // nmiss table in IEEE double exactly as cmd/muscato_confirm/main.go:198 writes it.
@@ -372,6 +657,9 @@ msc_ctx* msc_create(const msc_config* config, char* errbuf, uint64_t errlen) {
   ok = ok && ctx->nmiss.reserve(nm.size() * sizeof(int32_t)) == cudaSuccess;
   ok = ok && cudaMemcpy(ctx->nmiss.p, nm.data(), nm.size() * sizeof(int32_t), cudaMemcpyHostToDevice) == cudaSuccess;
   ok = ok && cudaMemset(ctx->counters.p, 0, C_COUNT * sizeof(unsigned long long)) == cudaSuccess;
+  // every event is recorded once so that cudaEventElapsedTime never sees a virgin event
+  for (int i = 0; ok && i < EV_COUNT; i++) ok = cudaEventRecord(ctx->ev[i], ctx->stream) == cudaSuccess;
+  ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
   if (!ok) {
     std::string m = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
     msc_destroy(ctx);
@@ -384,15 +672,17 @@ void msc_destroy(msc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->rd_ascii, &ctx->rd_offs, &ctx->rd_words, &ctx->rd_x,  &ctx->len_flags, &ctx->validmask,
-                    &ctx->tab_fp,   &ctx->tab_cnt, &ctx->tab_start, &ctx->tab_fill, &ctx->bloom, &ctx->items,
-                    &ctx->tg_ascii, &ctx->tg_off,  &ctx->tg_words, &ctx->tg_x,  &ctx->xsum,      &ctx->cand,
-                    &ctx->sizes,    &ctx->pstart, &ctx->cinfo, &ctx->block_first,  &ctx->match_pre, &ctx->best, &ctx->rcount,    &ctx->rstart,
-                    &ctx->rfill,    &ctx->match_out, &ctx->counters, &ctx->tile_sums, &ctx->nmiss};
+  DevBuf* bufs[] = {&ctx->rd_ascii,    &ctx->rd_offs,   &ctx->rd_words, &ctx->rd_x,      &ctx->len_flags, &ctx->validmask,
+                    &ctx->tab_fp,      &ctx->tab_item0, &ctx->tab_cnt,  &ctx->tab_start, &ctx->tab_fill,  &ctx->bloom,
+                    &ctx->items,       &ctx->dup_slot,  &ctx->fps,      &ctx->tg_ascii,  &ctx->tg_off,    &ctx->tg_words,
+                    &ctx->tg_x,        &ctx->xsum,      &ctx->cand,     &ctx->cinfo,     &ctx->sizes,     &ctx->pstart,
+                    &ctx->block_first, &ctx->match_pre, &ctx->best,     &ctx->rcount,    &ctx->rstart,    &ctx->rfill,
+                    &ctx->match_out,   &ctx->counters,  &ctx->tile_sums, &ctx->nmiss};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& te : ctx->trace_ev) cudaEventDestroy(te.second);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -408,16 +698,16 @@ int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint
   uint64_t total = 0;
   if (n_reads) {
     if (offs[0] != 0) return ctx->fail(MSC_ERR_INPUT, "reads: offs[0] must be 0");
+    const uint64_t mrl = (uint64_t)ctx->win.MRL;
     for (uint64_t i = 0; i < n_reads; i++) {
       if (offs[i + 1] < offs[i]) return ctx->fail(MSC_ERR_INPUT, "reads: offsets not monotone at %llu", (unsigned long long)i);
-      if (offs[i + 1] - offs[i] > (uint64_t)ctx->win.MRL)
+      if (offs[i + 1] - offs[i] > mrl)
         return ctx->fail(MSC_ERR_INPUT, "reads: read %llu is longer than MaxReadLength (prep_reads truncates, "
                          "cmd/muscato_prep_reads/main.go:67-69)", (unsigned long long)i);
     }
     total = offs[n_reads];
   }
   ctx->n_reads = n_reads;
-  ctx->rd_ascii_bytes = total;
   const int S = ctx->win.S;
   CK(ctx->rd_ascii.reserve(total + 64));
   CK(ctx->rd_offs.reserve((n_reads + 1) * sizeof(uint64_t)));
@@ -431,11 +721,14 @@ int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint
   ctx->lg_bloom = std::max(10, ceil_log2((kmax * (uint64_t)bpk + 63) / 64));
   const uint64_t slots = 1ull << ctx->lg_slots;
   CK(ctx->tab_fp.reserve(slots * sizeof(uint64_t)));
+  CK(ctx->tab_item0.reserve(slots * sizeof(uint32_t)));
   CK(ctx->tab_cnt.reserve(slots * sizeof(uint32_t)));
   CK(ctx->tab_start.reserve((slots + 1) * sizeof(uint32_t)));
   CK(ctx->tab_fill.reserve(slots * sizeof(uint32_t)));
   CK(ctx->bloom.reserve((1ull << ctx->lg_bloom) * sizeof(uint64_t)));
   CK(ctx->items.reserve((n_reads * nwin + 1) * sizeof(uint32_t)));
+  CK(ctx->dup_slot.reserve((n_reads * nwin + 1) * sizeof(uint32_t)));
+  CK(ctx->fps.reserve((n_reads * nwin + 1) * sizeof(uint64_t)));
   CK(ctx->best.reserve((n_reads + 1) * sizeof(uint32_t)));
   // rd_words / rd_x rows are read one word past their end by extract32: keep the pad defined.
   CK(cudaMemsetAsync(ctx->rd_words.as<uint64_t>() + n_reads * S, 0, 2 * sizeof(uint64_t), ctx->stream));
@@ -445,9 +738,11 @@ int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint
   else CK(cudaMemsetAsync(ctx->rd_offs.p, 0, sizeof(uint64_t), ctx->stream));
   ctx->st.h2d_bytes += total + (n_reads + 1) * sizeof(uint64_t);
   ctx->have_reads = true;
-  int rc = build_reads_device(ctx);
-  if (rc == MSC_OK && !ctx->cfg.keep_ascii) ctx->rd_ascii.release();
-  return rc;
+  RC(enqueue_build_reads(ctx));
+  RC(sync_counters(ctx));  // the caller's buffers are only borrowed for the call
+  account_build_reads(ctx);
+  if (!ctx->cfg.keep_ascii) ctx->rd_ascii.release();
+  return MSC_OK;
 }
 
 int msc_set_targets(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint64_t n_targets) {
@@ -478,142 +773,36 @@ int msc_set_targets(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, ui
   CK(ctx->xsum.reserve((ctx->n_words_alloc / 32 + 4) * sizeof(uint32_t)));
   if (total) CK(cudaMemcpyAsync(ctx->tg_ascii.p, ascii, total, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->tg_off.p, off32.data(), (n_targets + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));  // off32 is a local
   ctx->st.h2d_bytes += total + (n_targets + 1) * sizeof(uint32_t);
   ctx->have_targets = true;
-  int rc = pack_targets_device(ctx);
-  if (rc == MSC_OK && !ctx->cfg.keep_ascii) ctx->tg_ascii.release();
-  return rc;
+  RC(enqueue_pack_targets(ctx));
+  CK(cudaStreamSynchronize(ctx->stream));  // off32 is a local; the caller's buffers are only borrowed
+  account_pack_targets(ctx);
+  if (!ctx->cfg.keep_ascii) ctx->tg_ascii.release();
+  return MSC_OK;
 }
 
 int msc_rebuild(msc_ctx* ctx, int what) {
   if (!ctx) return MSC_ERR_STATE;
   CK(cudaSetDevice(ctx->device));
   if (!ctx->cfg.keep_ascii) return ctx->fail(MSC_ERR_STATE, "msc_rebuild needs keep_ascii=1");
-  if (what & 1) {
-    if (!ctx->have_reads) return ctx->fail(MSC_ERR_STATE, "msc_rebuild: no reads set");
-    if (int rc = build_reads_device(ctx)) return rc;
-  }
-  if (what & 2) {
-    if (!ctx->have_targets) return ctx->fail(MSC_ERR_STATE, "msc_rebuild: no targets set");
-    if (int rc = pack_targets_device(ctx)) return rc;
-  }
-  return MSC_OK;
+  if ((what & 1) && !ctx->have_reads) return ctx->fail(MSC_ERR_STATE, "msc_rebuild: no reads set");
+  if ((what & 2) && !ctx->have_targets) return ctx->fail(MSC_ERR_STATE, "msc_rebuild: no targets set");
+  return run_pipeline(ctx, what & 3, false, false, false);
 }
 
 int msc_screen(msc_ctx* ctx) {
   if (!ctx) return MSC_ERR_STATE;
   if (!ctx->have_reads || !ctx->have_targets) return ctx->fail(MSC_ERR_STATE, "msc_screen: set reads and targets first");
   CK(cudaSetDevice(ctx->device));
-  if (ctx->cand.cap == 0) CK(ctx->cand.reserve(std::max<uint64_t>(1u << 20, ctx->n_bases / 32) * sizeof(uint2)));
-  int blocks_per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_targets_kernel, kScanBlock, 0));
-  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ctx->n_tiles, (uint64_t)ctx->sm_count * std::max(1, blocks_per_sm)));
-  for (int attempt = 0; attempt < 3; attempt++) {
-    if (int rc = zero_counter(ctx, C_NCAND)) return rc;
-    if (int rc = zero_counter(ctx, C_BLOOMPASS)) return rc;
-    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    if (ctx->n_tiles && ctx->n_reads) {
-      ScanArgs a{};
-      a.tg_words = ctx->tg_words.as<uint64_t>();
-      a.tg_x = ctx->tg_x.as<uint64_t>();
-      a.xsum = ctx->xsum.as<uint32_t>();
-      a.n_bases = ctx->n_bases;
-      a.n_tiles = ctx->n_tiles;
-      a.bloom = ctx->bloom.as<uint2>();
-      a.lg_bloom = ctx->lg_bloom;
-      a.tab_fp = ctx->tab_fp.as<uint64_t>();
-      a.lg_slots = ctx->lg_slots;
-      a.cand = ctx->cand.as<uint2>();
-      a.cand_cap = ctx->cand.cap / sizeof(uint2);
-      a.n_cand = ctx->counters.as<unsigned long long>() + C_NCAND;
-      a.n_bloom_pass = ctx->counters.as<unsigned long long>() + C_BLOOMPASS;
-      a.W = ctx->win.W;
-      scan_targets_kernel<<<grid, kScanBlock, 0, ctx->stream>>>(a);
-      LAUNCH_CHECK();
-    }
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    if (int rc = fetch_counters(ctx)) return rc;
-    const float ms = elapsed(ctx, 0, 1);
-    ctx->st.ms_scan += ms;
-    ctx->st.ms_scan_kernel = ms;
-    ctx->n_cand = ctx->h_counters[C_NCAND];
-    if (ctx->n_cand <= ctx->cand.cap / sizeof(uint2)) {
-      ctx->st.n_candidates = ctx->n_cand;
-      ctx->st.positions_probed = ctx->n_bases;
-      ctx->st.reserved_f[0] = (float)ctx->h_counters[C_BLOOMPASS];
-      ctx->have_cand = true;
-      ctx->have_confirm = ctx->have_combine = false;
-      return MSC_OK;
-    }
-    CK(ctx->cand.reserve(ctx->n_cand * sizeof(uint2)));
-  }
-  return ctx->fail(MSC_ERR_NOMEM, "candidate buffer kept overflowing");
-}
-
-static int expand_candidates(msc_ctx* ctx) {
-  CK(ctx->sizes.reserve((ctx->n_cand + 1) * sizeof(uint32_t)));
-  CK(ctx->cinfo.reserve((ctx->n_cand + 1) * sizeof(uint2)));
-  CK(ctx->pstart.reserve((ctx->n_cand + 2) * sizeof(uint64_t)));
-  if (ctx->n_cand) {
-    cand_prepare_kernel<<<grid_for(ctx->n_cand, 256), 256, 0, ctx->stream>>>(
-        ctx->cand.as<uint2>(), ctx->n_cand, ctx->tab_cnt.as<uint32_t>(), ctx->tg_off.as<uint32_t>(), ctx->n_targets,
-        ctx->win.W, ctx->cinfo.as<uint2>(), ctx->sizes.as<uint32_t>());
-    LAUNCH_CHECK();
-  }
-  if (int rc = device_exclusive_scan<uint64_t>(ctx, ctx->sizes.as<uint32_t>(), ctx->n_cand, ctx->pstart.as<uint64_t>(), true))
-    return rc;
-  if (int rc = fetch_counters(ctx)) return rc;
-  ctx->n_pairs = ctx->h_counters[C_SCANTOTAL];
-  ctx->st.n_pairs = ctx->n_pairs;
-  const uint64_t n_blocks = (ctx->n_pairs + 255) / 256;
-  CK(ctx->block_first.reserve((n_blocks + 2) * sizeof(uint32_t)));
-  if (ctx->n_pairs) {
-    pair_block_starts_kernel<<<grid_for(n_blocks + 1, 256), 256, 0, ctx->stream>>>(
-        ctx->pstart.as<uint64_t>(), ctx->n_cand, ctx->n_pairs, n_blocks, ctx->block_first.as<uint32_t>());
-    LAUNCH_CHECK();
-  }
-  return MSC_OK;
+  return run_pipeline(ctx, 0, true, false, false);
 }
 
 int msc_confirm(msc_ctx* ctx) {
   if (!ctx) return MSC_ERR_STATE;
   if (!ctx->have_cand) return ctx->fail(MSC_ERR_STATE, "msc_confirm: run msc_screen first");
   CK(cudaSetDevice(ctx->device));
-  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  if (int rc = expand_candidates(ctx)) return rc;
-  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  if (ctx->match_pre.cap == 0) CK(ctx->match_pre.reserve((size_t)(1u << 20) * sizeof(uint4)));
-  if (int rc = run_confirm_kernel(ctx, 0, ctx->match_pre, &ctx->n_match_pre)) return rc;
-  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-  // MaxMatches pre-check (cmd/muscato_confirm/main.go:233-242, :424-448): truncation can only
-  // happen in a key group with more than MaxMatches passing pairs.
-  const uint64_t n_pass = ctx->h_counters[C_NPASS];
-  uint64_t n_over = 0;
-  if (n_pass > (uint64_t)ctx->cfg.max_matches) {
-    if (int rc = zero_counter(ctx, C_NOVER)) return rc;
-    const uint64_t slots = 1ull << ctx->lg_slots;
-    overflow_count_kernel<<<grid_for(slots, 256), 256, 0, ctx->stream>>>(
-        ctx->tab_fill.as<uint32_t>(), slots, (unsigned long long)ctx->cfg.max_matches,
-        ctx->counters.as<unsigned long long>() + C_NOVER);
-    LAUNCH_CHECK();
-    if (int rc = fetch_counters(ctx)) return rc;
-    n_over = ctx->h_counters[C_NOVER];
-  }
-  CK(cudaStreamSynchronize(ctx->stream));
-  ctx->st.ms_expand += elapsed(ctx, 0, 1);
-  ctx->st.ms_confirm += elapsed(ctx, 1, 2);
-  ctx->st.n_pass = n_pass;
-  ctx->st.n_matches_pre = ctx->n_match_pre;
-  ctx->st.n_overflow_groups = n_over;
-  if (n_over)
-    return ctx->fail(MSC_ERR_CONFIG,
-                     "%llu key group(s) exceed MaxMatches=%lld passing pairs; the order-dependent truncation of "
-                     "cmd/muscato_confirm/main.go:424-448 is not implemented yet -- raise MaxMatches",
-                     (unsigned long long)n_over, (long long)ctx->cfg.max_matches);
-  ctx->have_confirm = true;
-  ctx->have_combine = false;
-  return MSC_OK;
+  return run_pipeline(ctx, 0, false, true, false);
 }
 
 void* msc_best_device(msc_ctx* ctx) { return (ctx && ctx->have_confirm) ? ctx->best.p : nullptr; }
@@ -628,34 +817,24 @@ int msc_combine(msc_ctx* ctx) {
   if (!ctx) return MSC_ERR_STATE;
   if (!ctx->have_confirm) return ctx->fail(MSC_ERR_STATE, "msc_combine: run msc_confirm first");
   CK(cudaSetDevice(ctx->device));
-  const uint64_t U = ctx->n_reads, n = ctx->n_match_pre;
-  if (n >= 0xffffffffull) return ctx->fail(MSC_ERR_NOMEM, "more than 2^32 matches in one batch");
-  CK(ctx->rcount.reserve((U + 1) * sizeof(uint32_t)));
-  CK(ctx->rstart.reserve((U + 2) * sizeof(uint32_t)));
-  CK(ctx->rfill.reserve((U + 1) * sizeof(uint32_t)));
-  CK(ctx->match_out.reserve((n + 1) * sizeof(uint4)));
-  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  CK(cudaMemsetAsync(ctx->rcount.p, 0, (U + 1) * sizeof(uint32_t), ctx->stream));
-  CK(cudaMemsetAsync(ctx->rfill.p, 0, (U + 1) * sizeof(uint32_t), ctx->stream));
-  if (n) {
-    combine_count_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->match_pre.as<uint4>(), n, ctx->best.as<uint32_t>(),
-                                                                    (uint32_t)ctx->cfg.mmtol, ctx->rcount.as<uint32_t>());
-    LAUNCH_CHECK();
-  }
-  if (int rc = device_exclusive_scan<uint32_t>(ctx, ctx->rcount.as<uint32_t>(), U, ctx->rstart.as<uint32_t>(), true)) return rc;
-  if (n) {
-    combine_scatter_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->match_pre.as<uint4>(), n, ctx->best.as<uint32_t>(),
-                                                                      (uint32_t)ctx->cfg.mmtol, ctx->rstart.as<uint32_t>(),
-                                                                      ctx->rfill.as<uint32_t>(), ctx->match_out.as<uint4>());
-    LAUNCH_CHECK();
-  }
-  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  if (int rc = fetch_counters(ctx)) return rc;
-  ctx->n_match = ctx->h_counters[C_SCANTOTAL];
-  ctx->st.n_matches = ctx->n_match;
-  ctx->st.ms_combine += elapsed(ctx, 0, 1);
-  ctx->have_combine = true;
-  return MSC_OK;
+  if (ctx->n_match_pre >= 0xffffffffull) return ctx->fail(MSC_ERR_NOMEM, "more than 2^32 matches in one batch");
+  return run_pipeline(ctx, 0, false, false, true);
+}
+
+int msc_run(msc_ctx* ctx) {
+  if (!ctx) return MSC_ERR_STATE;
+  if (!ctx->have_reads || !ctx->have_targets) return ctx->fail(MSC_ERR_STATE, "msc_run: set reads and targets first");
+  CK(cudaSetDevice(ctx->device));
+  return run_pipeline(ctx, 0, true, true, true);
+}
+
+int msc_rebuild_and_run(msc_ctx* ctx, int what) {
+  if (!ctx) return MSC_ERR_STATE;
+  if (!ctx->have_reads || !ctx->have_targets)
+    return ctx->fail(MSC_ERR_STATE, "msc_rebuild_and_run: set reads and targets first");
+  if ((what & 3) && !ctx->cfg.keep_ascii) return ctx->fail(MSC_ERR_STATE, "msc_rebuild_and_run needs keep_ascii=1");
+  CK(cudaSetDevice(ctx->device));
+  return run_pipeline(ctx, what & 3, true, true, true);
 }
 
 int msc_fetch_matches(msc_ctx* ctx, msc_match** out, uint64_t* n) {
@@ -690,12 +869,6 @@ int msc_fetch_matches(msc_ctx* ctx, msc_match** out, uint64_t* n) {
   return MSC_OK;
 }
 
-int msc_run(msc_ctx* ctx) {
-  if (int rc = msc_screen(ctx)) return rc;
-  if (int rc = msc_confirm(ctx)) return rc;
-  return msc_combine(ctx);
-}
-
 int msc_get_stats(const msc_ctx* ctx, msc_stats* out) {
   if (!ctx || !out) return MSC_ERR_STATE;
   *out = ctx->st;
@@ -721,8 +894,23 @@ int msc_dump_keys(msc_ctx* ctx, msc_key_rec** out, uint64_t* n) {
   if (!ctx || !out || !n) return MSC_ERR_STATE;
   if (!ctx->have_reads) return ctx->fail(MSC_ERR_STATE, "msc_dump_keys: no reads set");
   CK(cudaSetDevice(ctx->device));
-  std::vector<uint32_t> items(ctx->n_keys);
-  if (ctx->n_keys) CK(cudaMemcpy(items.data(), ctx->items.p, ctx->n_keys * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CK(cudaStreamSynchronize(ctx->stream));
+  // group members: slot-resident first items + the CSR of further members
+  const uint64_t slots = 1ull << ctx->lg_slots;
+  std::vector<uint64_t> fps(slots);
+  std::vector<uint32_t> item0(slots), items;
+  CK(cudaMemcpy(fps.data(), ctx->tab_fp.p, slots * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(item0.data(), ctx->tab_item0.p, slots * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  for (uint64_t sl = 0; sl < slots; sl++)
+    if (fps[sl]) items.push_back(item0[sl]);
+  {
+    std::vector<uint32_t> dups(ctx->n_dup);
+    if (ctx->n_dup) CK(cudaMemcpy(dups.data(), ctx->items.p, ctx->n_dup * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    items.insert(items.end(), dups.begin(), dups.end());
+  }
+  if (items.size() != ctx->n_keys)
+    return ctx->fail(MSC_ERR_STATE, "key table inconsistent: %llu items for %llu keys", (unsigned long long)items.size(),
+                     (unsigned long long)ctx->n_keys);
   msc_key_rec* h = (msc_key_rec*)malloc(std::max<uint64_t>(1, ctx->n_keys) * sizeof(msc_key_rec));
   if (!h) return ctx->fail(MSC_ERR_NOMEM, "host allocation failed");
   const uint32_t nwin = (uint32_t)ctx->win.nwin;
@@ -742,19 +930,34 @@ int msc_dump_candidates(msc_ctx* ctx, msc_cand_rec** out, uint64_t* n) {
   if (!ctx || !out || !n) return MSC_ERR_STATE;
   if (!ctx->have_cand) return ctx->fail(MSC_ERR_STATE, "msc_dump_candidates: run msc_screen first");
   CK(cudaSetDevice(ctx->device));
-  if (int rc = expand_candidates(ctx)) return rc;
   DevBuf tmp;
-  CK(tmp.reserve((size_t)(1u << 16) * sizeof(uint4)));
   uint64_t cnt = 0;
-  int rc = run_confirm_kernel(ctx, 1, tmp, &cnt);
+  int rc = MSC_OK;
+  for (int attempt = 0; attempt < 5; attempt++) {
+    rc = mark_expand_start(ctx);
+    if (rc == MSC_OK) rc = enqueue_pairs(ctx, 1, tmp);
+    if (rc == MSC_OK) rc = sync_counters(ctx);
+    if (rc == MSC_OK) rc = finish_pairs(ctx, tmp, &cnt);
+    if (rc != NEED_RETRY) break;
+  }
   ctx->have_confirm = ctx->have_combine = false;  // the pair kernel scratch (best / pass counts) was reused
-  if (rc) { tmp.release(); return rc; }
+  if (rc == NEED_RETRY) rc = ctx->fail(MSC_ERR_NOMEM, "candidate dump buffer kept overflowing");
+  if (rc) {
+    tmp.release();
+    return rc;
+  }
   msc_cand_rec* h = (msc_cand_rec*)malloc(std::max<uint64_t>(1, cnt) * sizeof(msc_cand_rec));
-  if (!h) { tmp.release(); return ctx->fail(MSC_ERR_NOMEM, "host allocation failed"); }
+  if (!h) {
+    tmp.release();
+    return ctx->fail(MSC_ERR_NOMEM, "host allocation failed");
+  }
   static_assert(sizeof(msc_cand_rec) == sizeof(uint4), "msc_cand_rec layout");
   cudaError_t e = cnt ? cudaMemcpy(h, tmp.p, cnt * sizeof(uint4), cudaMemcpyDeviceToHost) : cudaSuccess;
   tmp.release();
-  if (e != cudaSuccess) { free(h); return ctx->fail(MSC_ERR_CUDA, "D2H failed: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) {
+    free(h);
+    return ctx->fail(MSC_ERR_CUDA, "D2H failed: %s", cudaGetErrorString(e));
+  }
   std::sort(h, h + cnt, [](const msc_cand_rec& a, const msc_cand_rec& b) {
     if (a.window != b.window) return a.window < b.window;
     if (a.gene_id != b.gene_id) return a.gene_id < b.gene_id;

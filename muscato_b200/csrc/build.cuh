@@ -32,93 +32,116 @@ __device__ __forceinline__ int dinuc_count(uint64_t key, uint64_t xm, int W) {
 }
 
 struct BuildArgs {
-  const uint64_t* rd_words;
-  const uint64_t* rd_x;
-  const uint32_t* len_flags;
-  uint64_t n_reads;
+  uint64_t n_items;      // n_reads * nwin
+  const uint64_t* fps;   // per item: key fingerprint, 0 = window not valid for the read
   uint64_t* tab_fp;
-  uint32_t* tab_cnt;
+  uint32_t* tab_item0;   // first (read, window) item of the slot's key group
+  uint32_t* tab_cnt;     // number of FURTHER items of the group (they go to the CSR `items`)
   int lg_slots;
   unsigned long long* bloom;
   int lg_bloom;
-  uint32_t* validmask;
-  unsigned long long* n_keys;    // valid (read, window) keys
+  uint32_t* dup_slot;    // per item: 1 + slot if the item is a further member of its group, else 0
   unsigned long long* n_groups;  // distinct fingerprints
+  unsigned long long* n_dup;     // items beyond the first of their group
 };
 
-// Pass A: per read, evaluate every window (length + entropy rule), claim / find the table
-// slot of its fingerprint, count it, and set the Bloom bits.
-__global__ void __launch_bounds__(256) build_insert_kernel(const WinCfg cfg, const BuildArgs a) {
+// Pass A1: per read, which windows are valid (length rule + entropy rule) and the fingerprint of
+// each valid window key.  Pure ALU over the packed words; item = read * nwin + window.
+__global__ void __launch_bounds__(256) window_keys_kernel(const WinCfg cfg, const uint64_t* __restrict__ rd_words,
+                                                          const uint64_t* __restrict__ rd_x,
+                                                          const uint32_t* __restrict__ len_flags, uint64_t n_reads,
+                                                          uint32_t* __restrict__ validmask, uint64_t* __restrict__ fps,
+                                                          unsigned long long* __restrict__ n_keys) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t nk = 0, ng = 0;
-  if (r < a.n_reads) {
-    const uint32_t lf = a.len_flags[r];
+  uint32_t nk = 0;
+  if (r < n_reads) {
+    const uint32_t lf = len_flags[r];
     const int L = (int)(lf & 0x7fffffffu);
     const bool hasx = lf >> 31;
-    const uint64_t* row = a.rd_words + r * (uint64_t)cfg.S;
-    const uint64_t* xrow = a.rd_x + r * (uint64_t)cfg.S;
+    const uint64_t* row = rd_words + r * (uint64_t)cfg.S;
+    const uint64_t* xrow = rd_x + r * (uint64_t)cfg.S;
     const uint64_t kmask = low_bases_mask(cfg.W);
-    const uint64_t smask = (1ull << a.lg_slots) - 1ull;
     uint32_t vm = 0;
     for (int k = 0; k < cfg.nwin; k++) {
       const int q1 = cfg.windows[k], q2 = q1 + cfg.W;
-      if (L < q2) continue;  // cmd/muscato_window_reads/main.go:109-112, cmd/muscato_screen/main.go:177-179
-      const uint64_t key = extract32(row, (uint64_t)q1) & kmask;
-      const uint64_t xm = hasx ? (extract32(xrow, (uint64_t)q1) & kmask) : 0ull;
-      if (cfg.min_dinuc > 0 && dinuc_count(key, xm, cfg.W) < cfg.min_dinuc) continue;  // :183-185 / :116-118
-      vm |= 1u << k;
-      nk++;
-      const uint64_t fp = key_fp(key, xm);
+      uint64_t fp = 0;
+      if (L >= q2) {  // cmd/muscato_window_reads/main.go:109-112, cmd/muscato_screen/main.go:177-179
+        const uint64_t key = extract32(row, (uint64_t)q1) & kmask;
+        const uint64_t xm = hasx ? (extract32(xrow, (uint64_t)q1) & kmask) : 0ull;
+        if (cfg.min_dinuc <= 0 || dinuc_count(key, xm, cfg.W) >= cfg.min_dinuc) {  // :183-185 / :116-118
+          fp = key_fp(key, xm);
+          vm |= 1u << k;
+          nk++;
+        }
+      }
+      fps[r * (uint64_t)cfg.nwin + (uint64_t)k] = fp;
+    }
+    validmask[r] = vm;
+  }
+  nk = __reduce_add_sync(0xffffffffu, nk);
+  if ((threadIdx.x & 31u) == 0 && nk) atomicAdd(n_keys, (unsigned long long)nk);
+}
+
+// Pass A2: one thread per item.  Claim / find the table slot of the fingerprint and set the
+// Bloom bits.  The first item of a key group lives in the slot itself (most groups have exactly
+// one member); further members are flagged in dup_slot and scattered into the slot's CSR range
+// by pass B.
+__global__ void __launch_bounds__(256) build_insert_kernel(const BuildArgs a) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t ng = 0, nd = 0;
+  if (idx < a.n_items) {
+    const uint64_t fp = __ldg(a.fps + idx);
+    uint32_t dup = 0;
+    if (fp) {
+      const uint64_t smask = (1ull << a.lg_slots) - 1ull;
       uint64_t s = table_home(fp, a.lg_slots);
+      bool first = false;
       while (true) {
         const unsigned long long cur =
             atomicCAS(reinterpret_cast<unsigned long long*>(a.tab_fp + s), 0ull, (unsigned long long)fp);
-        if (cur == 0ull) { ng++; break; }
+        if (cur == 0ull) { first = true; break; }
         if (cur == fp) break;
         s = (s + 1) & smask;
       }
-      atomicAdd(a.tab_cnt + s, 1u);
-      const unsigned long long bm = (unsigned long long)bloom_mask_lo(fp) | ((unsigned long long)bloom_mask_hi(fp) << 32);
-      atomicOr(a.bloom + bloom_index(fp, a.lg_bloom), bm);
+      if (first) {
+        ng = 1;
+        a.tab_item0[s] = (uint32_t)idx;
+        const unsigned long long bm =
+            (unsigned long long)bloom_mask_lo(fp) | ((unsigned long long)bloom_mask_hi(fp) << 32);
+        atomicOr(a.bloom + bloom_index(fp, a.lg_bloom), bm);
+      } else {
+        nd = 1;
+        atomicAdd(a.tab_cnt + s, 1u);
+        dup = (uint32_t)s + 1u;
+      }
     }
-    a.validmask[r] = vm;
+    a.dup_slot[idx] = dup;
   }
-  nk = __reduce_add_sync(0xffffffffu, nk);
   ng = __reduce_add_sync(0xffffffffu, ng);
+  nd = __reduce_add_sync(0xffffffffu, nd);
   if ((threadIdx.x & 31u) == 0) {
-    if (nk) atomicAdd(a.n_keys, (unsigned long long)nk);
     if (ng) atomicAdd(a.n_groups, (unsigned long long)ng);
+    if (nd) atomicAdd(a.n_dup, (unsigned long long)nd);
   }
 }
 
-// Pass B (after the exclusive scan of tab_cnt into tab_start): scatter the (read, window)
-// items into their slot's CSR range.  item = read * nwin + window.
-__global__ void __launch_bounds__(256) build_fill_kernel(const WinCfg cfg, const uint64_t* __restrict__ rd_words,
-                                                         const uint64_t* __restrict__ rd_x,
-                                                         const uint32_t* __restrict__ len_flags,
-                                                         const uint32_t* __restrict__ validmask, uint64_t n_reads,
-                                                         const uint64_t* __restrict__ tab_fp,
+// Pass B (after the exclusive scan of tab_cnt into tab_start): scatter the further members
+// into their slot's CSR range.
+__global__ void __launch_bounds__(256) build_fill_kernel(const uint32_t* __restrict__ dup_slot, uint64_t n_items,
                                                          const uint32_t* __restrict__ tab_start,
-                                                         uint32_t* __restrict__ tab_fill, int lg_slots,
+                                                         uint32_t* __restrict__ tab_fill,
                                                          uint32_t* __restrict__ items) {
-  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_reads) return;
-  uint32_t vm = validmask[r];
-  if (!vm) return;
-  const bool hasx = len_flags[r] >> 31;
-  const uint64_t* row = rd_words + r * (uint64_t)cfg.S;
-  const uint64_t* xrow = rd_x + r * (uint64_t)cfg.S;
-  const uint64_t kmask = low_bases_mask(cfg.W);
-  while (vm) {
-    const int k = __ffs(vm) - 1;
-    vm &= vm - 1;
-    const int q1 = cfg.windows[k];
-    const uint64_t key = extract32(row, (uint64_t)q1) & kmask;
-    const uint64_t xm = hasx ? (extract32(xrow, (uint64_t)q1) & kmask) : 0ull;
-    const int64_t s = table_find(tab_fp, lg_slots, key_fp(key, xm));
-    const uint32_t at = tab_start[s] + atomicAdd(tab_fill + s, 1u);
-    items[at] = (uint32_t)(r * (uint64_t)cfg.nwin + (uint64_t)k);
-  }
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_items) return;
+  const uint32_t d = __ldg(dup_slot + idx);
+  if (d) items[tab_start[d - 1] + atomicAdd(tab_fill + (d - 1), 1u)] = (uint32_t)idx;
+}
+
+// Member j of the key group in `slot` (j = 0 is stored in the slot, the rest in the CSR).
+__device__ __forceinline__ uint32_t group_item(const uint32_t* __restrict__ tab_item0,
+                                               const uint32_t* __restrict__ tab_start,
+                                               const uint32_t* __restrict__ items, uint32_t slot, uint32_t j) {
+  return j == 0 ? __ldg(tab_item0 + slot) : __ldg(items + __ldg(tab_start + slot) + (j - 1));
 }
 
 }  // namespace msc

@@ -8,23 +8,27 @@
 
 namespace msc {
 
-__global__ void __launch_bounds__(256) combine_count_kernel(const uint4* __restrict__ m, uint64_t n,
+__global__ void __launch_bounds__(256) combine_count_kernel(const uint4* __restrict__ m,
+                                                            const unsigned long long* __restrict__ n_ptr, uint64_t cap,
                                                             const uint32_t* __restrict__ best, uint32_t mmtol,
                                                             uint32_t* __restrict__ rcount) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint4 v = m[i];
-  if (v.w <= __ldg(best + v.x) + mmtol) atomicAdd(rcount + v.x, 1u);
+  const uint64_t n = min((uint64_t)*n_ptr, cap);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 v = m[i];
+    if (v.w <= __ldg(best + v.x) + mmtol) atomicAdd(rcount + v.x, 1u);
+  }
 }
 
-__global__ void __launch_bounds__(256) combine_scatter_kernel(const uint4* __restrict__ m, uint64_t n,
+__global__ void __launch_bounds__(256) combine_scatter_kernel(const uint4* __restrict__ m,
+                                                              const unsigned long long* __restrict__ n_ptr, uint64_t cap,
                                                               const uint32_t* __restrict__ best, uint32_t mmtol,
                                                               const uint32_t* __restrict__ rstart,
                                                               uint32_t* __restrict__ rfill, uint4* __restrict__ out) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint4 v = m[i];
-  if (v.w <= __ldg(best + v.x) + mmtol) out[__ldg(rstart + v.x) + atomicAdd(rfill + v.x, 1u)] = v;
+  const uint64_t n = min((uint64_t)*n_ptr, cap);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 v = m[i];
+    if (v.w <= __ldg(best + v.x) + mmtol) out[__ldg(rstart + v.x) + atomicAdd(rfill + v.x, 1u)] = v;
+  }
 }
 
 // Number of key groups whose passing-pair count exceeds MaxMatches (the only groups for
@@ -32,7 +36,9 @@ __global__ void __launch_bounds__(256) combine_scatter_kernel(const uint4* __res
 // drop anything).
 __global__ void __launch_bounds__(256) overflow_count_kernel(const uint32_t* __restrict__ pass_cnt, uint64_t n_slots,
                                                              unsigned long long max_matches,
+                                                             const unsigned long long* __restrict__ n_pass,
                                                              unsigned long long* __restrict__ n_over) {
+  if (*n_pass <= max_matches) return;  // no group can exceed MaxMatches
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t over = (i < n_slots && (unsigned long long)pass_cnt[i] > max_matches) ? 1u : 0u;
   over = __reduce_add_sync(0xffffffffu, over);

@@ -22,32 +22,39 @@ namespace msc {
 // (gene, window start p inside the gene) and the number of (read, window) items of its key
 // group.  A W-mer that straddles a target boundary is not a window of any target
 // (processSeq only rolls inside one target, cmd/muscato_screen/main.go:319): size 0.
-__global__ void __launch_bounds__(256) cand_prepare_kernel(const uint2* __restrict__ cand, uint64_t n_cand,
-                                                           const uint32_t* __restrict__ tab_cnt,
+__global__ void __launch_bounds__(256) cand_prepare_kernel(const uint2* __restrict__ cand,
+                                                           const unsigned long long* __restrict__ n_cand_ptr,
+                                                           uint64_t cand_cap, const uint32_t* __restrict__ tab_cnt,
                                                            const uint32_t* __restrict__ tg_off, uint64_t n_targets,
                                                            int W, uint2* __restrict__ cinfo,
                                                            uint32_t* __restrict__ sizes) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_cand) return;
-  const uint2 cd = cand[i];
-  const uint64_t g = upper_bound_dev<uint32_t>(tg_off, 0, n_targets + 1, cd.y) - 1;
-  const uint32_t goff = __ldg(tg_off + g);
-  const uint32_t gend = __ldg(tg_off + g + 1);
-  const uint32_t p = cd.y - goff;
-  cinfo[i] = make_uint2((uint32_t)g, p);
-  sizes[i] = ((uint64_t)cd.y + (uint64_t)W <= (uint64_t)gend) ? __ldg(tab_cnt + cd.x) : 0u;
+  const uint64_t n_cand = min((uint64_t)*n_cand_ptr, cand_cap);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint2 cd = cand[i];
+    const uint64_t g = upper_bound_dev<uint32_t>(tg_off, 0, n_targets + 1, cd.y) - 1;
+    const uint32_t goff = __ldg(tg_off + g);
+    const uint32_t gend = __ldg(tg_off + g + 1);
+    const uint32_t p = cd.y - goff;
+    cinfo[i] = make_uint2((uint32_t)g, p);
+    sizes[i] = ((uint64_t)cd.y + (uint64_t)W <= (uint64_t)gend) ? 1u + __ldg(tab_cnt + cd.x) : 0u;
+  }
 }
 
 // First candidate of every 256-pair block of the confirm kernel (one parallel binary search
-// per block instead of a serial one inside the block).
-__global__ void __launch_bounds__(256) pair_block_starts_kernel(const uint64_t* __restrict__ pstart, uint64_t n_cand,
-                                                                uint64_t n_pairs, uint64_t n_blocks,
-                                                                uint32_t* __restrict__ block_first) {
-  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b > n_blocks) return;
-  const uint64_t last = n_pairs ? n_pairs - 1 : 0;
-  const uint64_t first = b * 256ull < last ? b * 256ull : last;
-  block_first[b] = (uint32_t)(upper_bound_dev<uint64_t>(pstart, 0, n_cand, first) - 1);
+// per block instead of a serial one inside the block).  Entry n_blocks is a sentinel.
+__global__ void __launch_bounds__(256) pair_block_starts_kernel(const uint64_t* __restrict__ pstart,
+                                                                const unsigned long long* __restrict__ n_cand_ptr,
+                                                                uint64_t cand_cap,
+                                                                const unsigned long long* __restrict__ n_pairs_ptr,
+                                                                uint64_t block_cap, uint32_t* __restrict__ block_first) {
+  const uint64_t n_cand = min((uint64_t)*n_cand_ptr, cand_cap);
+  const uint64_t n_pairs = *n_pairs_ptr;
+  if (n_pairs == 0) return;
+  const uint64_t n_blocks = min((uint64_t)((n_pairs + 255) / 256), block_cap);
+  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= n_blocks; b += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t first = min((uint64_t)(b * 256ull), (uint64_t)(n_pairs - 1));
+    block_first[b] = (uint32_t)(upper_bound_dev<uint64_t>(pstart, 0, n_cand, first) - 1);
+  }
 }
 
 struct ConfirmArgs {
@@ -56,9 +63,10 @@ struct ConfirmArgs {
   const uint2* cinfo;          // (gene, p) per candidate
   const uint32_t* block_first; // first candidate of each 256-pair block (+1 sentinel entry)
   const uint64_t* pstart;  // n_cand + 1
-  uint64_t n_cand;
-  uint64_t n_pairs;
+  const unsigned long long* n_pairs_ptr;  // device-side pair count (grand total of the size scan)
+  uint64_t block_cap;                     // capacity of block_first (in 256-pair blocks)
   // key table
+  const uint32_t* tab_item0;
   const uint32_t* tab_start;
   const uint32_t* items;
   uint32_t* pass_cnt;  // per slot: pairs that passed (MaxMatches pre-check)
@@ -97,16 +105,15 @@ __device__ __forceinline__ bool tg_range_has_x(const uint32_t* __restrict__ xsum
   return false;
 }
 
-__global__ void __launch_bounds__(256) confirm_pairs_kernel(const WinCfg cfg, const ConfirmArgs a) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n_pairs) return;
-  const uint64_t clo = __ldg(a.block_first + blockIdx.x), chi = __ldg(a.block_first + blockIdx.x + 1);
+// One (candidate, read) pair.
+__device__ __forceinline__ void confirm_one_pair(const WinCfg& cfg, const ConfirmArgs& a, uint64_t i, uint64_t clo,
+                                                 uint64_t chi) {
   const uint64_t c = upper_bound_dev<uint64_t>(a.pstart, clo, chi + 1, i) - 1;
   const uint2 cd = __ldg(a.cand + c);
   const uint2 ci = __ldg(a.cinfo + c);
   const uint32_t slot = cd.x;
   const uint64_t gpos = cd.y;
-  const uint32_t item = __ldg(a.items + __ldg(a.tab_start + slot) + (uint32_t)(i - __ldg(a.pstart + c)));
+  const uint32_t item = group_item(a.tab_item0, a.tab_start, a.items, slot, (uint32_t)(i - __ldg(a.pstart + c)));
   const uint32_t r = item / (uint32_t)cfg.nwin;
   const int k = (int)(item - r * (uint32_t)cfg.nwin);
   const int W = cfg.W;
@@ -157,7 +164,9 @@ __global__ void __launch_bounds__(256) confirm_pairs_kernel(const WinCfg cfg, co
   }
 
   // Full-read mismatch count: nx = cdiff(left tails) + cdiff(right tails) (+0 inside the window).
+  // Early exit once the budget is exceeded (the count itself is only needed for kept pairs).
   int nx = 0;
+  const int budget = __ldg(a.nmiss + L);
   const int nwords = (L + 31) >> 5;
   for (int w = 0; w < nwords; w++) {
     const uint64_t ra = __ldg(row + w);
@@ -171,8 +180,8 @@ __global__ void __launch_bounds__(256) confirm_pairs_kernel(const WinCfg cfg, co
     }
     m &= low_bases_mask(min(32, L - 32 * w));
     nx += __popcll(m);
+    if (nx > budget) return;
   }
-  if (nx > __ldg(a.nmiss + L)) return;
 
   // The pair passes through window k.
   atomicAdd(a.pass_cnt + slot, 1u);
@@ -204,6 +213,17 @@ __global__ void __launch_bounds__(256) confirm_pairs_kernel(const WinCfg cfg, co
   atomicMin(a.best + r, (uint32_t)nx);
   const unsigned long long at = warp_agg_inc(a.n_match);
   if (at < a.match_cap) a.matches[at] = make_uint4(r, (uint32_t)g, (uint32_t)pos, (uint32_t)nx);
+}
+
+// Persistent grid: blocks stride over the 256-pair blocks; the pair count lives on the device,
+// so the launch configuration never depends on a host round trip.
+__global__ void __launch_bounds__(256) confirm_pairs_kernel(const WinCfg cfg, const ConfirmArgs a) {
+  const uint64_t n_pairs = *a.n_pairs_ptr;
+  const uint64_t n_blocks = min((uint64_t)((n_pairs + 255) / 256), a.block_cap);
+  for (uint64_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+    const uint64_t i = b * 256ull + threadIdx.x;
+    if (i < n_pairs) confirm_one_pair(cfg, a, i, __ldg(a.block_first + b), __ldg(a.block_first + b + 1));
+  }
 }
 
 }  // namespace msc

@@ -13,47 +13,86 @@ __device__ __forceinline__ void base_code(uint32_t c, uint32_t& code, uint32_t& 
   code = ok ? ((c >> 1) & 3u) : 0u;
 }
 
-// 16 ASCII bases held in a uint4 -> 32 packed bits (+ 32 X-plane bits).
-__device__ __forceinline__ void pack16(const uint4 v, uint32_t& bits, uint32_t& xbits) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-  bits = 0;
-  xbits = 0;
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      uint32_t code, isx;
-      base_code((w[q] >> (8 * b)) & 0xffu, code, isx);
-      const int sh = 2 * (4 * q + b);
-      bits |= code << sh;
-      xbits |= isx << sh;
-    }
-  }
+// 4 ASCII bases in one 32-bit word -> 8 packed bits + 8 X-plane bits (SWAR, no per-byte loop).
+// code = (byte>>1)&3; the byte is valid iff it equals LUT[code] with LUT = {A,C,T,G}, which
+// __byte_perm evaluates for all four bytes at once.
+__device__ __forceinline__ void pack4(uint32_t v, uint32_t& bits, uint32_t& xbits) {
+  uint32_t c = (v >> 1) & 0x03030303u;
+  uint32_t t = c | (c >> 4);                                  // nibble-pack the codes as a permute selector
+  const uint32_t sel = (t & 0xffu) | ((t >> 8) & 0xff00u);
+  const uint32_t expect = __byte_perm(0x47544341u, 0u, sel);  // bytes: 0:'A' 1:'C' 2:'T' 3:'G'
+  const uint32_t diff = v ^ expect;
+  const uint32_t nz = ((diff | ((diff & 0x7f7f7f7fu) + 0x7f7f7f7fu)) >> 7) & 0x01010101u;  // 1 per invalid byte
+  c &= ~(nz * 3u);
+  t = c | (c >> 6);
+  bits = (t | (t >> 12)) & 0xffu;
+  t = nz | (nz >> 6);
+  xbits = (t | (t >> 12)) & 0xffu;
 }
 
-// Reads: one thread per (read, word).  Row r of `words` / `xplane` has `stride` words;
-// len_flags[r] = length | (has X ? 1<<31 : 0) (zero-initialised by the caller).
+// 16 ASCII bases held in a uint4 -> 32 packed bits (+ 32 X-plane bits).
+__device__ __forceinline__ void pack16(const uint4 v, uint32_t& bits, uint32_t& xbits) {
+  uint32_t b0, x0, b1, x1, b2, x2, b3, x3;
+  pack4(v.x, b0, x0);
+  pack4(v.y, b1, x1);
+  pack4(v.z, b2, x2);
+  pack4(v.w, b3, x3);
+  bits = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+  xbits = x0 | (x1 << 8) | (x2 << 16) | (x3 << 24);
+}
+
+// Reads: one thread per (read, word); a block packs `reads_per_block` = 256/stride whole reads.
+// Row r of `words` / `xplane` has `stride` words; len_flags[r] = length | (has X ? 1<<31 : 0).
+// The block's reads are one contiguous byte range of the concatenated ASCII: it is staged into
+// shared memory with coalesced 16-byte loads and each thread then picks its (arbitrarily
+// aligned) 32 bytes out of shared memory with 32-bit loads + funnel shifts.
 __global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t* __restrict__ ascii,
                                                          const uint64_t* __restrict__ offs, uint64_t n_reads,
-                                                         int stride, uint64_t* __restrict__ words,
-                                                         uint64_t* __restrict__ xplane,
+                                                         int stride, int reads_per_block,
+                                                         uint64_t* __restrict__ words, uint64_t* __restrict__ xplane,
                                                          uint32_t* __restrict__ len_flags) {
-  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_reads * (uint64_t)stride) return;
-  const uint64_t r = idx / (uint64_t)stride;
-  const int w = (int)(idx - r * (uint64_t)stride);
-  const uint64_t o0 = offs[r];
-  const int L = (int)(offs[r + 1] - o0);
+  extern __shared__ __align__(16) uint8_t sm[];
+  const uint64_t r0 = (uint64_t)blockIdx.x * (uint64_t)reads_per_block;
+  const uint64_t r1 = min(r0 + (uint64_t)reads_per_block, n_reads);
+  const uint64_t blk_lo = __ldg(offs + r0), blk_hi = __ldg(offs + r1);
+  const uint64_t lo_al = blk_lo & ~15ull;
+  const uint32_t nbytes = (uint32_t)(blk_hi - lo_al);
+  for (uint32_t i = threadIdx.x * 16u; i < nbytes; i += 256u * 16u)
+    *reinterpret_cast<uint4*>(sm + i) = __ldg(reinterpret_cast<const uint4*>(ascii + lo_al + i));
+  __syncthreads();
+  const uint32_t lr = threadIdx.x / (uint32_t)stride;
+  const int w = (int)(threadIdx.x - lr * (uint32_t)stride);
+  const uint64_t r = r0 + lr;
+  if ((int)lr >= reads_per_block || r >= r1) return;
+  const uint64_t o0 = __ldg(offs + r);
+  const int L = (int)(__ldg(offs + r + 1) - o0);
   const int b0 = w * 32;
   const int n = min(32, L - b0);
   uint64_t bits = 0, xb = 0;
-  const uint8_t* src = ascii + o0 + b0;
-  for (int i = 0; i < n; i++) {
-    uint32_t code, isx;
-    base_code(__ldg(src + i), code, isx);
-    bits |= (uint64_t)code << (2 * i);
-    xb |= (uint64_t)isx << (2 * i);
+  if (n > 0) {
+    const uint32_t a = (uint32_t)(o0 + (uint64_t)b0 - lo_al);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(sm + (a & ~3u));
+    const unsigned sh = (a & 3u) * 8u;
+    uint32_t v[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) v[i] = wp[i];
+    uint4 q0, q1;
+    q0.x = __funnelshift_r(v[0], v[1], sh);
+    q0.y = __funnelshift_r(v[1], v[2], sh);
+    q0.z = __funnelshift_r(v[2], v[3], sh);
+    q0.w = __funnelshift_r(v[3], v[4], sh);
+    q1.x = __funnelshift_r(v[4], v[5], sh);
+    q1.y = __funnelshift_r(v[5], v[6], sh);
+    q1.z = __funnelshift_r(v[6], v[7], sh);
+    q1.w = __funnelshift_r(v[7], v[8], sh);
+    uint32_t blo, xlo, bhi, xhi;
+    pack16(q0, blo, xlo);
+    pack16(q1, bhi, xhi);
+    const uint64_t keep = low_bases_mask(n);
+    bits = ((uint64_t)blo | ((uint64_t)bhi << 32)) & keep;
+    xb = ((uint64_t)xlo | ((uint64_t)xhi << 32)) & keep;
   }
+  const uint64_t idx = r * (uint64_t)stride + (uint64_t)w;
   words[idx] = bits;
   xplane[idx] = xb;
   uint32_t lf = (w == 0) ? (uint32_t)L : 0u;

@@ -36,25 +36,61 @@ __device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_
   return warp_sums[wid] + inc - v;
 }
 
-// Pass 1: per-tile sums.
-__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* __restrict__ in, uint64_t n,
+// One launch that fills up to six device buffers with a byte value each (replaces a train of
+// cudaMemsetAsync calls: every memset is its own engine hand-over on the stream).
+struct FillJob {
+  void* ptr[6];
+  unsigned long long bytes[6];  // multiples of 16 (buffers are over-allocated accordingly)
+  unsigned int value[6];        // 32-bit pattern
+  int n;
+};
+
+__global__ void __launch_bounds__(256) fill_buffers_kernel(const FillJob job) {
+  for (int j = 0; j < job.n; j++) {
+    uint4* p = reinterpret_cast<uint4*>(job.ptr[j]);
+    const unsigned long long n16 = job.bytes[j] >> 4;
+    const unsigned int v = job.value[j];
+    const uint4 val = make_uint4(v, v, v, v);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+      p[i] = val;
+  }
+}
+
+// Element count of a scan: a host value, or (n_ptr != nullptr) a device counter clamped to n.
+__device__ __forceinline__ uint64_t scan_count(const unsigned long long* n_ptr, uint64_t n) {
+  if (!n_ptr) return n;
+  const unsigned long long v = *n_ptr;
+  return v < n ? v : n;
+}
+
+// Pass 1: per-tile sums (grid-stride over tiles, so the launch does not depend on n).
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* __restrict__ in,
+                                                               const unsigned long long* n_ptr, uint64_t n_host,
                                                                uint64_t* __restrict__ tile_sums) {
   __shared__ uint64_t warp_sums[kScanThreads / 32];
   __shared__ uint64_t total;
-  const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
-  uint64_t s = 0;
+  const uint64_t n = scan_count(n_ptr, n_host);
+  const uint64_t ntiles = (n + kScanTile - 1) / kScanTile;
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint64_t base = tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    uint64_t s = 0;
 #pragma unroll
-  for (int i = 0; i < kScanItems; i++)
-    if (base + i < n) s += in[base + i];
-  block_exclusive_scan_u64(s, &total, warp_sums);
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+    for (int i = 0; i < kScanItems; i++)
+      if (base + i < n) s += in[base + i];
+    block_exclusive_scan_u64(s, &total, warp_sums);
+    if (threadIdx.x == 0) tile_sums[tile] = total;
+    __syncthreads();
+  }
 }
 
 // Pass 2: one block scans the tile sums in place (exclusive); writes the grand total.
-__global__ void __launch_bounds__(kScanThreads) scan_tile_offsets(uint64_t* __restrict__ tile_sums, uint64_t ntiles,
+__global__ void __launch_bounds__(kScanThreads) scan_tile_offsets(uint64_t* __restrict__ tile_sums,
+                                                                  const unsigned long long* n_ptr, uint64_t n_host,
                                                                   uint64_t* __restrict__ grand_total) {
   __shared__ uint64_t warp_sums[kScanThreads / 32];
   __shared__ uint64_t total;
+  const uint64_t ntiles = (scan_count(n_ptr, n_host) + kScanTile - 1) / kScanTile;
   uint64_t carry = 0;
   for (uint64_t start = 0; start < ntiles; start += kScanThreads) {
     const uint64_t i = start + threadIdx.x;
@@ -70,25 +106,32 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_offsets(uint64_t* __re
 // Pass 3: rescan each tile with its offset.  out[n] (one past the end) receives the total
 // when write_end is set, so out can serve directly as a CSR offsets array.
 template <typename OutT>
-__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* __restrict__ in, uint64_t n,
+__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* __restrict__ in,
+                                                           const unsigned long long* n_ptr, uint64_t n_host,
                                                            const uint64_t* __restrict__ tile_offs,
                                                            OutT* __restrict__ out, int write_end) {
   __shared__ uint64_t warp_sums[kScanThreads / 32];
   __shared__ uint64_t total;
-  const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
-  uint32_t v[kScanItems];
-  uint64_t s = 0;
+  const uint64_t n = scan_count(n_ptr, n_host);
+  const uint64_t ntiles = (n + kScanTile - 1) / kScanTile;
+  if (n == 0 && write_end && blockIdx.x == 0 && threadIdx.x == 0) out[0] = (OutT)0;
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint64_t base = tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint64_t s = 0;
 #pragma unroll
-  for (int i = 0; i < kScanItems; i++) {
-    v[i] = base + i < n ? in[base + i] : 0u;
-    s += v[i];
-  }
-  uint64_t run = tile_offs[blockIdx.x] + block_exclusive_scan_u64(s, &total, warp_sums);
+    for (int i = 0; i < kScanItems; i++) {
+      v[i] = base + i < n ? in[base + i] : 0u;
+      s += v[i];
+    }
+    uint64_t run = tile_offs[tile] + block_exclusive_scan_u64(s, &total, warp_sums);
 #pragma unroll
-  for (int i = 0; i < kScanItems; i++) {
-    if (base + i < n) out[base + i] = (OutT)run;
-    run += v[i];
-    if (write_end && base + i + 1 == n) out[n] = (OutT)run;
+    for (int i = 0; i < kScanItems; i++) {
+      if (base + i < n) out[base + i] = (OutT)run;
+      run += v[i];
+      if (write_end && base + i + 1 == n) out[n] = (OutT)run;
+    }
+    __syncthreads();
   }
 }
 

@@ -117,6 +117,9 @@ class HotPath:
     def run(self):
         self._check(self._lib.msc_run(self._ctx))
 
+    def rebuild_and_run(self, what: int = 3):
+        self._check(self._lib.msc_rebuild_and_run(self._ctx, what))
+
     def best_device(self) -> _DevArray:
         ptr = self._lib.msc_best_device(self._ctx)
         if not ptr:
