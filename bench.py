@@ -236,7 +236,7 @@ def run_ours(args, rank, local_rank, world):
 
     w = dict(WORK)
     w.update(num_read=args.reads, num_gene=args.genes * world)  # weak scaling: the database grows with N
-    syn = gendat.generate(**w)
+    syn = gendat.generate(n_shards=world, **w)
     lo, hi = mdist.shard_targets(syn.target_offs, world)[rank]
     t_lo, t_hi = int(syn.target_offs[lo]), int(syn.target_offs[hi])
     shard_bases = t_hi - t_lo
@@ -279,11 +279,9 @@ def run_ours(args, rank, local_rank, world):
             # confirm, combine: one enqueue, one synchronisation
             hp.rebuild_and_run(3)
             return
-        hp.rebuild(3)
-        hp.screen()
-        hp.confirm()
-        exchange_best()
-        hp.combine()
+        hp.run_stages(3, 1 | 2)   # rebuild + screen + confirm, one sync
+        exchange_best()           # NCCL MIN all-reduce of the per-read best mismatch count
+        hp.run_stages(0, 4)       # combine
 
     def step_e2e():
         hp.set_reads_ptr(rd_a.data_ptr(), rd_o.data_ptr(), n_reads)
@@ -291,18 +289,22 @@ def run_ours(args, rank, local_rank, world):
         if world == 1:
             hp.run()
         else:
-            hp.screen()
-            hp.confirm()
+            hp.run_stages(0, 1 | 2)
             exchange_best()
-            hp.combine()
+            hp.run_stages(0, 4)
         if world > 1:
             holder, n = hp.matches_device()
             local = torch.as_tensor(holder, device=dev) if n else torch.zeros(0, dtype=torch.int32, device=dev)
             allm = mdist.gather_matches(local, gene_offset=lo)
             if allm is not None:
-                return int(allm.cpu().shape[0])
+                last_gathered[0] = allm.cpu().numpy()
+                return int(last_gathered[0].shape[0])
             return 0
-        return len(hp.fetch())
+        return hp.fetch_into(res_buf.data_ptr(), res_cap)
+
+    last_gathered = [None]
+    res_cap = 4 << 20   # pinned result buffer: 4M matches
+    res_buf = torch.empty(res_cap * 16, dtype=torch.uint8).pin_memory()
 
     def barrier():
         if world > 1:
@@ -376,6 +378,20 @@ def run_ours(args, rank, local_rank, world):
                    "candidates": int(n_cand), "bloom_pass": int(st["bloom_pass"]), "pairs": int(st["n_pairs"]),
                    "passing_pairs": int(st["n_pass"]), "matches": int(st["n_matches"]), "matches_e2e_gathered": n_match_e2e},
     }
+    if args.verify and world > 1:
+        # sharded result == single-GPU result on the whole database (rank 0 recomputes it unsharded)
+        if rank == 0:
+            hv = HotPath(cfg, device=local_rank)
+            hv.set_reads((syn.read_ascii, syn.read_offs))
+            hv.set_targets((syn.target_ascii, syn.target_offs))
+            hv.run()
+            ref = hv.fetch()
+            hv.close()
+            got = last_gathered[0].astype(np.int64)
+            got = got[np.lexsort((got[:, 2], got[:, 1], got[:, 0]))]
+            want = np.stack([ref["read_id"], ref["gene_id"], ref["pos"], ref["nx"]], axis=1).astype(np.int64)
+            line["verify_sharded_equals_unsharded"] = bool(got.shape == want.shape and np.array_equal(got, want))
+            line["verify_matches"] = int(want.shape[0])
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(syn, budget_s=args.cpu_budget)
@@ -398,6 +414,7 @@ def main():
     ap.add_argument("--reads", type=int, default=WORK["num_read"], help="debug only: shrink the workload")
     ap.add_argument("--genes", type=int, default=WORK["num_gene"], help="debug only: targets per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="N>1: compare the gathered sharded result with an unsharded run")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

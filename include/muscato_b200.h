@@ -139,9 +139,13 @@ int msc_combine(msc_ctx* ctx);
  * the compacted matches of all ranks over NCCL without a host round trip. */
 void* msc_matches_device(msc_ctx* ctx, uint64_t* n);
 
-/* Copy the surviving matches to the host, ordered by (read_id, gene_id, pos).
- * *out is owned by the library: release with msc_free. */
+/* Copy the surviving matches to the host, ordered by (read_id, gene_id, pos) (the order is
+ * established on the device).  *out is owned by the library: release with msc_free. */
 int msc_fetch_matches(msc_ctx* ctx, msc_match** out, uint64_t* n);
+
+/* Same, into a caller-owned buffer of `capacity` records (e.g. pinned memory: no staging copy).
+ * *n receives the number of matches; MSC_ERR_NOMEM if they do not fit. */
+int msc_fetch_matches_into(msc_ctx* ctx, msc_match* dst, uint64_t capacity, uint64_t* n);
 
 /* msc_screen + msc_confirm + msc_combine enqueued back to back on the context's stream with a
  * single host synchronisation at the end (intermediate counts stay on the device). */
@@ -150,6 +154,12 @@ int msc_run(msc_ctx* ctx);
 /* msc_rebuild(what) followed by msc_run, again with a single synchronisation: one full pass of
  * the hot path over inputs that are already resident in HBM (keep_ascii=1). */
 int msc_rebuild_and_run(msc_ctx* ctx, int what);
+
+/* General form: optional rebuild (what = 0..3) followed by any prefix-consistent subset of the
+ * stages, one synchronisation.  A multi-GPU host runs SCREEN|CONFIRM, all-reduces
+ * msc_best_device over the ranks, then runs COMBINE. */
+enum { MSC_STAGE_SCREEN = 1, MSC_STAGE_CONFIRM = 2, MSC_STAGE_COMBINE = 4 };
+int msc_run_stages(msc_ctx* ctx, int rebuild_what, int stages);
 
 int msc_get_stats(const msc_ctx* ctx, msc_stats* out);
 void msc_reset_stats(msc_ctx* ctx);

@@ -18,6 +18,7 @@ MSC_MAX_READ_LENGTH = 1024
 MSC_OK, MSC_ERR_CONFIG, MSC_ERR_INPUT, MSC_ERR_CUDA, MSC_ERR_STATE, MSC_ERR_NOMEM, MSC_ERR_IO = range(7)
 MSC_MATCH_FIRST, MSC_MATCH_BEST = 0, 1
 MSC_NO_MATCH = 0x7F7F7F7F
+MSC_STAGE_SCREEN, MSC_STAGE_CONFIRM, MSC_STAGE_COMBINE = 1, 2, 4
 
 
 class msc_config(C.Structure):
@@ -81,8 +82,10 @@ _SIGS = [
     ("msc_combine", C.c_int, [C.c_void_p]),
     ("msc_matches_device", C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),
     ("msc_fetch_matches", C.c_int, [C.c_void_p, C.POINTER(C.POINTER(msc_match)), C.POINTER(C.c_uint64)]),
+    ("msc_fetch_matches_into", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     ("msc_run", C.c_int, [C.c_void_p]),
     ("msc_rebuild_and_run", C.c_int, [C.c_void_p, C.c_int]),
+    ("msc_run_stages", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ("msc_get_stats", C.c_int, [C.c_void_p, C.POINTER(msc_stats)]),
     ("msc_reset_stats", None, [C.c_void_p]),
     ("msc_free", None, [C.c_void_p]),

@@ -62,6 +62,7 @@ struct DevBuf {
 // Device counter block (unsigned long long each).
 enum Counter {
   C_NKEYS = 0, C_NGROUPS, C_NDUP, C_SCRATCH, C_NCAND, C_BLOOMPASS, C_NMATCH, C_NPASS, C_NOVER, C_NOUT, C_NPAIRS,
+  C_PAD0, C_NLONG,  // C_NLONG at an even index
   C_COUNT = 16  // groups that are cleared together start at even indices (16-byte aligned)
 };
 
@@ -103,9 +104,16 @@ struct msc_ctx {
   // matches
   uint64_t n_match_pre = 0, n_match = 0;
   bool have_confirm = false, have_combine = false;
-  DevBuf match_pre, best, rcount, rstart, rfill, match_out;
+  DevBuf match_pre, best, rcount, rstart, rfill, match_out, long_list;
+  // confirm kernel mode 2 (MaxMatches overflow groups diverted to the host)
+  struct {
+    const uint8_t* slot_over = nullptr;
+    uint4* over = nullptr;
+    uint64_t over_cap = 0;
+  } pair_mode2;
   // misc
-  DevBuf counters, tile_sums, nmiss;
+  DevBuf counters, tile_sums, scan_state, nmiss;
+  uint32_t scan_epoch = 0;
   unsigned long long* h_counters = nullptr;  // pinned mirror
   // MSC_TRACE=1: an event after every launch, per-launch device times printed at each sync
   bool trace = false;
@@ -188,15 +196,19 @@ template <typename OutT>
 int enqueue_exclusive_scan(msc_ctx* ctx, const uint32_t* in, const unsigned long long* n_ptr, uint64_t n_host, OutT* out,
                            bool write_end, unsigned long long* total) {
   const uint64_t max_tiles = std::max<uint64_t>(1, (n_host + kScanTile - 1) / kScanTile);
-  CK(ctx->tile_sums.reserve(max_tiles * sizeof(uint64_t)));
+  const size_t had = ctx->tile_sums.cap;
+  CK(ctx->tile_sums.reserve((max_tiles + 1) * sizeof(uint64_t)));
+  ctx->scan_epoch = (ctx->scan_epoch + 1) % kScanEpochs;
+  if (ctx->tile_sums.cap != had || ctx->scan_epoch == 0) {
+    // fresh (or epoch-wrapped) descriptor array: make every descriptor invalid once
+    CK(cudaMemsetAsync(ctx->tile_sums.p, 0, ctx->tile_sums.cap, ctx->stream));
+    if (ctx->scan_epoch == 0) ctx->scan_epoch = 1;
+  }
   const unsigned grid = (unsigned)std::min<uint64_t>(max_tiles, (uint64_t)ctx->sm_count * 8);
-  scan_tile_sums<<<grid, kScanThreads, 0, ctx->stream>>>(in, n_ptr, n_host, ctx->tile_sums.as<uint64_t>());
-  LAUNCH_CHECK();
-  scan_tile_offsets<<<1, kScanThreads, 0, ctx->stream>>>(ctx->tile_sums.as<uint64_t>(), n_ptr, n_host,
-                                                         reinterpret_cast<uint64_t*>(total));
-  LAUNCH_CHECK();
-  scan_apply<OutT><<<grid, kScanThreads, 0, ctx->stream>>>(in, n_ptr, n_host, ctx->tile_sums.as<uint64_t>(), out,
-                                                           write_end ? 1 : 0);
+  scan_onepass_kernel<OutT><<<grid, kScanThreads, 0, ctx->stream>>>(in, n_ptr, n_host, out, write_end ? 1 : 0, total,
+                                                                    ctx->tile_sums.as<uint64_t>(),
+                                                                    ctx->scan_state.as<unsigned long long>(),
+                                                                    ctx->scan_epoch);
   LAUNCH_CHECK();
   return MSC_OK;
 }
@@ -436,7 +448,19 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   a.n_pass = ctx->ctr(C_NPASS);
   a.best = ctx->best.as<uint32_t>();
   a.mode = mode;
-  confirm_pairs_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->win, a);
+  if (mode == 2) {
+    a.slot_over = ctx->pair_mode2.slot_over;
+    a.fps = ctx->fps.as<uint64_t>();
+    a.tab_fp = ctx->tab_fp.as<uint64_t>();
+    a.lg_slots = ctx->lg_slots;
+    a.over = ctx->pair_mode2.over;
+    a.over_cap = ctx->pair_mode2.over_cap;
+    a.n_over_inst = ctx->ctr(C_NLONG);
+  }
+  const unsigned cgrid = (unsigned)ctx->sm_count * 8;
+  if (mode == 0) confirm_pairs_kernel<0><<<cgrid, 256, 0, ctx->stream>>>(ctx->win, a);
+  else if (mode == 1) confirm_pairs_kernel<1><<<cgrid, 256, 0, ctx->stream>>>(ctx->win, a);
+  else confirm_pairs_kernel<2><<<cgrid, 256, 0, ctx->stream>>>(ctx->win, a);
   LAUNCH_CHECK();
   if (mode == 0) {
     // MaxMatches pre-check (cmd/muscato_confirm/main.go:233-242, :424-448): truncation can only
@@ -457,11 +481,13 @@ int enqueue_combine(msc_ctx* ctx) {
   CK(ctx->rstart.reserve((U + 2) * sizeof(uint32_t)));
   CK(ctx->rfill.reserve((U + 1) * sizeof(uint32_t)));
   CK(ctx->match_out.reserve((mcap + 1) * sizeof(uint4)));
+  CK(ctx->long_list.reserve((U + 1) * sizeof(uint32_t)));
   CK(cudaEventRecord(ctx->ev[EV_COMB0], ctx->stream));
   {
     Filler f;
     f.add(ctx->rcount.p, (U + 1) * sizeof(uint32_t));
     f.add(ctx->rfill.p, (U + 1) * sizeof(uint32_t));
+    f.add(ctx->ctr(C_NLONG), 2 * sizeof(unsigned long long));
     RC(enqueue_fill(ctx, f));
   }
   const unsigned g = (unsigned)ctx->sm_count * 8;
@@ -476,6 +502,16 @@ int enqueue_combine(msc_ctx* ctx) {
                                                      ctx->rstart.as<uint32_t>(), ctx->rfill.as<uint32_t>(),
                                                      ctx->match_out.as<uint4>());
   LAUNCH_CHECK();
+  if (U) {
+    // deterministic (gene, pos) order inside every read group; match_pre is dead and serves as scratch
+    segment_sort_short_kernel<<<grid_for(U, 256), 256, 0, ctx->stream>>>(
+        ctx->match_out.as<uint4>(), ctx->rstart.as<uint32_t>(), U, ctx->long_list.as<uint32_t>(), ctx->ctr(C_NLONG));
+    LAUNCH_CHECK();
+    segment_rank_sort_kernel<<<g, kRankThreads, 0, ctx->stream>>>(ctx->match_out.as<uint4>(), ctx->match_pre.as<uint4>(),
+                                                         ctx->rstart.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
+                                                         ctx->ctr(C_NLONG));
+    LAUNCH_CHECK();
+  }
   CK(cudaEventRecord(ctx->ev[EV_COMB1], ctx->stream));
   return MSC_OK;
 }
@@ -483,7 +519,7 @@ int enqueue_combine(msc_ctx* ctx) {
 // ---- completion: read the counter block, grow buffers that were too small --------------------
 // finish_* return MSC_OK, an error, or NEED_RETRY when a buffer was grown and the caller must
 // enqueue again.
-enum { NEED_RETRY = -1 };
+enum { NEED_RETRY = -1, NEED_RECOMBINE = -2 };
 
 int finish_scan(msc_ctx* ctx) {
   const float ms = elapsed(ctx, EV_SCAN0, EV_SCAN1);
@@ -521,6 +557,10 @@ int finish_pairs(msc_ctx* ctx, DevBuf& outbuf, uint64_t* n_out) {
   return MSC_OK;
 }
 
+int mark_expand_start(msc_ctx* ctx);
+
+#include "maxmatches.inc"
+
 int finish_confirm(msc_ctx* ctx) {
   RC(finish_pairs(ctx, ctx->match_pre, &ctx->n_match_pre));
   ctx->st.ms_expand += elapsed(ctx, EV_SCAN1, EV_EXPAND1);
@@ -529,11 +569,17 @@ int finish_confirm(msc_ctx* ctx) {
   ctx->st.n_pass = ctx->h_counters[C_NPASS];
   ctx->st.n_matches_pre = ctx->n_match_pre;
   ctx->st.n_overflow_groups = ctx->h_counters[C_NOVER];
-  if (ctx->st.n_overflow_groups)
-    return ctx->fail(MSC_ERR_CONFIG,
-                     "%llu key group(s) exceed MaxMatches=%lld passing pairs; the order-dependent truncation of "
-                     "cmd/muscato_confirm/main.go:424-448 is not implemented yet -- raise MaxMatches",
-                     (unsigned long long)ctx->st.n_overflow_groups, (long long)ctx->cfg.max_matches);
+  if (ctx->st.n_overflow_groups) {
+    // Some key group holds more passing pairs than MaxMatches: replay the reference's
+    // order-dependent truncation for those groups (rare path, host assisted).
+    const float ms_e = ctx->st.ms_expand, ms_c = ctx->st.ms_confirm;
+    RC(resolve_maxmatches_overflow(ctx));
+    ctx->st.ms_expand = ms_e;
+    ctx->st.ms_confirm = ms_c;
+    ctx->have_confirm = true;
+    ctx->have_combine = false;
+    return NEED_RECOMBINE;  // a combine enqueued together with this confirm saw the untruncated set
+  }
   ctx->have_confirm = true;
   ctx->have_combine = false;
   return MSC_OK;
@@ -576,6 +622,13 @@ int run_pipeline(msc_ctx* ctx, int rebuild_what, bool do_scan, bool do_confirm, 
     int rc = MSC_OK;
     if (do_scan) rc = finish_scan(ctx);
     if (rc == MSC_OK && do_confirm) rc = finish_confirm(ctx);
+    if (rc == NEED_RECOMBINE) {
+      rc = MSC_OK;
+      if (do_combine) {
+        RC(enqueue_combine(ctx));
+        RC(sync_counters(ctx));
+      }
+    }
     if (rc == MSC_OK && do_combine) rc = finish_combine(ctx);
     if (rc != NEED_RETRY) return rc;
     if (!ctx->have_cand) do_scan = true;  // the candidate buffer was grown: scan again
@@ -657,6 +710,8 @@ msc_ctx* msc_create(const msc_config* config, char* errbuf, uint64_t errlen) {
   ok = ok && ctx->nmiss.reserve(nm.size() * sizeof(int32_t)) == cudaSuccess;
   ok = ok && cudaMemcpy(ctx->nmiss.p, nm.data(), nm.size() * sizeof(int32_t), cudaMemcpyHostToDevice) == cudaSuccess;
   ok = ok && cudaMemset(ctx->counters.p, 0, C_COUNT * sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && ctx->scan_state.reserve(2 * sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaMemset(ctx->scan_state.p, 0, 2 * sizeof(unsigned long long)) == cudaSuccess;
   // every event is recorded once so that cudaEventElapsedTime never sees a virgin event
   for (int i = 0; ok && i < EV_COUNT; i++) ok = cudaEventRecord(ctx->ev[i], ctx->stream) == cudaSuccess;
   ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
@@ -677,7 +732,7 @@ void msc_destroy(msc_ctx* ctx) {
                     &ctx->items,       &ctx->dup_slot,  &ctx->fps,      &ctx->tg_ascii,  &ctx->tg_off,    &ctx->tg_words,
                     &ctx->tg_x,        &ctx->xsum,      &ctx->cand,     &ctx->cinfo,     &ctx->sizes,     &ctx->pstart,
                     &ctx->block_first, &ctx->match_pre, &ctx->best,     &ctx->rcount,    &ctx->rstart,    &ctx->rfill,
-                    &ctx->match_out,   &ctx->counters,  &ctx->tile_sums, &ctx->nmiss};
+                    &ctx->match_out,   &ctx->long_list, &ctx->counters,  &ctx->tile_sums, &ctx->scan_state, &ctx->nmiss};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   for (auto& e : ctx->ev)
@@ -828,42 +883,50 @@ int msc_run(msc_ctx* ctx) {
   return run_pipeline(ctx, 0, true, true, true);
 }
 
-int msc_rebuild_and_run(msc_ctx* ctx, int what) {
+int msc_run_stages(msc_ctx* ctx, int rebuild_what, int stages) {
   if (!ctx) return MSC_ERR_STATE;
-  if (!ctx->have_reads || !ctx->have_targets)
-    return ctx->fail(MSC_ERR_STATE, "msc_rebuild_and_run: set reads and targets first");
-  if ((what & 3) && !ctx->cfg.keep_ascii) return ctx->fail(MSC_ERR_STATE, "msc_rebuild_and_run needs keep_ascii=1");
+  if (!ctx->have_reads || !ctx->have_targets) return ctx->fail(MSC_ERR_STATE, "msc_run_stages: set reads and targets first");
+  if ((rebuild_what & 3) && !ctx->cfg.keep_ascii) return ctx->fail(MSC_ERR_STATE, "rebuild needs keep_ascii=1");
+  const bool scan = stages & MSC_STAGE_SCREEN, conf = stages & MSC_STAGE_CONFIRM, comb = stages & MSC_STAGE_COMBINE;
+  if (conf && !scan && (!ctx->have_cand || (rebuild_what & 3)))
+    return ctx->fail(MSC_ERR_STATE, "msc_run_stages: confirm needs candidates (run the screen stage)");
+  if (comb && !conf && (!ctx->have_confirm || scan || (rebuild_what & 3)))
+    return ctx->fail(MSC_ERR_STATE, "msc_run_stages: combine needs confirmed pairs");
   CK(cudaSetDevice(ctx->device));
-  return run_pipeline(ctx, what & 3, true, true, true);
+  return run_pipeline(ctx, rebuild_what & 3, scan, conf, comb);
+}
+
+int msc_rebuild_and_run(msc_ctx* ctx, int what) {
+  return msc_run_stages(ctx, what, MSC_STAGE_SCREEN | MSC_STAGE_CONFIRM | MSC_STAGE_COMBINE);
+}
+
+int msc_fetch_matches_into(msc_ctx* ctx, msc_match* dst, uint64_t capacity, uint64_t* n) {
+  if (!ctx || !n) return MSC_ERR_STATE;
+  if (!ctx->have_combine) return ctx->fail(MSC_ERR_STATE, "msc_fetch_matches: run msc_combine first");
+  CK(cudaSetDevice(ctx->device));
+  *n = ctx->n_match;
+  if (ctx->n_match > capacity)
+    return ctx->fail(MSC_ERR_NOMEM, "msc_fetch_matches_into: %llu matches do not fit %llu slots",
+                     (unsigned long long)ctx->n_match, (unsigned long long)capacity);
+  if (ctx->n_match) {
+    if (!dst) return ctx->fail(MSC_ERR_INPUT, "msc_fetch_matches_into: NULL destination");
+    static_assert(sizeof(msc_match) == sizeof(uint4), "msc_match layout");
+    CK(cudaMemcpyAsync(dst, ctx->match_out.p, ctx->n_match * sizeof(msc_match), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->st.d2h_bytes += ctx->n_match * sizeof(msc_match);
+  }
+  return MSC_OK;
 }
 
 int msc_fetch_matches(msc_ctx* ctx, msc_match** out, uint64_t* n) {
   if (!ctx || !out || !n) return MSC_ERR_STATE;
   if (!ctx->have_combine) return ctx->fail(MSC_ERR_STATE, "msc_fetch_matches: run msc_combine first");
-  CK(cudaSetDevice(ctx->device));
-  *n = ctx->n_match;
   msc_match* h = (msc_match*)malloc(std::max<uint64_t>(1, ctx->n_match) * sizeof(msc_match));
   if (!h) return ctx->fail(MSC_ERR_NOMEM, "host allocation failed");
-  if (ctx->n_match) {
-    static_assert(sizeof(msc_match) == sizeof(uint4), "msc_match layout");
-    cudaError_t e = cudaMemcpyAsync(h, ctx->match_out.p, ctx->n_match * sizeof(msc_match), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) {
-      free(h);
-      return ctx->fail(MSC_ERR_CUDA, "D2H of matches failed: %s", cudaGetErrorString(e));
-    }
-    ctx->st.d2h_bytes += ctx->n_match * sizeof(msc_match);
-    // The device groups by read (counting sort on read_id); order inside a read group is made
-    // deterministic here.  Groups are short, so this is a linear pass in practice.
-    auto by_gene_pos = [](const msc_match& a, const msc_match& b) {
-      return a.gene_id != b.gene_id ? a.gene_id < b.gene_id : a.pos < b.pos;
-    };
-    for (uint64_t i = 0; i < ctx->n_match;) {
-      uint64_t j = i + 1;
-      while (j < ctx->n_match && h[j].read_id == h[i].read_id) j++;
-      if (j - i > 1) std::sort(h + i, h + j, by_gene_pos);
-      i = j;
-    }
+  const int rc = msc_fetch_matches_into(ctx, h, std::max<uint64_t>(1, ctx->n_match), n);
+  if (rc) {
+    free(h);
+    return rc;
   }
   *out = h;
   return MSC_OK;

@@ -31,6 +31,106 @@ __global__ void __launch_bounds__(256) combine_scatter_kernel(const uint4* __res
   }
 }
 
+// Order inside each read group: (gene, pos) ascending, so that the library's output is
+// deterministic without a host-side sort.  Short groups (the norm) are sorted by one thread in
+// registers; longer ones are queued for segment_rank_sort_kernel.
+constexpr int kShortSegment = 16;
+
+__device__ __forceinline__ bool match_less(const uint4& a, const uint4& b) {
+  return a.y != b.y ? a.y < b.y : a.z < b.z;
+}
+
+__global__ void __launch_bounds__(256) segment_sort_short_kernel(uint4* __restrict__ m,
+                                                                 const uint32_t* __restrict__ rstart, uint64_t n_reads,
+                                                                 uint32_t* __restrict__ long_list,
+                                                                 unsigned long long* __restrict__ n_long) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const uint32_t lo = rstart[r], hi = rstart[r + 1];
+  const uint32_t n = hi - lo;
+  if (n <= 1) return;
+  if (n > kShortSegment) {
+    long_list[atomicAdd(n_long, 1ull)] = (uint32_t)r;
+    return;
+  }
+  uint4 v[kShortSegment];
+#pragma unroll
+  for (int i = 0; i < kShortSegment; i++)
+    if (i < (int)n) v[i] = m[lo + i];
+  // insertion sort with static indexing (odd-even transposition keeps v[] in registers)
+#pragma unroll
+  for (int pass = 0; pass < kShortSegment; pass++) {
+#pragma unroll
+    for (int i = pass & 1; i + 1 < kShortSegment; i += 2) {
+      if (i + 1 < (int)n && match_less(v[i + 1], v[i])) {
+        const uint4 t = v[i];
+        v[i] = v[i + 1];
+        v[i + 1] = t;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kShortSegment; i++)
+    if (i < (int)n) m[lo + i] = v[i];
+}
+
+// One block per long read group: every element counts the elements that precede it (keys are
+// unique inside a group after de-duplication) and is written at that rank into `scratch`, then
+// the sorted segment is copied back.  Groups of up to kRankSmem members are ranked out of shared
+// memory (broadcast reads); larger ones fall back to global memory.
+constexpr int kRankThreads = 256;
+constexpr int kRankSmem = 4096;
+
+__global__ void __launch_bounds__(kRankThreads) segment_rank_sort_kernel(
+    uint4* __restrict__ m, uint4* __restrict__ scratch, const uint32_t* __restrict__ rstart,
+    const uint32_t* __restrict__ long_list, const unsigned long long* __restrict__ n_long) {
+  __shared__ uint64_t keys[kRankSmem];
+  const uint64_t nl = *n_long;
+  for (uint64_t s = blockIdx.x; s < nl; s += gridDim.x) {
+    const uint32_t r = long_list[s];
+    const uint32_t lo = rstart[r], hi = rstart[r + 1], n = hi - lo;
+    if (n <= (uint32_t)kRankSmem) {
+      for (uint32_t i = threadIdx.x; i < n; i += kRankThreads) {
+        const uint4 a = m[lo + i];
+        keys[i] = ((uint64_t)a.y << 32) | (uint64_t)a.z;
+      }
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < n; i += kRankThreads) {
+        const uint64_t k = keys[i];
+        uint32_t rank = 0;
+#pragma unroll 8
+        for (uint32_t j = 0; j < n; j++) rank += keys[j] < k ? 1u : 0u;
+        scratch[lo + rank] = m[lo + i];
+      }
+    } else {
+      for (uint32_t i = lo + threadIdx.x; i < hi; i += kRankThreads) {
+        const uint4 a = m[i];
+        uint32_t rank = 0;
+        for (uint32_t j = lo; j < hi; j++) rank += match_less(m[j], a) ? 1u : 0u;
+        scratch[lo + rank] = a;
+      }
+    }
+    __syncthreads();
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += kRankThreads) m[i] = scratch[i];
+    __syncthreads();
+  }
+}
+
+// Flag the key groups whose passing-pair count exceeds MaxMatches (mode-2 input).
+__global__ void __launch_bounds__(256) overflow_flag_kernel(const uint32_t* __restrict__ pass_cnt, uint64_t n_slots,
+                                                            unsigned long long max_matches,
+                                                            uint8_t* __restrict__ slot_over) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_slots) slot_over[i] = (unsigned long long)pass_cnt[i] > max_matches ? 1 : 0;
+}
+
+// best[read] = min nx over a match list (used after the host merged truncated groups back in).
+__global__ void __launch_bounds__(256) best_from_matches_kernel(const uint4* __restrict__ m, uint64_t n,
+                                                                uint32_t* __restrict__ best) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicMin(best + m[i].x, m[i].w);
+}
+
 // Number of key groups whose passing-pair count exceeds MaxMatches (the only groups for
 // which qinsert / "first" truncation, cmd/muscato_confirm/main.go:233-242 and :424-448, can
 // drop anything).

@@ -120,6 +120,12 @@ __device__ __forceinline__ unsigned long long warp_agg_inc(unsigned long long* c
   return base + (unsigned long long)__popc(active & ((1u << lane) - 1u));
 }
 
+// Warp-aggregated counter bump without a return value (compiles to a fire-and-forget RED).
+__device__ __forceinline__ void warp_agg_count(unsigned long long* counter) {
+  const unsigned active = __activemask();
+  if ((int)(threadIdx.x & 31u) == __ffs(active) - 1) atomicAdd(counter, (unsigned long long)__popc(active));
+}
+
 // First index i in [lo, hi) with a[i] > v  (a ascending).
 template <typename T>
 __device__ __forceinline__ uint64_t upper_bound_dev(const T* __restrict__ a, uint64_t lo, uint64_t hi, T v) {

@@ -89,7 +89,20 @@ struct ConfirmArgs {
   unsigned long long* n_match;
   unsigned long long* n_pass;
   uint32_t* best;  // per read min nx
-  int mode;        // 0 = confirm, 1 = dump exact-key candidates as (gene, p, read, window)
+  int mode;        // 0 = confirm, 1 = dump exact-key candidates as (gene, p, read, window),
+                   // 2 = confirm with MaxMatches overflow groups diverted (see below)
+  // mode 2 only: key groups whose passing-pair count exceeds MaxMatches are flagged in
+  // slot_over.  A passing pair found through such a group is written to `over` as
+  // (read, gene, pos, nx | window<<16) for the host-side emulation of the reference's
+  // order-dependent truncation (cmd/muscato_confirm/main.go:233-242, :424-448); the
+  // cross-window de-duplication only counts windows whose group is not flagged.
+  const uint8_t* slot_over;
+  const uint64_t* fps;     // per (read, window) key fingerprint (0 = window not valid)
+  const uint64_t* tab_fp;
+  int lg_slots;
+  uint4* over;
+  unsigned long long over_cap;
+  unsigned long long* n_over_inst;
 };
 
 __device__ __forceinline__ bool tg_range_has_x(const uint32_t* __restrict__ xsum, uint64_t w0, uint64_t w1) {
@@ -105,10 +118,10 @@ __device__ __forceinline__ bool tg_range_has_x(const uint32_t* __restrict__ xsum
   return false;
 }
 
-// One (candidate, read) pair.
-__device__ __forceinline__ void confirm_one_pair(const WinCfg& cfg, const ConfirmArgs& a, uint64_t i, uint64_t clo,
-                                                 uint64_t chi) {
-  const uint64_t c = upper_bound_dev<uint64_t>(a.pstart, clo, chi + 1, i) - 1;
+// One (candidate, read) pair; c = index of its candidate.  MODE is a compile-time copy of
+// ConfirmArgs::mode so that the hot mode-0 kernel carries none of the tap / overflow code.
+template <int MODE>
+__device__ __forceinline__ void confirm_one_pair(const WinCfg& cfg, const ConfirmArgs& a, uint64_t i, uint64_t c) {
   const uint2 cd = __ldg(a.cand + c);
   const uint2 ci = __ldg(a.cinfo + c);
   const uint32_t slot = cd.x;
@@ -148,7 +161,7 @@ __device__ __forceinline__ void confirm_one_pair(const WinCfg& cfg, const Confir
       if (rxm != txm) return;
     }
   }
-  if (a.mode == 1) {
+  if (MODE == 1) {
     const unsigned long long at = warp_agg_inc(a.n_match);
     if (at < a.match_cap) a.matches[at] = make_uint4((uint32_t)g, (uint32_t)p, r, (uint32_t)k);
     return;
@@ -185,9 +198,11 @@ __device__ __forceinline__ void confirm_one_pair(const WinCfg& cfg, const Confir
 
   // The pair passes through window k.
   atomicAdd(a.pass_cnt + slot, 1u);
-  {
-    const unsigned long long np = warp_agg_inc(a.n_pass);
-    (void)np;
+  (void)warp_agg_inc(a.n_pass);
+  if (MODE == 2 && a.slot_over[slot]) {
+    const unsigned long long at = warp_agg_inc(a.n_over_inst);
+    if (at < a.over_cap) a.over[at] = make_uint4(r, (uint32_t)g, (uint32_t)pos, (uint32_t)nx | ((uint32_t)k << 16));
+    return;
   }
 
   // Cross-window de-duplication: emit only through the lowest window index that delivers
@@ -207,6 +222,11 @@ __device__ __forceinline__ void confirm_one_pair(const WinCfg& cfg, const Confir
       const uint64_t txm = tx ? (extract32(a.tg_x, gstart + (uint64_t)q1b) & kmask) : 0ull;
       if (rxm != txm) continue;
     }
+    if (MODE == 2) {
+      // a window whose key group is subject to truncation does not "own" the pair
+      const int64_t s2 = table_find(a.tab_fp, a.lg_slots, __ldg(a.fps + (uint64_t)r * cfg.nwin + k2));
+      if (s2 >= 0 && a.slot_over[s2]) continue;
+    }
     return;  // an earlier window owns this pair
   }
 
@@ -217,12 +237,16 @@ __device__ __forceinline__ void confirm_one_pair(const WinCfg& cfg, const Confir
 
 // Persistent grid: blocks stride over the 256-pair blocks; the pair count lives on the device,
 // so the launch configuration never depends on a host round trip.
+template <int MODE>
 __global__ void __launch_bounds__(256) confirm_pairs_kernel(const WinCfg cfg, const ConfirmArgs a) {
   const uint64_t n_pairs = *a.n_pairs_ptr;
   const uint64_t n_blocks = min((uint64_t)((n_pairs + 255) / 256), a.block_cap);
   for (uint64_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
     const uint64_t i = b * 256ull + threadIdx.x;
-    if (i < n_pairs) confirm_one_pair(cfg, a, i, __ldg(a.block_first + b), __ldg(a.block_first + b + 1));
+    if (i >= n_pairs) continue;
+    const uint64_t clo = __ldg(a.block_first + b), chi = __ldg(a.block_first + b + 1);
+    const uint64_t c = upper_bound_dev<uint64_t>(a.pstart, clo, chi + 1, i) - 1;
+    confirm_one_pair<MODE>(cfg, a, i, c);
   }
 }
 

@@ -64,58 +64,43 @@ __device__ __forceinline__ uint64_t scan_count(const unsigned long long* n_ptr, 
   return v < n ? v : n;
 }
 
-// Pass 1: per-tile sums (grid-stride over tiles, so the launch does not depend on n).
-__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* __restrict__ in,
-                                                               const unsigned long long* n_ptr, uint64_t n_host,
-                                                               uint64_t* __restrict__ tile_sums) {
-  __shared__ uint64_t warp_sums[kScanThreads / 32];
-  __shared__ uint64_t total;
-  const uint64_t n = scan_count(n_ptr, n_host);
-  const uint64_t ntiles = (n + kScanTile - 1) / kScanTile;
-  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const uint64_t base = tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
-    uint64_t s = 0;
-#pragma unroll
-    for (int i = 0; i < kScanItems; i++)
-      if (base + i < n) s += in[base + i];
-    block_exclusive_scan_u64(s, &total, warp_sums);
-    if (threadIdx.x == 0) tile_sums[tile] = total;
-    __syncthreads();
-  }
+// ---------------------------------------------------------------------------------------------
+// Single-launch exclusive scan (decoupled look-back).  Tiles are handed out by an atomic ticket,
+// so a tile only ever waits on tiles held by blocks that are already running.  Each tile
+// publishes one 64-bit descriptor {status:2 | epoch:14 | value:48}: first its aggregate, then
+// its inclusive prefix; warp 0 of the block walks back over the predecessors 32 at a time.  The
+// epoch makes descriptors of earlier scans invisible, so the descriptor array is never cleared
+// between scans; the ticket / completion counters reset themselves when the last block leaves.
+// ---------------------------------------------------------------------------------------------
+constexpr uint64_t kDescValueMask = (1ull << 48) - 1ull;
+constexpr uint32_t kScanEpochs = 1u << 14;
+constexpr uint64_t kDescAggregate = 1ull, kDescInclusive = 2ull;
+
+__device__ __forceinline__ uint64_t desc_pack(uint64_t status, uint32_t epoch, uint64_t value) {
+  return (status << 62) | ((uint64_t)epoch << 48) | (value & kDescValueMask);
 }
 
-// Pass 2: one block scans the tile sums in place (exclusive); writes the grand total.
-__global__ void __launch_bounds__(kScanThreads) scan_tile_offsets(uint64_t* __restrict__ tile_sums,
-                                                                  const unsigned long long* n_ptr, uint64_t n_host,
-                                                                  uint64_t* __restrict__ grand_total) {
-  __shared__ uint64_t warp_sums[kScanThreads / 32];
-  __shared__ uint64_t total;
-  const uint64_t ntiles = (scan_count(n_ptr, n_host) + kScanTile - 1) / kScanTile;
-  uint64_t carry = 0;
-  for (uint64_t start = 0; start < ntiles; start += kScanThreads) {
-    const uint64_t i = start + threadIdx.x;
-    const uint64_t v = i < ntiles ? tile_sums[i] : 0;
-    const uint64_t ex = block_exclusive_scan_u64(v, &total, warp_sums);
-    if (i < ntiles) tile_sums[i] = carry + ex;
-    carry += total;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *grand_total = carry;
-}
-
-// Pass 3: rescan each tile with its offset.  out[n] (one past the end) receives the total
-// when write_end is set, so out can serve directly as a CSR offsets array.
 template <typename OutT>
-__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* __restrict__ in,
-                                                           const unsigned long long* n_ptr, uint64_t n_host,
-                                                           const uint64_t* __restrict__ tile_offs,
-                                                           OutT* __restrict__ out, int write_end) {
+__global__ void __launch_bounds__(kScanThreads) scan_onepass_kernel(const uint32_t* __restrict__ in,
+                                                                    const unsigned long long* n_ptr, uint64_t n_host,
+                                                                    OutT* __restrict__ out, int write_end,
+                                                                    unsigned long long* __restrict__ total_out,
+                                                                    uint64_t* desc, unsigned long long* state,
+                                                                    uint32_t epoch) {
   __shared__ uint64_t warp_sums[kScanThreads / 32];
-  __shared__ uint64_t total;
+  __shared__ uint64_t s_total, s_tile, s_excl;
+  const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
   const uint64_t n = scan_count(n_ptr, n_host);
   const uint64_t ntiles = (n + kScanTile - 1) / kScanTile;
-  if (n == 0 && write_end && blockIdx.x == 0 && threadIdx.x == 0) out[0] = (OutT)0;
-  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (write_end) out[0] = (OutT)0;
+    *total_out = 0ull;
+  }
+  while (true) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(&state[0], 1ull);
+    __syncthreads();
+    const uint64_t tile = s_tile;
+    if (tile >= ntiles) break;
     const uint64_t base = tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
     uint32_t v[kScanItems];
     uint64_t s = 0;
@@ -124,14 +109,58 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* __res
       v[i] = base + i < n ? in[base + i] : 0u;
       s += v[i];
     }
-    uint64_t run = tile_offs[tile] + block_exclusive_scan_u64(s, &total, warp_sums);
+    const uint64_t in_block = block_exclusive_scan_u64(s, &s_total, warp_sums);
+    if (wid == 0) {
+      const uint64_t agg = s_total;
+      uint64_t excl = 0;
+      if (tile > 0) {
+        if (lane == 0) *reinterpret_cast<volatile uint64_t*>(desc + tile) = desc_pack(kDescAggregate, epoch, agg);
+        int64_t back = (int64_t)tile - 1;
+        while (true) {
+          const int64_t p = back - (int64_t)lane;
+          uint64_t status = kDescInclusive, val = 0;
+          if (p >= 0) {
+            uint64_t d;
+            do {
+              d = *reinterpret_cast<volatile uint64_t*>(desc + p);
+            } while (((d >> 48) & (kScanEpochs - 1)) != epoch || (d >> 62) == 0);
+            status = d >> 62;
+            val = d & kDescValueMask;
+          }
+          const unsigned incl = __ballot_sync(0xffffffffu, status == kDescInclusive);
+          const int first = incl ? __ffs(incl) - 1 : 31;
+          uint64_t c = (int)lane <= first ? val : 0ull;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+          excl += c;
+          if (incl) break;
+          back -= 32;
+        }
+      }
+      if (lane == 0) {
+        *reinterpret_cast<volatile uint64_t*>(desc + tile) = desc_pack(kDescInclusive, epoch, excl + agg);
+        s_excl = excl;
+        if (tile + 1 == ntiles) {
+          *total_out = excl + agg;
+          if (write_end) out[n] = (OutT)(excl + agg);
+        }
+      }
+    }
+    __syncthreads();
+    uint64_t run = s_excl + in_block;
 #pragma unroll
     for (int i = 0; i < kScanItems; i++) {
       if (base + i < n) out[base + i] = (OutT)run;
       run += v[i];
-      if (write_end && base + i + 1 == n) out[n] = (OutT)run;
     }
     __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&state[1], 1ull) == (unsigned long long)gridDim.x - 1ull) {
+      state[0] = 0ull;  // every block has stopped taking tickets: ready for the next scan
+      state[1] = 0ull;
+    }
   }
 }
 

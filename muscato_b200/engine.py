@@ -117,6 +117,9 @@ class HotPath:
     def run(self):
         self._check(self._lib.msc_run(self._ctx))
 
+    def run_stages(self, rebuild_what: int, stages: int):
+        self._check(self._lib.msc_run_stages(self._ctx, rebuild_what, stages))
+
     def rebuild_and_run(self, what: int = 3):
         self._check(self._lib.msc_rebuild_and_run(self._ctx, what))
 
@@ -145,6 +148,12 @@ class HotPath:
             return np.frombuffer(buf, dtype=MATCH_DTYPE).copy()
         finally:
             self._lib.msc_free(out)
+
+    def fetch_into(self, dst_ptr: int, capacity: int) -> int:
+        """Copy the matches into a caller-owned (e.g. pinned) buffer of `capacity` 16-byte records."""
+        n = C.c_uint64(0)
+        self._check(self._lib.msc_fetch_matches_into(self._ctx, dst_ptr, capacity, C.byref(n)))
+        return int(n.value)
 
     def dump_keys(self) -> np.ndarray:
         out = C.POINTER(_capi.msc_key_rec)()

@@ -59,15 +59,22 @@ def revcomp_rows(genes: np.ndarray) -> np.ndarray:
 
 
 def generate(num_read: int, read_len: int, num_gene: int, gene_len: int, seed: int = 1, rev: bool = False,
-             mutated_fraction: float = 0.0, sub_rate: float = 0.02) -> Synthetic:
+             mutated_fraction: float = 0.0, sub_rate: float = 0.02, n_shards: int = 1) -> Synthetic:
+    """num_gene genes in total.  With n_shards > 1 the gene list is n_shards consecutive gendat
+    databases of num_gene/n_shards genes each (every one plants the ten reads in its own first
+    half), so that contiguous target sharding gives every rank a statistically identical shard."""
     if num_read < 10:
         raise ValueError("numRead must be at least 10")  # :148-150
     rng = np.random.default_rng(seed)
     reads = _BASES[rng.integers(0, 4, size=(num_read, read_len), dtype=np.uint8)]
     genes = _BASES[rng.integers(0, 4, size=(num_gene, gene_len), dtype=np.uint8)]
     # plant read i%10 at offset i%10 of gene i for i < NumGene/2 (:122-125)
-    for i in range(min(num_gene // 2, num_gene)):
-        j = i % 10
+    per = max(1, num_gene // max(1, n_shards))
+    for i in range(num_gene):
+        li = i % per
+        if li >= per // 2:
+            continue
+        j = li % 10
         n = min(read_len, gene_len - j)
         if n > 0:
             genes[i, j:j + n] = reads[j, :n]

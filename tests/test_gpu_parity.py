@@ -32,7 +32,16 @@ def run_cuda(cfg: Config, reads, targets, taps=False):
         hp.combine()
         m = hp.fetch()
         st = hp.stats()
+    assert_fetch_order(m)
     return m, st, keys, cands
+
+
+def assert_fetch_order(m):
+    """msc_fetch_matches promises (read_id, gene_id, pos) order, established on the device."""
+    if len(m) > 1:
+        key = np.stack([m["read_id"], m["gene_id"], m["pos"]], axis=1).astype(np.int64)
+        order = np.lexsort((key[:, 2], key[:, 1], key[:, 0]))
+        assert np.array_equal(order, np.arange(len(m)))
 
 
 def check_against_oracle(tmp_path, raw_reads, names, genes, cfgd, gene_names=None, taps=True):
@@ -191,7 +200,14 @@ def test_gendat_medium_vs_oracle(tmp_path, oracle_bin):
         hp.set_targets((syn.target_ascii, syn.target_offs))
         hp.run()
         m = hp.fetch()
+        # the staged form used across ranks: screen+confirm, (all-reduce of best), combine
+        hp.run_stages(0, 1 | 2)
+        hp.run_stages(0, 4)
+        m2 = hp.fetch()
+    assert_fetch_order(m)
+    assert np.array_equal(m, m2)
     assert len(m) > 5000
+    assert max(np.bincount(m["read_id"])) > 16   # exercises the long-segment rank sort
     assert formats.matches_lines(m, seqs, targets) == helpers.read_lines(out["matches"])
     gnames, glens = formats.load_gene_ids(gi)
     res = b"".join(ln + b"\n" for ln in formats.results_lines(m, seqs, counts, rnames, targets, gnames, glens))
@@ -253,3 +269,33 @@ def test_cli_files_drop_in(case, tmp_path, oracle_bin):
         helpers.read_bytes(os.path.join(src, "result.nonmatch_e.txt"))
     assert sz.read_file(str(tmp_path / "tmp" / "matches.txt.sz")) == helpers.read_bytes(out["matches"])
     assert sz.read_file(str(tmp_path / "tmp" / "reads_sorted.txt.sz")) == helpers.read_bytes(out["reads_sorted"])
+
+
+MM_CASES = [("best", 1), ("best", 3), ("best", 7), ("best", 40), ("first", 1), ("first", 5), ("first", 40)]
+
+
+@pytest.mark.parametrize("mode,mm", MM_CASES, ids=[f"{m}{k}" for m, k in MM_CASES])
+def test_maxmatches_truncation_vs_oracle(mode, mm, tmp_path, oracle_bin):
+    """Q7: per (window, k-mer) group the reference keeps at most MaxMatches pairs through an
+    order-dependent heap ("best", cmd/muscato_confirm/main.go:424-448) or the first MaxMatches+1
+    ("first", :233-238).  Repetitive targets + many near-identical reads overflow small limits."""
+    rng = np.random.default_rng(100 + mm)
+    unit = helpers.random_dna(rng, 37)
+    genes = []
+    for gi in range(12):
+        a = np.frombuffer(unit * 6, dtype=np.uint8).copy()       # tandem repeats: the same k-mers everywhere
+        m = rng.random(len(a)) < 0.02
+        a[m] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(m.sum()))]
+        genes.append(bytes(a) + helpers.random_dna(rng, int(rng.integers(0, 30))))
+    reads = []
+    for _ in range(150):
+        g = genes[int(rng.integers(0, len(genes)))]
+        p = int(rng.integers(0, len(g) - 50))
+        a = np.frombuffer(g[p:p + 50], dtype=np.uint8).copy()
+        m = rng.random(50) < 0.03
+        a[m] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(m.sum()))]
+        reads.append(bytes(a))
+    cfgd = dict(Windows=[0, 12, 30], WindowWidth=10, MaxReadLength=50, PMatch=0.9, MinDinuc=0, MMTol=2,
+                BloomSize=1000000, NumHash=6, MaxMatches=mm, MatchMode=mode, MaxConfirmProcs=3)
+    m, st = check_against_oracle(tmp_path, reads, None, genes, cfgd, taps=False)
+    assert st["n_overflow_groups"] > 0, "the case must actually truncate"
