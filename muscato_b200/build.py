@@ -12,6 +12,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libmuscato_b200.so")
+EXE_PATH = os.path.join(HERE, "bin", "muscato_b200_hotpath")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -27,15 +28,15 @@ def _sources():
 def _deps():
     out = []
     for root, _, files in os.walk(CSRC):
-        out += [os.path.join(root, f) for f in files if f.endswith((".cu", ".cuh", ".h"))]
+        out += [os.path.join(root, f) for f in files if f.endswith((".cu", ".cuh", ".h", ".inc", ".hpp", ".cc"))]
     out.append(os.path.join(HERE, "..", "include", "muscato_b200.h"))
     return out
 
 
 def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(EXE_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = min(os.path.getmtime(LIB_PATH), os.path.getmtime(EXE_PATH))
     return any(os.path.getmtime(p) > t for p in _deps() if os.path.exists(p))
 
 
@@ -52,7 +53,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
+    build_host_exe()
     return LIB_PATH
+
+
+def build_host_exe() -> str:
+    """The stage-compatible C++ executable (host text I/O above the C ABI), linked against the library."""
+    os.makedirs(os.path.dirname(EXE_PATH), exist_ok=True)
+    cxx = shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-o", EXE_PATH,
+           os.path.join(CSRC, "host", "muscato_b200_hotpath.cc"),
+           "-L" + HERE, "-lmuscato_b200", "-Wl,-rpath,$ORIGIN/.."]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return EXE_PATH
 
 
 if __name__ == "__main__":

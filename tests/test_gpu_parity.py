@@ -299,3 +299,57 @@ def test_maxmatches_truncation_vs_oracle(mode, mm, tmp_path, oracle_bin):
                 BloomSize=1000000, NumHash=6, MaxMatches=mm, MatchMode=mode, MaxConfirmProcs=3)
     m, st = check_against_oracle(tmp_path, reads, None, genes, cfgd, taps=False)
     assert st["n_overflow_groups"] > 0, "the case must actually truncate"
+
+
+@pytest.mark.parametrize("case", ["00", "01", "02", "03", "04"])
+def test_cpp_executable_drop_in(case, tmp_path, oracle_bin):
+    """muscato_b200_hotpath (C++ host + C ABI): same config.json and .sz files as the reference
+    stages, outputs compared with the reference's expected files and the oracle's matches.txt."""
+    import subprocess
+    from muscato_b200 import build, sz
+    src = os.path.join(helpers.GOLDEN, "muscato", case)
+    cfgd = json.load(open(os.path.join(src, "config.json")))
+    seq, ids = str(tmp_path / "genes_seq.txt"), str(tmp_path / "genes_ids.txt")
+    helpers.oracle_prep_targets(os.path.join(src, "genes.txt"), seq, ids, rev=(case == "04"))
+    sz.write_file(str(tmp_path / "genes.txt.sz"), helpers.read_bytes(seq))
+    sz.write_file(str(tmp_path / "genes_ids.txt.sz"), helpers.read_bytes(ids))
+    out = helpers.oracle_pipeline(str(tmp_path / "oracle"), os.path.join(src, "reads.fastq"), seq, ids, cfgd)
+    os.makedirs(tmp_path / "tmp")
+    cfgd.update(ReadFileName=os.path.join(src, "reads.fastq"), GeneFileName=str(tmp_path / "genes.txt.sz"),
+                GeneIdFileName=str(tmp_path / "genes_ids.txt.sz"), ResultsFileName=str(tmp_path / "result.txt"),
+                TempDir=str(tmp_path / "tmp"))
+    json.dump(cfgd, open(tmp_path / "config.json", "w"))
+    r = subprocess.run([build.EXE_PATH, str(tmp_path / "config.json"), "--from-fastq"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert helpers.read_bytes(str(tmp_path / "result.txt")) == helpers.read_bytes(os.path.join(src, "result_e.txt"))
+    assert helpers.read_bytes(str(tmp_path / "result.nonmatch.txt.fastq")) == \
+        helpers.read_bytes(os.path.join(src, "result.nonmatch_e.txt"))
+    assert sz.read_file(str(tmp_path / "tmp" / "matches.txt.sz")) == helpers.read_bytes(out["matches"])
+    assert sz.read_file(str(tmp_path / "tmp" / "reads_sorted.txt.sz")) == helpers.read_bytes(out["reads_sorted"])
+    # second run from the reads_sorted.txt.sz it left behind (the driver's normal hand-over)
+    os.remove(tmp_path / "result.txt")
+    r = subprocess.run([build.EXE_PATH, str(tmp_path / "config.json")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert helpers.read_bytes(str(tmp_path / "result.txt")) == helpers.read_bytes(os.path.join(src, "result_e.txt"))
+
+
+def test_cpp_executable_random_case_vs_oracle(tmp_path, oracle_bin):
+    import subprocess
+    from muscato_b200 import build, sz
+    rng = np.random.default_rng(77)
+    reads, genes = _planted_case(rng, 25, 260, 400, [70, 64, 50], 0.03, x_rate=0.01)
+    names = [b"@r%d desc" % i for i in range(len(reads))]
+    cfgd = dict(Windows=[0, 16, 33], WindowWidth=14, MaxReadLength=70, PMatch=0.94, MinDinuc=3, MMTol=1,
+                BloomSize=2000000, NumHash=6, MaxMatches=1000000, MatchMode="best", MinReadLength=0)
+    fq, gs, gi = helpers.write_case(str(tmp_path), reads, names, genes)
+    out = helpers.oracle_pipeline(str(tmp_path / "oracle"), fq, gs, gi, cfgd)
+    os.makedirs(tmp_path / "tmp")
+    c = dict(cfgd)
+    c.update(ReadFileName=fq, GeneFileName=gs, GeneIdFileName=gi, ResultsFileName=str(tmp_path / "res.txt"),
+             TempDir=str(tmp_path / "tmp"))
+    json.dump(c, open(tmp_path / "config.json", "w"))
+    r = subprocess.run([build.EXE_PATH, str(tmp_path / "config.json"), "--from-fastq"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert helpers.read_bytes(str(tmp_path / "res.txt")) == helpers.read_bytes(out["results"])
+    assert helpers.read_bytes(str(tmp_path / "res.nonmatch.txt.fastq")) == helpers.read_bytes(out["nonmatch"])
+    assert sz.read_file(str(tmp_path / "tmp" / "matches.txt.sz")) == helpers.read_bytes(out["matches"])

@@ -134,3 +134,42 @@ def test_product_never_touches_the_oracle():
                 txt = open(os.path.join(root, f), errors="replace").read()
                 assert "oracle/" not in txt.replace("write_oracle_inputs", "") or f == "gendat.py", f
                 assert "muscato_oracle" not in txt, f
+
+
+def test_cpp_sz_codec_matches_python_and_reference_fixture(tmp_path):
+    """The C++ host executable's .sz codec (sztool -d / -c equivalents) against the reference's own
+    compressed fixture and the Python codec."""
+    import subprocess
+    build.build()
+    exe = build.EXE_PATH
+    src = os.path.join(helpers.GOLDEN, "prep_targets", "06", "genes.txt.sz")
+    out = subprocess.run([exe, "--sz-cat", src], capture_output=True, check=True).stdout
+    assert out == sz.read_file(src)
+    rng = np.random.default_rng(4)
+    blob = b"\n".join(helpers.random_dna(rng, int(rng.integers(1, 300))) for _ in range(2000)) + b"\n"
+    plain, packed = tmp_path / "x.txt", tmp_path / "x.txt.sz"
+    plain.write_bytes(blob)
+    subprocess.run([exe, "--sz-pack", str(plain), str(packed)], check=True)
+    assert sz.read_file(str(packed)) == blob                       # Python reads what C++ wrote
+    sz.write_file(str(tmp_path / "y.txt.sz"), blob)
+    out = subprocess.run([exe, "--sz-cat", str(tmp_path / "y.txt.sz")], capture_output=True, check=True).stdout
+    assert out == blob                                             # C++ reads what Python wrote
+
+
+def test_cpp_executable_fails_loudly_without_gpu(tmp_path):
+    import json
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    build.build()
+    src = os.path.join(helpers.GOLDEN, "muscato", "00")
+    cfgd = json.load(open(os.path.join(src, "config.json")))
+    seq, ids = str(tmp_path / "g.txt"), str(tmp_path / "gi.txt")
+    helpers.oracle_prep_targets(os.path.join(src, "genes.txt"), seq, ids)
+    cfgd.update(ReadFileName=os.path.join(src, "reads.fastq"), GeneFileName=seq, GeneIdFileName=ids,
+                ResultsFileName=str(tmp_path / "result.txt"), TempDir=str(tmp_path))
+    json.dump(cfgd, open(tmp_path / "config.json", "w"))
+    r = subprocess.run([build.EXE_PATH, str(tmp_path / "config.json"), "--from-fastq"], capture_output=True, text=True)
+    assert r.returncode != 0 and "CUDA" in r.stderr
+    assert not os.path.exists(tmp_path / "result.txt")            # nothing is produced by a fallback
