@@ -62,7 +62,7 @@ struct DevBuf {
 // Device counter block (unsigned long long each).
 enum Counter {
   C_NKEYS = 0, C_NGROUPS, C_NDUP, C_SCRATCH, C_NCAND, C_BLOOMPASS, C_NMATCH, C_NPASS, C_NOVER, C_NOUT, C_NPAIRS,
-  C_PAD0, C_NLONG,  // C_NLONG at an even index
+  C_PAD0, C_NLONG, C_PAD1, C_TGX,  // C_NLONG, C_TGX at even indices; C_TGX = "some target word has X"
   C_COUNT = 16  // groups that are cleared together start at even indices (16-byte aligned)
 };
 
@@ -261,7 +261,7 @@ int enqueue_build_reads(msc_ctx* ctx) {
   {
     Filler f;
     f.add(ctx->len_flags.p, (U + 1) * sizeof(uint32_t));
-    f.add(ctx->counters.p, C_COUNT * sizeof(unsigned long long));
+    f.add(ctx->ctr(C_NKEYS), 4 * sizeof(unsigned long long));  // C_NKEYS, C_NGROUPS, C_NDUP, C_SCRATCH
     RC(enqueue_fill(ctx, f));
   }
   if (U) {
@@ -337,11 +337,12 @@ int enqueue_pack_targets(msc_ctx* ctx) {
     Filler f;
     f.add(ctx->tg_x.p, ctx->n_words_alloc * sizeof(uint64_t));
     f.add(ctx->xsum.p, (ctx->n_words_alloc / 32 + 4) * sizeof(uint32_t));
+    f.add(ctx->ctr(C_TGX), 2 * sizeof(unsigned long long));
     RC(enqueue_fill(ctx, f));
   }
   pack_targets_kernel<<<grid_for(ctx->n_words_alloc, 256), 256, 0, ctx->stream>>>(
       ctx->tg_ascii.as<uint8_t>(), ctx->n_bases, ctx->tg_words.as<uint64_t>(), ctx->n_words_alloc,
-      ctx->tg_x.as<uint64_t>(), ctx->xsum.as<uint32_t>());
+      ctx->tg_x.as<uint64_t>(), ctx->xsum.as<uint32_t>(), ctx->ctr(C_TGX));
   LAUNCH_CHECK();
   CK(cudaEventRecord(ctx->ev[EV_PACKT1], ctx->stream));
   ctx->have_cand = ctx->have_confirm = ctx->have_combine = false;
@@ -442,6 +443,8 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   a.tg_off = ctx->tg_off.as<uint32_t>();
   a.n_targets = ctx->n_targets;
   a.nmiss = ctx->nmiss.as<int32_t>();
+  a.nwin_magic = ctx->win.nwin == 1 ? 0ull : (~0ull / (uint64_t)ctx->win.nwin) + 1ull;
+  a.targets_have_x = ctx->ctr(C_TGX);
   a.matches = outbuf.as<uint4>();
   a.match_cap = outbuf.cap / sizeof(uint4);
   a.n_match = ctx->ctr(C_NMATCH);

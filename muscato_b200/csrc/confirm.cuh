@@ -83,6 +83,8 @@ struct ConfirmArgs {
   uint64_t n_targets;
   // rules
   const int32_t* nmiss;  // [MRL + 1]
+  uint64_t nwin_magic;   // floor(2^64 / nwin) + 1: item / nwin == umul64hi(item, magic) for 32-bit items
+  const unsigned long long* targets_have_x;  // device flag: 0 = no target word contains X
   // outputs
   uint4* matches;  // (read, gene, pos, nx)
   unsigned long long match_cap;
@@ -120,14 +122,18 @@ __device__ __forceinline__ bool tg_range_has_x(const uint32_t* __restrict__ xsum
 
 // One (candidate, read) pair; c = index of its candidate.  MODE is a compile-time copy of
 // ConfirmArgs::mode so that the hot mode-0 kernel carries none of the tap / overflow code.
+// Returns true when the pair yields an output record (`rec`): a match (read, gene, pos, nx) in
+// modes 0/2, an exact-key candidate (gene, p, read, window) in mode 1.  n_pass counts pairs
+// that passed through their window (before cross-window de-duplication).
 template <int MODE>
-__device__ __forceinline__ void confirm_one_pair(const WinCfg& cfg, const ConfirmArgs& a, uint64_t i, uint64_t c) {
+__device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const ConfirmArgs& a, uint64_t i, uint64_t c,
+                                                 uint4& rec, uint32_t& n_pass) {
   const uint2 cd = __ldg(a.cand + c);
   const uint2 ci = __ldg(a.cinfo + c);
   const uint32_t slot = cd.x;
   const uint64_t gpos = cd.y;
   const uint32_t item = group_item(a.tab_item0, a.tab_start, a.items, slot, (uint32_t)(i - __ldg(a.pstart + c)));
-  const uint32_t r = item / (uint32_t)cfg.nwin;
+  const uint32_t r = cfg.nwin == 1 ? item : (uint32_t)__umul64hi((uint64_t)item, a.nwin_magic);  // item / nwin
   const int k = (int)(item - r * (uint32_t)cfg.nwin);
   const int W = cfg.W;
   const int q1 = cfg.windows[k], q2 = q1 + W;
@@ -137,7 +143,7 @@ __device__ __forceinline__ void confirm_one_pair(const WinCfg& cfg, const Confir
   const int64_t p = (int64_t)ci.y;
   const int64_t glen = (int64_t)__ldg(a.tg_off + g + 1) - (int64_t)__ldg(a.tg_off + g);
   const int64_t pos = p - q1;      // jw = jx - q1 >= 0 (cmd/muscato_screen/main.go:345, :355)
-  if (pos < 0) return;
+  if (pos < 0) return false;
 
   const uint32_t lf = __ldg(a.len_flags + r);
   const int L = (int)(lf & 0x7fffffffu);
@@ -146,7 +152,7 @@ __device__ __forceinline__ void confirm_one_pair(const WinCfg& cfg, const Confir
   const uint64_t* xrow = a.rd_x + (uint64_t)r * cfg.S;
   const uint64_t kmask = low_bases_mask(W);
   const uint64_t gstart = gpos - (uint64_t)q1;  // global base index of the read's first base
-  const bool tx = tg_range_has_x(a.xsum, gstart >> 5, ((gstart + (uint64_t)L) >> 5) + 1);
+  const bool tx = __ldg(a.targets_have_x) != 0ull && tg_range_has_x(a.xsum, gstart >> 5, ((gstart + (uint64_t)L) >> 5) + 1);
   const bool anyx = rx | tx;
 
   // Exact key equality for the window that produced this pair (merge join on the k-mer bytes,
@@ -154,26 +160,25 @@ __device__ __forceinline__ void confirm_one_pair(const WinCfg& cfg, const Confir
   {
     const uint64_t rk = extract32(row, (uint64_t)q1) & kmask;
     const uint64_t tk = extract32(a.tg_words, gpos) & kmask;
-    if (rk != tk) return;
+    if (rk != tk) return false;
     if (anyx) {
       const uint64_t rxm = rx ? (extract32(xrow, (uint64_t)q1) & kmask) : 0ull;
       const uint64_t txm = tx ? (extract32(a.tg_x, gpos) & kmask) : 0ull;
-      if (rxm != txm) return;
+      if (rxm != txm) return false;
     }
   }
   if (MODE == 1) {
-    const unsigned long long at = warp_agg_inc(a.n_match);
-    if (at < a.match_cap) a.matches[at] = make_uint4((uint32_t)g, (uint32_t)p, r, (uint32_t)k);
-    return;
+    rec = make_uint4((uint32_t)g, (uint32_t)p, r, (uint32_t)k);
+    return true;
   }
 
   // Fit rule (cmd/muscato_confirm/main.go:200-203) on the candidate's clipped right tail.
   const int64_t lim0 = min((int64_t)(100 - W), glen);  // position-0 record: right = t[W : min(100-q2, len)]
   if (p == 0) {
-    if ((int64_t)L > lim0) return;  // len(srgt) = L - W <= min(100 - W, len) - W
+    if ((int64_t)L > lim0) return false;  // len(srgt) = L - W <= min(100 - W, len) - W
   } else {
     const int64_t mr = min(p + W + (int64_t)cfg.MRL - q2, glen) - (p + W);
-    if ((int64_t)(L - q2) > mr) return;
+    if ((int64_t)(L - q2) > mr) return false;
   }
 
   // Full-read mismatch count: nx = cdiff(left tails) + cdiff(right tails) (+0 inside the window).
@@ -193,16 +198,16 @@ __device__ __forceinline__ void confirm_one_pair(const WinCfg& cfg, const Confir
     }
     m &= low_bases_mask(min(32, L - 32 * w));
     nx += __popcll(m);
-    if (nx > budget) return;
+    if (nx > budget) return false;
   }
 
   // The pair passes through window k.
   atomicAdd(a.pass_cnt + slot, 1u);
-  (void)warp_agg_inc(a.n_pass);
+  n_pass++;
   if (MODE == 2 && a.slot_over[slot]) {
     const unsigned long long at = warp_agg_inc(a.n_over_inst);
     if (at < a.over_cap) a.over[at] = make_uint4(r, (uint32_t)g, (uint32_t)pos, (uint32_t)nx | ((uint32_t)k << 16));
-    return;
+    return false;
   }
 
   // Cross-window de-duplication: emit only through the lowest window index that delivers
@@ -227,26 +232,72 @@ __device__ __forceinline__ void confirm_one_pair(const WinCfg& cfg, const Confir
       const int64_t s2 = table_find(a.tab_fp, a.lg_slots, __ldg(a.fps + (uint64_t)r * cfg.nwin + k2));
       if (s2 >= 0 && a.slot_over[s2]) continue;
     }
-    return;  // an earlier window owns this pair
+    return false;  // an earlier window owns this pair
   }
 
   atomicMin(a.best + r, (uint32_t)nx);
-  const unsigned long long at = warp_agg_inc(a.n_match);
-  if (at < a.match_cap) a.matches[at] = make_uint4(r, (uint32_t)g, (uint32_t)pos, (uint32_t)nx);
+  rec = make_uint4(r, (uint32_t)g, (uint32_t)pos, (uint32_t)nx);
+  return true;
 }
 
-// Persistent grid: blocks stride over the 256-pair blocks; the pair count lives on the device,
-// so the launch configuration never depends on a host round trip.
+// Persistent grid: blocks stride over chunks of kPairsPerThread * 256 consecutive pairs; the pair
+// count lives on the device, so the launch configuration never depends on a host round trip.
+// A thread owns kPairsPerThread consecutive pairs: one binary search (narrowed by block_first)
+// for the first, a linear advance for the rest.  Output records are staged in shared memory and
+// appended with ONE global atomic per chunk; the pass counter costs one atomic per block.
+constexpr int kPairsPerThread = 4;
+constexpr int kChunkPairs = kPairsPerThread * 256;
+
 template <int MODE>
 __global__ void __launch_bounds__(256) confirm_pairs_kernel(const WinCfg cfg, const ConfirmArgs a) {
+  __shared__ uint4 s_out[kChunkPairs];
+  __shared__ uint32_t s_n;
+  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_pass[8];
   const uint64_t n_pairs = *a.n_pairs_ptr;
-  const uint64_t n_blocks = min((uint64_t)((n_pairs + 255) / 256), a.block_cap);
-  for (uint64_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
-    const uint64_t i = b * 256ull + threadIdx.x;
-    if (i >= n_pairs) continue;
-    const uint64_t clo = __ldg(a.block_first + b), chi = __ldg(a.block_first + b + 1);
-    const uint64_t c = upper_bound_dev<uint64_t>(a.pstart, clo, chi + 1, i) - 1;
-    confirm_one_pair<MODE>(cfg, a, i, c);
+  const uint64_t n_blocks256 = min((uint64_t)((n_pairs + 255) / 256), a.block_cap);
+  const uint64_t n_chunks = (n_blocks256 + kPairsPerThread - 1) / kPairsPerThread;
+  uint32_t n_pass = 0;
+  for (uint64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const uint64_t i0 = ch * (uint64_t)kChunkPairs + (uint64_t)threadIdx.x * kPairsPerThread;
+    if (i0 < n_pairs && (i0 >> 8) < n_blocks256) {
+      const uint64_t b = i0 >> 8;
+      const uint64_t clo = __ldg(a.block_first + b), chi = __ldg(a.block_first + b + 1);
+      uint64_t c = upper_bound_dev<uint64_t>(a.pstart, clo, chi + 1, i0) - 1;
+      uint64_t c_end = __ldg(a.pstart + c + 1);
+#pragma unroll 1
+      for (int j = 0; j < kPairsPerThread; j++) {
+        const uint64_t i = i0 + j;
+        if (i >= n_pairs) break;
+        while (c_end <= i) {  // next candidate with at least one pair
+          c++;
+          c_end = __ldg(a.pstart + c + 1);
+        }
+        uint4 rec;
+        if (confirm_one_pair<MODE>(cfg, a, i, c, rec, n_pass)) s_out[atomicAdd(&s_n, 1u)] = rec;
+      }
+    }
+    __syncthreads();
+    const uint32_t n_out = s_n;
+    if (n_out) {
+      if (threadIdx.x == 0) s_base = atomicAdd(a.n_match, (unsigned long long)n_out);
+      __syncthreads();
+      const unsigned long long base = s_base;
+      for (uint32_t t = threadIdx.x; t < n_out; t += 256)
+        if (base + t < a.match_cap) a.matches[base + t] = s_out[t];
+    }
+    __syncthreads();
+  }
+  // one pass-count atomic per block
+  n_pass = __reduce_add_sync(0xffffffffu, n_pass);
+  if ((threadIdx.x & 31u) == 0) s_pass[threadIdx.x >> 5] = n_pass;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < 8; w++) t += s_pass[w];
+    if (t) atomicAdd(a.n_pass, (unsigned long long)t);
   }
 }
 

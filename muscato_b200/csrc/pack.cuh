@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t* __restri
 __global__ void __launch_bounds__(256) pack_targets_kernel(const uint8_t* __restrict__ ascii, uint64_t n_bases,
                                                            uint64_t* __restrict__ words, uint64_t n_words_alloc,
                                                            uint64_t* __restrict__ xplane,
-                                                           uint32_t* __restrict__ xsum) {
+                                                           uint32_t* __restrict__ xsum,
+                                                           unsigned long long* __restrict__ any_x) {
   const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= n_words_alloc) return;
   const uint64_t b0 = w * 32;
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(256) pack_targets_kernel(const uint8_t* __rest
   if (xb) {
     xplane[w] = xb;
     atomicOr(xsum + (w >> 5), 1u << (unsigned)(w & 31u));
+    atomicOr(any_x, 1ull);
   }
 }
 
