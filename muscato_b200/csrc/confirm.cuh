@@ -243,62 +243,61 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
 // Persistent grid: blocks stride over chunks of kPairsPerThread * 256 consecutive pairs; the pair
 // count lives on the device, so the launch configuration never depends on a host round trip.
 // A thread owns kPairsPerThread consecutive pairs: one binary search (narrowed by block_first)
-// for the first, a linear advance for the rest.  Output records are staged in shared memory and
-// appended with ONE global atomic per chunk; the pass counter costs one atomic per block.
+// for the first, a linear advance for the rest.  Each WARP stages its output records in its own
+// shared-memory slice (positions from a ballot prefix, no atomics) and appends them with one
+// global atomic per warp and chunk; there is no block-wide barrier, so a warp never waits for
+// the slowest pair of another warp.  The pass counter costs one atomic per warp.
 constexpr int kPairsPerThread = 4;
 constexpr int kChunkPairs = kPairsPerThread * 256;
 
 template <int MODE>
 __global__ void __launch_bounds__(256) confirm_pairs_kernel(const WinCfg cfg, const ConfirmArgs a) {
-  __shared__ uint4 s_out[kChunkPairs];
-  __shared__ uint32_t s_n;
-  __shared__ unsigned long long s_base;
-  __shared__ uint32_t s_pass[8];
+  __shared__ uint4 s_out[8][kPairsPerThread * 32];
+  const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  uint4* my_out = s_out[wid];
   const uint64_t n_pairs = *a.n_pairs_ptr;
   const uint64_t n_blocks256 = min((uint64_t)((n_pairs + 255) / 256), a.block_cap);
   const uint64_t n_chunks = (n_blocks256 + kPairsPerThread - 1) / kPairsPerThread;
   uint32_t n_pass = 0;
   for (uint64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
     const uint64_t i0 = ch * (uint64_t)kChunkPairs + (uint64_t)threadIdx.x * kPairsPerThread;
-    if (i0 < n_pairs && (i0 >> 8) < n_blocks256) {
+    const bool live = i0 < n_pairs && (i0 >> 8) < n_blocks256;
+    uint64_t c = 0, c_end = 0;
+    if (live) {
       const uint64_t b = i0 >> 8;
       const uint64_t clo = __ldg(a.block_first + b), chi = __ldg(a.block_first + b + 1);
-      uint64_t c = upper_bound_dev<uint64_t>(a.pstart, clo, chi + 1, i0) - 1;
-      uint64_t c_end = __ldg(a.pstart + c + 1);
+      c = upper_bound_dev<uint64_t>(a.pstart, clo, chi + 1, i0) - 1;
+      c_end = __ldg(a.pstart + c + 1);
+    }
+    uint32_t n_out = 0;  // records staged by this warp (warp-uniform)
 #pragma unroll 1
-      for (int j = 0; j < kPairsPerThread; j++) {
-        const uint64_t i = i0 + j;
-        if (i >= n_pairs) break;
+    for (int j = 0; j < kPairsPerThread; j++) {
+      const uint64_t i = i0 + j;
+      bool has = false;
+      uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+      if (live && i < n_pairs) {
         while (c_end <= i) {  // next candidate with at least one pair
           c++;
           c_end = __ldg(a.pstart + c + 1);
         }
-        uint4 rec;
-        if (confirm_one_pair<MODE>(cfg, a, i, c, rec, n_pass)) s_out[atomicAdd(&s_n, 1u)] = rec;
+        has = confirm_one_pair<MODE>(cfg, a, i, c, rec, n_pass);
       }
+      const unsigned m = __ballot_sync(0xffffffffu, has);
+      if (has) my_out[n_out + __popc(m & ((1u << lane) - 1u))] = rec;
+      n_out += __popc(m);
     }
-    __syncthreads();
-    const uint32_t n_out = s_n;
+    __syncwarp();
     if (n_out) {
-      if (threadIdx.x == 0) s_base = atomicAdd(a.n_match, (unsigned long long)n_out);
-      __syncthreads();
-      const unsigned long long base = s_base;
-      for (uint32_t t = threadIdx.x; t < n_out; t += 256)
-        if (base + t < a.match_cap) a.matches[base + t] = s_out[t];
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(a.n_match, (unsigned long long)n_out);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (uint32_t t = lane; t < n_out; t += 32)
+        if (base + t < a.match_cap) a.matches[base + t] = my_out[t];
     }
-    __syncthreads();
+    __syncwarp();
   }
-  // one pass-count atomic per block
   n_pass = __reduce_add_sync(0xffffffffu, n_pass);
-  if ((threadIdx.x & 31u) == 0) s_pass[threadIdx.x >> 5] = n_pass;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t t = 0;
-    for (int w = 0; w < 8; w++) t += s_pass[w];
-    if (t) atomicAdd(a.n_pass, (unsigned long long)t);
-  }
+  if (lane == 0 && n_pass) atomicAdd(a.n_pass, (unsigned long long)n_pass);
 }
 
 }  // namespace msc
