@@ -283,8 +283,22 @@ def run_ours(args, rank, local_rank, world):
         exchange_best()           # NCCL MIN all-reduce of the per-read best mismatch count
         hp.run_stages(0, 4)       # combine
 
+    if world > 1:
+        d_rd_a = torch.empty(rd_a.numel(), dtype=torch.uint8, device=dev)
+        d_rd_o = torch.empty(rd_o.numel(), dtype=torch.int64, device=dev)
+
     def step_e2e():
-        hp.set_reads_ptr(rd_a.data_ptr(), rd_o.data_ptr(), n_reads)
+        if world == 1:
+            hp.set_reads_ptr(rd_a.data_ptr(), rd_o.data_ptr(), n_reads)
+        else:
+            # the replicated read set crosses PCIe once (rank 0) and NVLink N-1 times (NCCL broadcast)
+            if rank == 0:
+                d_rd_a.copy_(rd_a, non_blocking=True)
+                d_rd_o.copy_(rd_o, non_blocking=True)
+            dist.broadcast(d_rd_a, src=0)
+            dist.broadcast(d_rd_o, src=0)
+            torch.cuda.synchronize()
+            hp.set_reads_device(d_rd_a.data_ptr(), d_rd_o.data_ptr(), n_reads, int(rd_a.numel()))
         hp.set_targets_ptr(tg_a.data_ptr(), tg_o.data_ptr(), n_tg)
         if world == 1:
             hp.run()
@@ -297,8 +311,14 @@ def run_ours(args, rank, local_rank, world):
             local = torch.as_tensor(holder, device=dev) if n else torch.zeros(0, dtype=torch.int32, device=dev)
             allm = mdist.gather_matches(local, gene_offset=lo)
             if allm is not None:
-                last_gathered[0] = allm.cpu().numpy()
-                return int(last_gathered[0].shape[0])
+                ng = int(allm.shape[0])
+                if ng * 16 > res_buf.numel():
+                    raise RuntimeError("pinned result buffer too small")
+                dst = res_buf[: ng * 16].view(torch.int32).view(ng, 4)
+                dst.copy_(allm, non_blocking=True)   # D2H into pinned memory
+                torch.cuda.synchronize()
+                last_gathered[0] = dst.numpy()
+                return ng
             return 0
         return hp.fetch_into(res_buf.data_ptr(), res_cap)
 
@@ -362,7 +382,8 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": workload_name(w, world), "l2": "256 MiB device write between timed steps",
                    "sharding": f"targets by gene range over {world} rank(s), read key table replicated"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": 1000.0 * t_e2e / K,
-                "h2d_bytes_per_step": int(st_e["h2d_bytes"] // K), "d2h_bytes_per_step": int(st_e["d2h_bytes"] // K)},
+                "h2d_bytes_per_step": int(st_e["h2d_bytes"] // K) + (int(rd_a.numel() + rd_o.numel() * 8) if world > 1 else 0),
+                "d2h_bytes_per_step": int(st_e["d2h_bytes"] // K) + (16 * n_match_e2e if world > 1 else 0)},
         "gpu_launches": int(st["kernel_launches"]),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -100,6 +100,12 @@ const char* msc_last_error(const msc_ctx* ctx);
  * (cmd/muscato_window_reads/main.go:94-141) and sortWindows (cmd/muscato/main.go:237-304). */
 int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint64_t n_reads);
 
+/* Same as msc_set_reads for buffers that are already in the memory of ctx's device (e.g. the
+ * read set was uploaded once by rank 0 and broadcast over NVLink with NCCL).  offs has
+ * n_reads + 1 entries ending at total_bytes; it is validated on the device. */
+int msc_set_reads_device(msc_ctx* ctx, const uint8_t* d_ascii, const uint64_t* d_offs, uint64_t n_reads,
+                         uint64_t total_bytes);
+
 /* Targets in GeneFileName order (gene id = index, cmd/muscato_screen/main.go:440-452):
  * target g is ascii[offs[g] .. offs[g+1]).  Total length < 2^32 - 4096 bases per call
  * (shard larger databases by target range).  Uploads and 2-bit packs on the device. */

@@ -74,6 +74,7 @@ _SIGS = [
     ("msc_destroy", None, [C.c_void_p]),
     ("msc_last_error", C.c_char_p, [C.c_void_p]),
     ("msc_set_reads", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    ("msc_set_reads_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     ("msc_set_targets", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     ("msc_rebuild", C.c_int, [C.c_void_p, C.c_int]),
     ("msc_screen", C.c_int, [C.c_void_p]),

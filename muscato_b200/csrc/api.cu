@@ -747,24 +747,10 @@ void msc_destroy(msc_ctx* ctx) {
 
 const char* msc_last_error(const msc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint64_t n_reads) {
-  if (!ctx) return MSC_ERR_STATE;
-  if (n_reads && (!offs || (!ascii && offs[n_reads] != offs[0]))) return ctx->fail(MSC_ERR_INPUT, "reads: NULL buffer");
-  CK(cudaSetDevice(ctx->device));
+// Size every read-side buffer and the key table for n_reads reads / total ASCII bytes.
+static int reads_reserve(msc_ctx* ctx, uint64_t n_reads, uint64_t total) {
   const uint64_t nwin = (uint64_t)ctx->win.nwin;
   if (n_reads * nwin >= 0xffffffffull) return ctx->fail(MSC_ERR_INPUT, "reads: n_reads * n_windows must be < 2^32");
-  uint64_t total = 0;
-  if (n_reads) {
-    if (offs[0] != 0) return ctx->fail(MSC_ERR_INPUT, "reads: offs[0] must be 0");
-    const uint64_t mrl = (uint64_t)ctx->win.MRL;
-    for (uint64_t i = 0; i < n_reads; i++) {
-      if (offs[i + 1] < offs[i]) return ctx->fail(MSC_ERR_INPUT, "reads: offsets not monotone at %llu", (unsigned long long)i);
-      if (offs[i + 1] - offs[i] > mrl)
-        return ctx->fail(MSC_ERR_INPUT, "reads: read %llu is longer than MaxReadLength (prep_reads truncates, "
-                         "cmd/muscato_prep_reads/main.go:67-69)", (unsigned long long)i);
-    }
-    total = offs[n_reads];
-  }
   ctx->n_reads = n_reads;
   const int S = ctx->win.S;
   CK(ctx->rd_ascii.reserve(total + 64));
@@ -791,6 +777,26 @@ int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint
   // rd_words / rd_x rows are read one word past their end by extract32: keep the pad defined.
   CK(cudaMemsetAsync(ctx->rd_words.as<uint64_t>() + n_reads * S, 0, 2 * sizeof(uint64_t), ctx->stream));
   CK(cudaMemsetAsync(ctx->rd_x.as<uint64_t>() + n_reads * S, 0, 2 * sizeof(uint64_t), ctx->stream));
+  return MSC_OK;
+}
+
+int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint64_t n_reads) {
+  if (!ctx) return MSC_ERR_STATE;
+  if (n_reads && (!offs || (!ascii && offs[n_reads] != offs[0]))) return ctx->fail(MSC_ERR_INPUT, "reads: NULL buffer");
+  CK(cudaSetDevice(ctx->device));
+  uint64_t total = 0;
+  if (n_reads) {
+    if (offs[0] != 0) return ctx->fail(MSC_ERR_INPUT, "reads: offs[0] must be 0");
+    const uint64_t mrl = (uint64_t)ctx->win.MRL;
+    for (uint64_t i = 0; i < n_reads; i++) {
+      if (offs[i + 1] < offs[i]) return ctx->fail(MSC_ERR_INPUT, "reads: offsets not monotone at %llu", (unsigned long long)i);
+      if (offs[i + 1] - offs[i] > mrl)
+        return ctx->fail(MSC_ERR_INPUT, "reads: read %llu is longer than MaxReadLength (prep_reads truncates, "
+                         "cmd/muscato_prep_reads/main.go:67-69)", (unsigned long long)i);
+    }
+    total = offs[n_reads];
+  }
+  RC(reads_reserve(ctx, n_reads, total));
   if (total) CK(cudaMemcpyAsync(ctx->rd_ascii.p, ascii, total, cudaMemcpyHostToDevice, ctx->stream));
   if (n_reads) CK(cudaMemcpyAsync(ctx->rd_offs.p, offs, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   else CK(cudaMemsetAsync(ctx->rd_offs.p, 0, sizeof(uint64_t), ctx->stream));
@@ -798,6 +804,40 @@ int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint
   ctx->have_reads = true;
   RC(enqueue_build_reads(ctx));
   RC(sync_counters(ctx));  // the caller's buffers are only borrowed for the call
+  account_build_reads(ctx);
+  if (!ctx->cfg.keep_ascii) ctx->rd_ascii.release();
+  return MSC_OK;
+}
+
+int msc_set_reads_device(msc_ctx* ctx, const uint8_t* d_ascii, const uint64_t* d_offs, uint64_t n_reads,
+                         uint64_t total_bytes) {
+  if (!ctx) return MSC_ERR_STATE;
+  if (n_reads && (!d_offs || (!d_ascii && total_bytes))) return ctx->fail(MSC_ERR_INPUT, "reads: NULL device buffer");
+  CK(cudaSetDevice(ctx->device));
+  RC(reads_reserve(ctx, n_reads, total_bytes));
+  if (total_bytes) CK(cudaMemcpyAsync(ctx->rd_ascii.p, d_ascii, total_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (n_reads) CK(cudaMemcpyAsync(ctx->rd_offs.p, d_offs, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  else CK(cudaMemsetAsync(ctx->rd_offs.p, 0, sizeof(uint64_t), ctx->stream));
+  // the offsets were never seen by the host: validate them on the device
+  {
+    Filler f;
+    f.add(ctx->ctr(C_NLONG), 2 * sizeof(unsigned long long));  // C_PAD1 doubles as the "bad offsets" flag
+    RC(enqueue_fill(ctx, f));
+  }
+  if (n_reads) {
+    validate_read_offsets_kernel<<<grid_for(n_reads, 256), 256, 0, ctx->stream>>>(
+        ctx->rd_offs.as<uint64_t>(), n_reads, total_bytes, (uint64_t)ctx->win.MRL, ctx->ctr(C_PAD1));
+    LAUNCH_CHECK();
+  }
+  RC(sync_counters(ctx));  // nothing may index the ASCII buffer through unchecked offsets
+  if (ctx->h_counters[C_PAD1]) {
+    ctx->have_reads = false;
+    return ctx->fail(MSC_ERR_INPUT, "reads: device offsets are not monotone, do not end at total_bytes, or a read is longer "
+                     "than MaxReadLength");
+  }
+  ctx->have_reads = true;
+  RC(enqueue_build_reads(ctx));
+  RC(sync_counters(ctx));
   account_build_reads(ctx);
   if (!ctx->cfg.keep_ascii) ctx->rd_ascii.release();
   return MSC_OK;

@@ -100,6 +100,20 @@ __global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t* __restri
   if (lf) atomicOr(len_flags + r, lf);
 }
 
+// Offsets that arrive in device memory (msc_set_reads_device) are validated here instead of on
+// the host: offs[0]==0, monotone, offs[n]==total, every length <= max_len.
+__global__ void __launch_bounds__(256) validate_read_offsets_kernel(const uint64_t* __restrict__ offs, uint64_t n_reads,
+                                                                    uint64_t total, uint64_t max_len,
+                                                                    unsigned long long* __restrict__ bad) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_reads) return;
+  const uint64_t a = offs[i], b = offs[i + 1];
+  bool ok = b >= a && b - a <= max_len;
+  if (i == 0) ok = ok && a == 0;
+  if (i + 1 == n_reads) ok = ok && b == total;
+  if (!ok) atomicOr(bad, 1ull);
+}
+
 // Targets: the ASCII stream is the concatenation of all targets (no separators); one
 // thread packs 32 consecutive bases with two aligned 16-byte loads.  xplane must be
 // zero-initialised; only words containing X are written.  xsum bit w = word w has X.

@@ -98,6 +98,11 @@ class HotPath:
         self.n_reads = n
         self._check(self._lib.msc_set_reads(self._ctx, ascii_ptr, offs_ptr, n))
 
+    def set_reads_device(self, d_ascii_ptr: int, d_offs_ptr: int, n: int, total_bytes: int):
+        """Reads already resident on this context's device (e.g. after an NCCL broadcast)."""
+        self.n_reads = n
+        self._check(self._lib.msc_set_reads_device(self._ctx, d_ascii_ptr, d_offs_ptr, n, total_bytes))
+
     def set_targets_ptr(self, ascii_ptr: int, offs_ptr: int, n: int):
         self.n_targets = n
         self._check(self._lib.msc_set_targets(self._ctx, ascii_ptr, offs_ptr, n))

@@ -353,3 +353,33 @@ def test_cpp_executable_random_case_vs_oracle(tmp_path, oracle_bin):
     assert helpers.read_bytes(str(tmp_path / "res.txt")) == helpers.read_bytes(out["results"])
     assert helpers.read_bytes(str(tmp_path / "res.nonmatch.txt.fastq")) == helpers.read_bytes(out["nonmatch"])
     assert sz.read_file(str(tmp_path / "tmp" / "matches.txt.sz")) == helpers.read_bytes(out["matches"])
+
+
+def test_set_reads_device_equals_host_upload():
+    """msc_set_reads_device (reads already in HBM, e.g. after an NCCL broadcast) must give the same
+    matches as msc_set_reads, and must reject inconsistent offsets found on the device."""
+    import torch
+    from muscato_b200.engine import MuscatoError
+    syn = gendat.generate(5000, 80, 60, 900, seed=5, rev=True, mutated_fraction=0.6)
+    cfg = Config(Windows=[0, 25, 50], WindowWidth=16, MaxReadLength=80, PMatch=0.95, MinDinuc=4, MMTol=1).apply_defaults()
+    with _engine(cfg) as hp:
+        hp.set_reads((syn.read_ascii, syn.read_offs))
+        hp.set_targets((syn.target_ascii, syn.target_offs))
+        hp.run()
+        want = hp.fetch()
+    d_a = torch.from_numpy(syn.read_ascii.copy()).cuda()
+    d_o = torch.from_numpy(syn.read_offs.view(np.int64).copy()).cuda()
+    torch.cuda.synchronize()
+    with _engine(cfg) as hp:
+        hp.set_reads_device(d_a.data_ptr(), d_o.data_ptr(), syn.n_reads, int(d_a.numel()))
+        hp.set_targets((syn.target_ascii, syn.target_offs))
+        hp.run()
+        got = hp.fetch()
+        assert len(want) > 1000 and np.array_equal(want, got)
+        bad = d_o.clone()
+        bad[10] = bad[12]          # not monotone
+        torch.cuda.synchronize()
+        with pytest.raises(MuscatoError):
+            hp.set_reads_device(d_a.data_ptr(), bad.data_ptr(), syn.n_reads, int(d_a.numel()))
+        with pytest.raises(MuscatoError):
+            hp.set_reads_device(d_a.data_ptr(), d_o.data_ptr(), syn.n_reads, int(d_a.numel()) - 1)
