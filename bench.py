@@ -375,6 +375,11 @@ def run_ours(args, rank, local_rank, world):
     n_cand = st["n_candidates"]
     alg_bytes = shard_bases / 4.0 + 16.0 * n_cand   # T/4 + 16*H (Bloom front is L2-resident)
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
+    # DRAM traffic of the scan kernel per launch from the committed `ncu --set full` capture of this
+    # exact workload (profiles/ncu_full_r01_v2.txt: dram__bytes_read.sum 45.24 MB + dram__bytes_write.sum
+    # 1.66 MB, cold caches as ncu flushes them; 8.0 MB with warm caches, profiles/ncu_full_r01_v4_warm.txt).
+    default_workload = (world == 1 and args.reads == WORK["num_read"] and args.genes == WORK["num_gene"])
+    scan_traffic = 46.9e6 if default_workload else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
         "ms_per_step": 1000.0 * t_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -387,7 +392,7 @@ def run_ours(args, rank, local_rank, world):
         "gpu_launches": int(st["kernel_launches"]),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "scan_targets_kernel", "peak_source": peak_src,
+                     "traffic": scan_traffic, "kernel": "scan_targets_kernel", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_ms,
                      "positions_per_s": shard_bases / (scan_ms * 1e-3),
                      "note": "Bloom front + key table are L2-resident at this size, so SURVEY 8(d) counts T/4 + 16*H only; "
