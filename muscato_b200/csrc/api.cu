@@ -80,7 +80,10 @@ struct msc_ctx {
   int device = 0;
   int sm_count = 148;
   int scan_grid = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // every kernel runs here
+  cudaStream_t copy_stream = nullptr;  // input H2D copies: overlap with kernels of the previous input
+  cudaEvent_t ev_copy = nullptr, ev_compute = nullptr;
+  bool pend_reads = false, pend_targets = false;  // enqueued builds whose counters/timers are not read yet
   cudaEvent_t ev[EV_COUNT] = {};
   std::string err;
   msc_stats st{};
@@ -232,12 +235,40 @@ int enqueue_fill(msc_ctx* ctx, const Filler& f) {
   return MSC_OK;
 }
 
+void account_build_reads(msc_ctx* ctx);
+void account_pack_targets(msc_ctx* ctx);
+
+// The one host synchronisation of a call: brings the counter block over and books the
+// counters / timers of every build that was enqueued since the last one.
 int sync_counters(msc_ctx* ctx) {
   CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                      ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->st.d2h_bytes += C_COUNT * sizeof(unsigned long long);
+  if (ctx->pend_reads) account_build_reads(ctx);
+  if (ctx->pend_targets) account_pack_targets(ctx);
+  ctx->pend_reads = ctx->pend_targets = false;
   if (ctx->trace) ctx->trace_dump();
+  return MSC_OK;
+}
+
+// Input upload on the copy stream.  The copy waits for everything already enqueued on the
+// compute stream (the destination may still be read by earlier kernels); the compute stream
+// waits for the copy; the HOST only waits for the copy, because the caller's buffers are
+// borrowed for the duration of the call -- the kernels that consume the data keep running while
+// the caller prepares (or uploads) its next input.
+int begin_upload(msc_ctx* ctx) {
+  CK(cudaEventRecord(ctx->ev_compute, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_compute, 0));
+  return MSC_OK;
+}
+int end_upload(msc_ctx* ctx) {
+  CK(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+  return MSC_OK;
+}
+int wait_upload(msc_ctx* ctx) {
+  CK(cudaEventSynchronize(ctx->ev_copy));
   return MSC_OK;
 }
 
@@ -315,6 +346,7 @@ int enqueue_build_reads(msc_ctx* ctx) {
   }
   CK(cudaEventRecord(ctx->ev[EV_BUILD1], ctx->stream));
   ctx->have_cand = ctx->have_confirm = ctx->have_combine = false;
+  ctx->pend_reads = true;
   return MSC_OK;
 }
 
@@ -346,6 +378,7 @@ int enqueue_pack_targets(msc_ctx* ctx) {
   LAUNCH_CHECK();
   CK(cudaEventRecord(ctx->ev[EV_PACKT1], ctx->stream));
   ctx->have_cand = ctx->have_confirm = ctx->have_combine = false;
+  ctx->pend_targets = true;
   return MSC_OK;
 }
 
@@ -618,10 +651,6 @@ int run_pipeline(msc_ctx* ctx, int rebuild_what, bool do_scan, bool do_confirm, 
     }
     if (do_combine) RC(enqueue_combine(ctx));
     RC(sync_counters(ctx));
-    if (attempt == 0) {
-      if (rebuild_what & 1) account_build_reads(ctx);
-      if (rebuild_what & 2) account_pack_targets(ctx);
-    }
     int rc = MSC_OK;
     if (do_scan) rc = finish_scan(ctx);
     if (rc == MSC_OK && do_confirm) rc = finish_confirm(ctx);
@@ -700,6 +729,9 @@ msc_ctx* msc_create(const msc_config* config, char* errbuf, uint64_t errlen) {
   ctx->win.min_dinuc = c.min_dinuc;
   for (int k = 0; k < c.n_windows; k++) ctx->win.windows[k] = c.windows[k];
   bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < EV_COUNT; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
   ok = ok && ctx->counters.reserve(C_COUNT * sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaMallocHost(&ctx->h_counters, C_COUNT * sizeof(unsigned long long)) == cudaSuccess;
@@ -729,6 +761,7 @@ msc_ctx* msc_create(const msc_config* config, char* errbuf, uint64_t errlen) {
 void msc_destroy(msc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->rd_ascii,    &ctx->rd_offs,   &ctx->rd_words, &ctx->rd_x,      &ctx->len_flags, &ctx->validmask,
                     &ctx->tab_fp,      &ctx->tab_item0, &ctx->tab_cnt,  &ctx->tab_start, &ctx->tab_fill,  &ctx->bloom,
@@ -741,6 +774,9 @@ void msc_destroy(msc_ctx* ctx) {
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
   for (auto& te : ctx->trace_ev) cudaEventDestroy(te.second);
+  if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+  if (ctx->ev_compute) cudaEventDestroy(ctx->ev_compute);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -807,15 +843,19 @@ int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint
     total = offs[n_reads];
   }
   RC(reads_reserve(ctx, n_reads, total));
-  if (total) CK(cudaMemcpyAsync(ctx->rd_ascii.p, ascii, total, cudaMemcpyHostToDevice, ctx->stream));
-  if (n_reads) CK(cudaMemcpyAsync(ctx->rd_offs.p, offs, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-  else CK(cudaMemsetAsync(ctx->rd_offs.p, 0, sizeof(uint64_t), ctx->stream));
+  RC(begin_upload(ctx));
+  if (total) CK(cudaMemcpyAsync(ctx->rd_ascii.p, ascii, total, cudaMemcpyHostToDevice, ctx->copy_stream));
+  if (n_reads) CK(cudaMemcpyAsync(ctx->rd_offs.p, offs, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+  else CK(cudaMemsetAsync(ctx->rd_offs.p, 0, sizeof(uint64_t), ctx->copy_stream));
+  RC(end_upload(ctx));
   ctx->st.h2d_bytes += total + (n_reads + 1) * sizeof(uint64_t);
   ctx->have_reads = true;
-  RC(enqueue_build_reads(ctx));
-  RC(sync_counters(ctx));  // the caller's buffers are only borrowed for the call
-  account_build_reads(ctx);
-  if (!ctx->cfg.keep_ascii) ctx->rd_ascii.release();
+  RC(enqueue_build_reads(ctx));  // runs behind the copy; its counters are booked at the next sync
+  RC(wait_upload(ctx));          // the caller's buffers are only borrowed for the call
+  if (!ctx->cfg.keep_ascii) {
+    RC(sync_counters(ctx));
+    ctx->rd_ascii.release();
+  }
   return MSC_OK;
 }
 
@@ -847,8 +887,7 @@ int msc_set_reads_device(msc_ctx* ctx, const uint8_t* d_ascii, const uint64_t* d
   }
   ctx->have_reads = true;
   RC(enqueue_build_reads(ctx));
-  RC(sync_counters(ctx));
-  account_build_reads(ctx);
+  RC(sync_counters(ctx));  // d_ascii / d_offs are only borrowed for the call
   if (!ctx->cfg.keep_ascii) ctx->rd_ascii.release();
   return MSC_OK;
 }
@@ -879,14 +918,18 @@ int msc_set_targets(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, ui
   CK(ctx->tg_words.reserve(ctx->n_words_alloc * sizeof(uint64_t)));
   CK(ctx->tg_x.reserve(ctx->n_words_alloc * sizeof(uint64_t)));
   CK(ctx->xsum.reserve((ctx->n_words_alloc / 32 + 4) * sizeof(uint32_t)));
-  if (total) CK(cudaMemcpyAsync(ctx->tg_ascii.p, ascii, total, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->tg_off.p, off32.data(), (n_targets + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  RC(begin_upload(ctx));
+  if (total) CK(cudaMemcpyAsync(ctx->tg_ascii.p, ascii, total, cudaMemcpyHostToDevice, ctx->copy_stream));
+  CK(cudaMemcpyAsync(ctx->tg_off.p, off32.data(), (n_targets + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+  RC(end_upload(ctx));
   ctx->st.h2d_bytes += total + (n_targets + 1) * sizeof(uint32_t);
   ctx->have_targets = true;
   RC(enqueue_pack_targets(ctx));
-  CK(cudaStreamSynchronize(ctx->stream));  // off32 is a local; the caller's buffers are only borrowed
-  account_pack_targets(ctx);
-  if (!ctx->cfg.keep_ascii) ctx->tg_ascii.release();
+  RC(wait_upload(ctx));  // off32 is a local; the caller's buffers are only borrowed
+  if (!ctx->cfg.keep_ascii) {
+    RC(sync_counters(ctx));
+    ctx->tg_ascii.release();
+  }
   return MSC_OK;
 }
 
@@ -985,8 +1028,13 @@ int msc_fetch_matches(msc_ctx* ctx, msc_match** out, uint64_t* n) {
   return MSC_OK;
 }
 
-int msc_get_stats(const msc_ctx* ctx, msc_stats* out) {
-  if (!ctx || !out) return MSC_ERR_STATE;
+int msc_get_stats(const msc_ctx* cctx, msc_stats* out) {
+  if (!cctx || !out) return MSC_ERR_STATE;
+  msc_ctx* ctx = const_cast<msc_ctx*>(cctx);
+  if (ctx->pend_reads || ctx->pend_targets) {  // a build is still in flight: book it first
+    CK(cudaSetDevice(ctx->device));
+    RC(sync_counters(ctx));
+  }
   *out = ctx->st;
   return MSC_OK;
 }
@@ -1010,7 +1058,7 @@ int msc_dump_keys(msc_ctx* ctx, msc_key_rec** out, uint64_t* n) {
   if (!ctx || !out || !n) return MSC_ERR_STATE;
   if (!ctx->have_reads) return ctx->fail(MSC_ERR_STATE, "msc_dump_keys: no reads set");
   CK(cudaSetDevice(ctx->device));
-  CK(cudaStreamSynchronize(ctx->stream));
+  RC(sync_counters(ctx));
   // group members: slot-resident first items + the CSR of further members
   const uint64_t slots = 1ull << ctx->lg_slots;
   std::vector<uint64_t> fps(slots);

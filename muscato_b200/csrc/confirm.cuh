@@ -251,7 +251,7 @@ constexpr int kPairsPerThread = 4;
 constexpr int kChunkPairs = kPairsPerThread * 256;
 
 template <int MODE>
-__global__ void __launch_bounds__(256) confirm_pairs_kernel(const WinCfg cfg, const ConfirmArgs a) {
+__global__ void __launch_bounds__(256, 8) confirm_pairs_kernel(const WinCfg cfg, const ConfirmArgs a) {
   __shared__ uint4 s_out[8][kPairsPerThread * 32];
   const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
   uint4* my_out = s_out[wid];
