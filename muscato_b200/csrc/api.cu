@@ -331,13 +331,11 @@ int enqueue_build_reads(msc_ctx* ctx) {
     a.bloom = ctx->bloom.as<unsigned long long>();
     a.lg_bloom = ctx->lg_bloom;
     a.dup_slot = ctx->dup_slot.as<uint32_t>();
-    a.n_groups = ctx->ctr(C_NGROUPS);
-    a.n_dup = ctx->ctr(C_NDUP);
     build_insert_kernel<<<grid_for(n_items, 256), 256, 0, ctx->stream>>>(a);
     LAUNCH_CHECK();
   }
   RC(enqueue_exclusive_scan<uint32_t>(ctx, ctx->tab_cnt.as<uint32_t>(), nullptr, slots, ctx->tab_start.as<uint32_t>(),
-                                      true, ctx->ctr(C_SCRATCH)));
+                                      true, ctx->ctr(C_NDUP)));  // grand total = members beyond the first of their group
   if (U) {
     build_fill_kernel<<<grid_for(n_items, 256), 256, 0, ctx->stream>>>(
         ctx->dup_slot.as<uint32_t>(), n_items, ctx->tab_start.as<uint32_t>(), ctx->tab_fill.as<uint32_t>(),
@@ -352,8 +350,8 @@ int enqueue_build_reads(msc_ctx* ctx) {
 
 void account_build_reads(msc_ctx* ctx) {
   ctx->n_keys = ctx->h_counters[C_NKEYS];
-  ctx->n_groups = ctx->h_counters[C_NGROUPS];
   ctx->n_dup = ctx->h_counters[C_NDUP];
+  ctx->n_groups = ctx->n_keys - ctx->n_dup;
   ctx->st.n_reads = ctx->n_reads;
   ctx->st.n_keys = ctx->n_keys;
   ctx->st.n_key_groups = ctx->n_groups;

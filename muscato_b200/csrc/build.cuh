@@ -41,9 +41,10 @@ struct BuildArgs {
   unsigned long long* bloom;
   int lg_bloom;
   uint32_t* dup_slot;    // per item: 1 + slot if the item is a further member of its group, else 0
-  unsigned long long* n_groups;  // distinct fingerprints
-  unsigned long long* n_dup;     // items beyond the first of their group
 };
+// (The number of further members, n_dup, is the grand total of the tab_cnt scan and the number of
+// distinct fingerprints is n_keys - n_dup: no per-warp counter atomics in the insert kernel --
+// ~10^6 same-address atomics cost more than the inserts themselves.)
 
 // Pass A1: per read, which windows are valid (length rule + entropy rule) and the fingerprint of
 // each valid window key.  Pure ALU over the packed words; item = read * nwin + window.
@@ -88,7 +89,6 @@ __global__ void __launch_bounds__(256) window_keys_kernel(const WinCfg cfg, cons
 // by pass B.
 __global__ void __launch_bounds__(256) build_insert_kernel(const BuildArgs a) {
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t ng = 0, nd = 0;
   if (idx < a.n_items) {
     const uint64_t fp = __ldg(a.fps + idx);
     uint32_t dup = 0;
@@ -104,24 +104,16 @@ __global__ void __launch_bounds__(256) build_insert_kernel(const BuildArgs a) {
         s = (s + 1) & smask;
       }
       if (first) {
-        ng = 1;
         a.tab_item0[s] = (uint32_t)idx;
         const unsigned long long bm =
             (unsigned long long)bloom_mask_lo(fp) | ((unsigned long long)bloom_mask_hi(fp) << 32);
         atomicOr(a.bloom + bloom_index(fp, a.lg_bloom), bm);
       } else {
-        nd = 1;
         atomicAdd(a.tab_cnt + s, 1u);
         dup = (uint32_t)s + 1u;
       }
     }
     a.dup_slot[idx] = dup;
-  }
-  ng = __reduce_add_sync(0xffffffffu, ng);
-  nd = __reduce_add_sync(0xffffffffu, nd);
-  if ((threadIdx.x & 31u) == 0) {
-    if (ng) atomicAdd(a.n_groups, (unsigned long long)ng);
-    if (nd) atomicAdd(a.n_dup, (unsigned long long)nd);
   }
 }
 
