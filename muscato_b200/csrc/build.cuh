@@ -79,8 +79,16 @@ __global__ void __launch_bounds__(256) window_keys_kernel(const WinCfg cfg, cons
     }
     validmask[r] = vm;
   }
+  // one counter atomic per block (same-address atomics serialise)
+  __shared__ uint32_t s_nk[8];
   nk = __reduce_add_sync(0xffffffffu, nk);
-  if ((threadIdx.x & 31u) == 0 && nk) atomicAdd(n_keys, (unsigned long long)nk);
+  if ((threadIdx.x & 31u) == 0) s_nk[threadIdx.x >> 5] = nk;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < 8; w++) t += s_nk[w];
+    if (t) atomicAdd(n_keys, (unsigned long long)t);
+  }
 }
 
 // Pass A2: one thread per item.  Claim / find the table slot of the fingerprint and set the

@@ -249,16 +249,27 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
 // the slowest pair of another warp.  The pass counter costs one atomic per warp.
 constexpr int kPairsPerThread = 4;
 constexpr int kChunkPairs = kPairsPerThread * 256;
+constexpr int kOutStage = 128;  // per-warp output staging (records); flushed when nearly full
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 8) confirm_pairs_kernel(const WinCfg cfg, const ConfirmArgs a) {
-  __shared__ uint4 s_out[8][kPairsPerThread * 32];
+__global__ void __launch_bounds__(256, 6) confirm_pairs_kernel(const WinCfg cfg, const ConfirmArgs a) {
+  __shared__ uint4 s_out[8][kOutStage];
   const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
   uint4* my_out = s_out[wid];
   const uint64_t n_pairs = *a.n_pairs_ptr;
   const uint64_t n_blocks256 = min((uint64_t)((n_pairs + 255) / 256), a.block_cap);
   const uint64_t n_chunks = (n_blocks256 + kPairsPerThread - 1) / kPairsPerThread;
   uint32_t n_pass = 0;
+  uint32_t n_out = 0;  // records staged by this warp (warp-uniform), carried across chunks
+  auto flush_out = [&]() {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(a.n_match, (unsigned long long)n_out);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (uint32_t t = lane; t < n_out; t += 32)
+      if (base + t < a.match_cap) a.matches[base + t] = my_out[t];
+    __syncwarp();
+    n_out = 0;
+  };
   for (uint64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
     const uint64_t i0 = ch * (uint64_t)kChunkPairs + (uint64_t)threadIdx.x * kPairsPerThread;
     const bool live = i0 < n_pairs && (i0 >> 8) < n_blocks256;
@@ -269,7 +280,6 @@ __global__ void __launch_bounds__(256, 8) confirm_pairs_kernel(const WinCfg cfg,
       c = upper_bound_dev<uint64_t>(a.pstart, clo, chi + 1, i0) - 1;
       c_end = __ldg(a.pstart + c + 1);
     }
-    uint32_t n_out = 0;  // records staged by this warp (warp-uniform)
 #pragma unroll 1
     for (int j = 0; j < kPairsPerThread; j++) {
       const uint64_t i = i0 + j;
@@ -285,17 +295,11 @@ __global__ void __launch_bounds__(256, 8) confirm_pairs_kernel(const WinCfg cfg,
       const unsigned m = __ballot_sync(0xffffffffu, has);
       if (has) my_out[n_out + __popc(m & ((1u << lane) - 1u))] = rec;
       n_out += __popc(m);
+      __syncwarp();
+      if (n_out > kOutStage - 32) flush_out();
     }
-    __syncwarp();
-    if (n_out) {
-      unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(a.n_match, (unsigned long long)n_out);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      for (uint32_t t = lane; t < n_out; t += 32)
-        if (base + t < a.match_cap) a.matches[base + t] = my_out[t];
-    }
-    __syncwarp();
   }
+  if (n_out) flush_out();
   n_pass = __reduce_add_sync(0xffffffffu, n_pass);
   if (lane == 0 && n_pass) atomicAdd(a.n_pass, (unsigned long long)n_pass);
 }

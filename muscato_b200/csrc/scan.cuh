@@ -22,6 +22,7 @@ constexpr int kScanBlock = 256;
 constexpr int kTileWords = 256;                       // one 32-base word per thread per tile
 constexpr int kTileCopyWords = kTileWords + 2;        // halo word + 1 (byte count multiple of 16)
 constexpr int kTileSmemWords = kTileWords + 8;
+constexpr int kStageCap = 128;                        // per-warp candidate staging (entries)
 
 struct ScanArgs {
   const uint64_t* tg_words;
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(kScanBlock) scan_targets_kernel(const ScanArgs
   __shared__ alignas(128) uint64_t tile[2][kTileSmemWords];
   __shared__ alignas(8) uint64_t bar[2];
   __shared__ uint16_t queue[kScanBlock / 32][1024];
+  __shared__ uint2 stage[kScanBlock / 32][kStageCap];  // found (slot, position) pairs, flushed when nearly full
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31u, warp = tid >> 5;
   constexpr uint32_t kBytes = kTileCopyWords * sizeof(uint64_t);
@@ -75,6 +77,18 @@ __global__ void __launch_bounds__(kScanBlock) scan_targets_kernel(const ScanArgs
   int buf = 0;
   uint32_t n_pass = 0;
   uint16_t* q = queue[warp];
+  uint2* st = stage[warp];
+  uint32_t n_st = 0;  // staged candidates of this warp (warp-uniform)
+  // One global atomic per flush instead of one per drain round: same-address atomics serialise.
+  auto flush_stage = [&]() {
+    unsigned long long out0 = 0;
+    if (lane == 0) out0 = atomicAdd(a.n_cand, (unsigned long long)n_st);
+    out0 = __shfl_sync(0xffffffffu, out0, 0);
+    for (uint32_t i = lane; i < n_st; i += 32)
+      if (out0 + i < a.cand_cap) a.cand[out0 + i] = st[i];
+    __syncwarp();
+    n_st = 0;
+  };
   for (; t < a.n_tiles; t += gridDim.x) {
     const uint64_t tn = t + gridDim.x;
     if (tid == 0 && tn < a.n_tiles) {
@@ -157,13 +171,10 @@ __global__ void __launch_bounds__(kScanBlock) scan_targets_kernel(const ScanArgs
         if (active) slot = table_find(a.tab_fp, a.lg_slots, key_fp(window_at(l, h, j, kmask), window_at(xl, xh, j, kmask)));
         const unsigned found = __ballot_sync(0xffffffffu, slot >= 0);
         if (found) {
-          unsigned long long out0 = 0;
-          if (lane == 0) out0 = atomicAdd(a.n_cand, (unsigned long long)__popc(found));
-          out0 = __shfl_sync(0xffffffffu, out0, 0);
-          if (slot >= 0) {
-            const unsigned long long o = out0 + __popc(found & ((1u << lane) - 1u));
-            if (o < a.cand_cap) a.cand[o] = make_uint2((uint32_t)slot, (uint32_t)(wbase + e));
-          }
+          if (slot >= 0) st[n_st + __popc(found & ((1u << lane) - 1u))] = make_uint2((uint32_t)slot, (uint32_t)(wbase + e));
+          n_st += __popc(found);
+          __syncwarp();
+          if (n_st > kStageCap - 32) flush_stage();
         }
       }
       __syncwarp();
@@ -171,6 +182,7 @@ __global__ void __launch_bounds__(kScanBlock) scan_targets_kernel(const ScanArgs
     __syncthreads();  // all reads of tile[buf] are done before it is refilled
     buf ^= 1;
   }
+  if (n_st) flush_stage();
   n_pass = __reduce_add_sync(0xffffffffu, n_pass);
   if (lane == 0 && n_pass) atomicAdd(a.n_bloom_pass, (unsigned long long)n_pass);
 }
