@@ -95,7 +95,9 @@ struct msc_ctx {
   // key table
   int lg_slots = 0, lg_bloom = 0;
   uint64_t n_keys = 0, n_groups = 0, n_dup = 0;
-  DevBuf tab_fp, tab_item0, tab_cnt, tab_start, tab_fill, bloom, items, dup_slot, fps;
+  DevBuf tab_fp, tab_item0, tab_cnt, tab_start, tab_fill, pass_cnt, bloom, items, dup_slot, fps;
+  // zero-fills already issued by a merged prologue launch (consumed by the stage that owns them)
+  struct { bool reads = false, targets = false, scan = false, pairs = false, combine = false; } pro;
   // targets
   uint64_t n_targets = 0, n_bases = 0, n_words_alloc = 0, n_tiles = 0;
   bool have_targets = false;
@@ -228,6 +230,31 @@ struct Filler {
   }
 };
 
+// The zero-fills every stage needs before it runs.  A fused run issues them all in ONE prologue
+// launch (add_*_fills + ctx->pro flags); a stage enqueued on its own issues just its own.
+void add_reads_fills(msc_ctx* ctx, Filler& f) {
+  f.add(ctx->len_flags.p, (ctx->n_reads + 1) * sizeof(uint32_t));
+  f.add(ctx->ctr(C_NKEYS), 4 * sizeof(unsigned long long));  // C_NKEYS, C_NGROUPS, C_NDUP, C_SCRATCH
+}
+void add_targets_fills(msc_ctx* ctx, Filler& f) {
+  f.add(ctx->tg_x.p, ctx->n_words_alloc * sizeof(uint64_t));
+  f.add(ctx->xsum.p, (ctx->n_words_alloc / 32 + 4) * sizeof(uint32_t));
+  f.add(ctx->ctr(C_TGX), 2 * sizeof(unsigned long long));
+}
+void add_scan_fills(msc_ctx* ctx, Filler& f) {
+  f.add(ctx->ctr(C_NCAND), 2 * sizeof(unsigned long long));  // C_NCAND, C_BLOOMPASS
+}
+void add_pairs_fills(msc_ctx* ctx, Filler& f) {
+  f.add(ctx->ctr(C_NMATCH), 4 * sizeof(unsigned long long));  // C_NMATCH, C_NPASS, C_NOVER, C_NOUT
+  f.add(ctx->best.p, (ctx->n_reads + 1) * sizeof(uint32_t), MSC_NO_MATCH);
+  f.add(ctx->pass_cnt.p, (1ull << ctx->lg_slots) * sizeof(uint32_t));
+}
+void add_combine_fills(msc_ctx* ctx, Filler& f) {
+  f.add(ctx->rcount.p, (ctx->n_reads + 1) * sizeof(uint32_t));
+  f.add(ctx->rfill.p, (ctx->n_reads + 1) * sizeof(uint32_t));
+  f.add(ctx->ctr(C_NLONG), 2 * sizeof(unsigned long long));
+}
+
 int enqueue_fill(msc_ctx* ctx, const Filler& f) {
   if (f.job.n == 0) return MSC_OK;
   fill_buffers_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, ctx->stream>>>(f.job);
@@ -289,12 +316,12 @@ int enqueue_build_reads(msc_ctx* ctx) {
   if (ctx->trace) ctx->trace_mark("start build_reads");
   const uint64_t slots = 1ull << ctx->lg_slots;
   const uint64_t bwords = 1ull << ctx->lg_bloom;
-  {
+  if (!ctx->pro.reads) {
     Filler f;
-    f.add(ctx->len_flags.p, (U + 1) * sizeof(uint32_t));
-    f.add(ctx->ctr(C_NKEYS), 4 * sizeof(unsigned long long));  // C_NKEYS, C_NGROUPS, C_NDUP, C_SCRATCH
+    add_reads_fills(ctx, f);
     RC(enqueue_fill(ctx, f));
   }
+  ctx->pro.reads = false;
   if (U) {
     const int rpb = std::max(1, 256 / S);  // whole reads per block
     const size_t smem = (size_t)rpb * (size_t)ctx->win.MRL + 64;
@@ -363,13 +390,12 @@ void account_build_reads(msc_ctx* ctx) {
 
 int enqueue_pack_targets(msc_ctx* ctx) {
   CK(cudaEventRecord(ctx->ev[EV_PACKT0], ctx->stream));
-  {
+  if (!ctx->pro.targets) {
     Filler f;
-    f.add(ctx->tg_x.p, ctx->n_words_alloc * sizeof(uint64_t));
-    f.add(ctx->xsum.p, (ctx->n_words_alloc / 32 + 4) * sizeof(uint32_t));
-    f.add(ctx->ctr(C_TGX), 2 * sizeof(unsigned long long));
+    add_targets_fills(ctx, f);
     RC(enqueue_fill(ctx, f));
   }
+  ctx->pro.targets = false;
   pack_targets_kernel<<<grid_for(ctx->n_words_alloc, 256), 256, 0, ctx->stream>>>(
       ctx->tg_ascii.as<uint8_t>(), ctx->n_bases, ctx->tg_words.as<uint64_t>(), ctx->n_words_alloc,
       ctx->tg_x.as<uint64_t>(), ctx->xsum.as<uint32_t>(), ctx->ctr(C_TGX));
@@ -394,11 +420,12 @@ int enqueue_scan(msc_ctx* ctx) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_targets_kernel, kScanBlock, 0));
     ctx->scan_grid = ctx->sm_count * std::max(1, blocks_per_sm);
   }
-  {
+  if (!ctx->pro.scan) {
     Filler f;
-    f.add(ctx->ctr(C_NCAND), 2 * sizeof(unsigned long long));  // C_NCAND, C_BLOOMPASS
+    add_scan_fills(ctx, f);
     RC(enqueue_fill(ctx, f));
   }
+  ctx->pro.scan = false;
   CK(cudaEventRecord(ctx->ev[EV_SCAN0], ctx->stream));
   if (ctx->n_tiles && ctx->n_reads) {
     ScanArgs a{};
@@ -446,13 +473,12 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   LAUNCH_CHECK();
   CK(cudaEventRecord(ctx->ev[EV_EXPAND1], ctx->stream));
 
-  {
+  if (!ctx->pro.pairs) {
     Filler f;
-    f.add(ctx->ctr(C_NMATCH), 4 * sizeof(unsigned long long));  // C_NMATCH, C_NPASS, C_NOVER, C_NOUT
-    f.add(ctx->best.p, (ctx->n_reads + 1) * sizeof(uint32_t), MSC_NO_MATCH);
-    f.add(ctx->tab_fill.p, (1ull << ctx->lg_slots) * sizeof(uint32_t));
+    add_pairs_fills(ctx, f);
     RC(enqueue_fill(ctx, f));
   }
+  ctx->pro.pairs = false;
   ConfirmArgs a{};
   a.cand = ctx->cand.as<uint2>();
   a.cinfo = ctx->cinfo.as<uint2>();
@@ -463,7 +489,7 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   a.tab_item0 = ctx->tab_item0.as<uint32_t>();
   a.tab_start = ctx->tab_start.as<uint32_t>();
   a.items = ctx->items.as<uint32_t>();
-  a.pass_cnt = ctx->tab_fill.as<uint32_t>();
+  a.pass_cnt = ctx->pass_cnt.as<uint32_t>();
   a.rd_words = ctx->rd_words.as<uint64_t>();
   a.rd_x = ctx->rd_x.as<uint64_t>();
   a.len_flags = ctx->len_flags.as<uint32_t>();
@@ -501,7 +527,7 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
     // happen in a key group with more than MaxMatches passing pairs.
     const uint64_t slots = 1ull << ctx->lg_slots;
     overflow_count_kernel<<<grid_for(slots, 256), 256, 0, ctx->stream>>>(
-        ctx->tab_fill.as<uint32_t>(), slots, (unsigned long long)ctx->cfg.max_matches, ctx->ctr(C_NPASS),
+        ctx->pass_cnt.as<uint32_t>(), slots, (unsigned long long)ctx->cfg.max_matches, ctx->ctr(C_NPASS),
         ctx->ctr(C_NOVER));
     LAUNCH_CHECK();
   }
@@ -517,13 +543,12 @@ int enqueue_combine(msc_ctx* ctx) {
   CK(ctx->match_out.reserve((mcap + 1) * sizeof(uint4)));
   CK(ctx->long_list.reserve((U + 1) * sizeof(uint32_t)));
   CK(cudaEventRecord(ctx->ev[EV_COMB0], ctx->stream));
-  {
+  if (!ctx->pro.combine) {
     Filler f;
-    f.add(ctx->rcount.p, (U + 1) * sizeof(uint32_t));
-    f.add(ctx->rfill.p, (U + 1) * sizeof(uint32_t));
-    f.add(ctx->ctr(C_NLONG), 2 * sizeof(unsigned long long));
+    add_combine_fills(ctx, f);
     RC(enqueue_fill(ctx, f));
   }
+  ctx->pro.combine = false;
   const unsigned g = (unsigned)ctx->sm_count * 8;
   combine_count_kernel<<<g, 256, 0, ctx->stream>>>(ctx->match_pre.as<uint4>(), ctx->ctr(C_NMATCH), mcap,
                                                    ctx->best.as<uint32_t>(), (uint32_t)ctx->cfg.mmtol,
@@ -637,6 +662,22 @@ int mark_expand_start(msc_ctx* ctx) {
 // [rebuild +] screen [+ confirm + combine] with a single synchronisation; repeated from the
 // scan when a buffer had to grow.
 int run_pipeline(msc_ctx* ctx, int rebuild_what, bool do_scan, bool do_confirm, bool do_combine) {
+  // Fused run: all zero-fills of the stages below in one prologue launch.
+  if ((int)((rebuild_what & 1) != 0) + (int)((rebuild_what & 2) != 0) + (int)do_scan + (int)do_confirm + (int)do_combine > 1) {
+    Filler f;
+    if (rebuild_what & 1) { add_reads_fills(ctx, f); ctx->pro.reads = true; }
+    if (rebuild_what & 2) { add_targets_fills(ctx, f); ctx->pro.targets = true; }
+    if (do_scan) { add_scan_fills(ctx, f); ctx->pro.scan = true; }
+    if (do_confirm) { add_pairs_fills(ctx, f); ctx->pro.pairs = true; }
+    if (do_combine) {
+      const uint64_t U = ctx->n_reads;
+      CK(ctx->rcount.reserve((U + 1) * sizeof(uint32_t)));
+      CK(ctx->rfill.reserve((U + 1) * sizeof(uint32_t)));
+      add_combine_fills(ctx, f);
+      ctx->pro.combine = true;
+    }
+    RC(enqueue_fill(ctx, f));
+  }
   for (int attempt = 0; attempt < 5; attempt++) {
     if (attempt == 0) {
       if (rebuild_what & 1) RC(enqueue_build_reads(ctx));
@@ -762,7 +803,7 @@ void msc_destroy(msc_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->rd_ascii,    &ctx->rd_offs,   &ctx->rd_words, &ctx->rd_x,      &ctx->len_flags, &ctx->validmask,
-                    &ctx->tab_fp,      &ctx->tab_item0, &ctx->tab_cnt,  &ctx->tab_start, &ctx->tab_fill,  &ctx->bloom,
+                    &ctx->tab_fp,      &ctx->tab_item0, &ctx->tab_cnt,  &ctx->tab_start, &ctx->tab_fill,  &ctx->pass_cnt, &ctx->bloom,
                     &ctx->items,       &ctx->dup_slot,  &ctx->fps,      &ctx->tg_ascii,  &ctx->tg_off,    &ctx->tg_words,
                     &ctx->tg_x,        &ctx->xsum,      &ctx->cand,     &ctx->cinfo,     &ctx->sizes,     &ctx->pstart,
                     &ctx->block_first, &ctx->match_pre, &ctx->best,     &ctx->rcount,    &ctx->rstart,    &ctx->rfill,
@@ -813,6 +854,7 @@ static int reads_reserve(msc_ctx* ctx, uint64_t n_reads, uint64_t total) {
   CK(ctx->tab_cnt.reserve(slots * sizeof(uint32_t)));
   CK(ctx->tab_start.reserve((slots + 1) * sizeof(uint32_t)));
   CK(ctx->tab_fill.reserve(slots * sizeof(uint32_t)));
+  CK(ctx->pass_cnt.reserve(slots * sizeof(uint32_t)));
   CK(ctx->bloom.reserve((1ull << ctx->lg_bloom) * sizeof(uint64_t)));
   CK(ctx->items.reserve((n_reads * nwin + 1) * sizeof(uint32_t)));
   CK(ctx->dup_slot.reserve((n_reads * nwin + 1) * sizeof(uint32_t)));

@@ -8,7 +8,7 @@
 namespace msc {
 
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
+constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 __device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_t* total, uint64_t* warp_sums) {
@@ -36,12 +36,13 @@ __device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_
   return warp_sums[wid] + inc - v;
 }
 
-// One launch that fills up to six device buffers with a byte value each (replaces a train of
+// One launch that fills up to kMaxFillJobs device buffers with a byte value each (replaces a train of
 // cudaMemsetAsync calls: every memset is its own engine hand-over on the stream).
+constexpr int kMaxFillJobs = 12;
 struct FillJob {
-  void* ptr[6];
-  unsigned long long bytes[6];  // multiples of 16 (buffers are over-allocated accordingly)
-  unsigned int value[6];        // 32-bit pattern
+  void* ptr[kMaxFillJobs];
+  unsigned long long bytes[kMaxFillJobs];  // multiples of 16 (buffers are over-allocated accordingly)
+  unsigned int value[kMaxFillJobs];        // 32-bit pattern
   int n;
 };
 
