@@ -383,3 +383,46 @@ def test_set_reads_device_equals_host_upload():
             hp.set_reads_device(d_a.data_ptr(), bad.data_ptr(), syn.n_reads, int(d_a.numel()))
         with pytest.raises(MuscatoError):
             hp.set_reads_device(d_a.data_ptr(), d_o.data_ptr(), syn.n_reads, int(d_a.numel()) - 1)
+
+
+def _repeat_case(rng, n_genes, n_reads, read_len):
+    """BASELINE config[4]: low-entropy, repetitive targets (tandem repeats of period 1-6 and
+    low-complexity blocks interleaved with random sequence) with reads sampled from them."""
+    genes = []
+    pool = [helpers.random_dna(rng, int(p)) for p in (1, 2, 3, 4, 5, 6)]   # shared repeat units
+    for g in range(n_genes):
+        parts = []
+        while sum(map(len, parts)) < 500:
+            u = rng.random()
+            if u < 0.5:
+                unit = pool[int(rng.integers(0, len(pool)))]
+                parts.append(unit * int(rng.integers(10, 40)))
+            elif u < 0.7:
+                parts.append(helpers.random_dna(rng, int(rng.integers(20, 60)), b"AT"))
+            else:
+                parts.append(helpers.random_dna(rng, int(rng.integers(20, 80))))
+        genes.append(b"".join(parts))
+    reads = []
+    for _ in range(n_reads):
+        g = genes[int(rng.integers(0, n_genes))]
+        p = int(rng.integers(0, len(g) - read_len))
+        a = np.frombuffer(g[p:p + read_len], dtype=np.uint8).copy()
+        m = rng.random(read_len) < 0.02
+        a[m] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(m.sum()))]
+        reads.append(bytes(a))
+    return reads, genes
+
+
+@pytest.mark.parametrize("mm,mode,mindinuc", [(1000000, "best", 1), (1000, "best", 2), (300, "first", 3)])
+def test_high_multiplicity_stress_vs_oracle(mm, mode, mindinuc, tmp_path, oracle_bin):
+    """Hit explosion: thousands of candidates x dozens of reads per k-mer group, 5 mismatches at 100 bp
+    (PMatch=0.95), default and small MaxMatches (the latter forces the order-dependent truncation)."""
+    rng = np.random.default_rng(1234 + mm % 97)
+    reads, genes = _repeat_case(rng, 30, 400, 100)
+    cfgd = dict(Windows=[0, 30, 60], WindowWidth=12, MaxReadLength=100, PMatch=0.95, MinDinuc=mindinuc, MMTol=2,
+                BloomSize=4000000, NumHash=8, MaxMatches=mm, MatchMode=mode, MaxConfirmProcs=3)
+    m, st = check_against_oracle(tmp_path, reads, None, genes, cfgd, taps=(mm == 1000000))
+    assert st["n_pairs"] > 10 * st["n_candidates"] > 0          # quadratic blow-up inside the groups
+    assert len(m) > 2000
+    if mm < 1000000:
+        assert st["n_overflow_groups"] > 0
