@@ -21,6 +21,12 @@ struct WinCfg {
 // symbol pairs over a 5-letter alphabet (4 bases + X).  The count is invariant under
 // relabelling of the symbols, so the packed codes are used directly.
 __device__ __forceinline__ int dinuc_count(uint64_t key, uint64_t xm, int W) {
+  if (xm == 0) {
+    // no X in the window: the adjacent pair (c_i, c_{i+1}) is the nibble of `key` at bit 2i
+    uint32_t seen = 0;
+    for (int i = 0; i + 1 < W; i++) seen |= 1u << (unsigned)((key >> (2 * i)) & 15ull);
+    return __popc(seen);
+  }
   uint32_t seen = 0;
   uint32_t prev = (xm & 1ull) ? 4u : (uint32_t)(key & 3ull);
   for (int i = 1; i < W; i++) {

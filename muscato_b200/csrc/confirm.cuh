@@ -156,8 +156,10 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
   const bool anyx = rx | tx;
 
   // Exact key equality for the window that produced this pair (merge join on the k-mer bytes,
-  // cmd/muscato_confirm/main.go:382-393): rejects fingerprint collisions.
-  {
+  // cmd/muscato_confirm/main.go:382-393) rejects fingerprint collisions.  The tap (mode 1) tests
+  // it on its own; the confirm modes fold it into the mismatch loop below (a mismatch inside
+  // [q1, q2) disqualifies the pair), which saves two window extractions per pair.
+  if (MODE == 1) {
     const uint64_t rk = extract32(row, (uint64_t)q1) & kmask;
     const uint64_t tk = extract32(a.tg_words, gpos) & kmask;
     if (rk != tk) return false;
@@ -166,8 +168,6 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
       const uint64_t txm = tx ? (extract32(a.tg_x, gpos) & kmask) : 0ull;
       if (rxm != txm) return false;
     }
-  }
-  if (MODE == 1) {
     rec = make_uint4((uint32_t)g, (uint32_t)p, r, (uint32_t)k);
     return true;
   }
@@ -197,6 +197,9 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
       m = (m & ~(xa | xb)) | (xa ^ xb);  // X==X matches, X vs base mismatches (cdiff compares bytes)
     }
     m &= low_bases_mask(min(32, L - 32 * w));
+    // bases of window k inside this word must match exactly
+    const int wl = max(q1 - 32 * w, 0), wh = min(q2 - 32 * w, 32);
+    if (wl < wh && (m & (low_bases_mask(wh) & ~low_bases_mask(wl)))) return false;
     nx += __popcll(m);
     if (nx > budget) return false;
   }
