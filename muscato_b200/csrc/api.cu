@@ -361,9 +361,11 @@ int enqueue_build_reads(msc_ctx* ctx) {
     build_insert_kernel<<<grid_for(n_items, 256), 256, 0, ctx->stream>>>(a);
     LAUNCH_CHECK();
   }
-  RC(enqueue_exclusive_scan<uint32_t>(ctx, ctx->tab_cnt.as<uint32_t>(), nullptr, slots, ctx->tab_start.as<uint32_t>(),
-                                      true, ctx->ctr(C_NDUP)));  // grand total = members beyond the first of their group
   if (U) {
+    build_alloc_kernel<<<grid_for(n_items, 256), 256, 0, ctx->stream>>>(
+        ctx->dup_slot.as<uint32_t>(), n_items, ctx->tab_cnt.as<uint32_t>(), ctx->tab_fill.as<uint32_t>(),
+        ctx->tab_start.as<uint32_t>(), ctx->ctr(C_NDUP));
+    LAUNCH_CHECK();
     build_fill_kernel<<<grid_for(n_items, 256), 256, 0, ctx->stream>>>(
         ctx->dup_slot.as<uint32_t>(), n_items, ctx->tab_start.as<uint32_t>(), ctx->tab_fill.as<uint32_t>(),
         ctx->items.as<uint32_t>());

@@ -131,8 +131,23 @@ __global__ void __launch_bounds__(256) build_insert_kernel(const BuildArgs a) {
   }
 }
 
-// Pass B (after the exclusive scan of tab_cnt into tab_start): scatter the further members
-// into their slot's CSR range.
+// Pass B1: CSR ranges for the further members.  Only slots that own further members need one, so
+// instead of scanning the counts of ALL slots the first further member of a slot to arrive
+// reserves the slot's range from a bump counter (tab_cnt is final by now).  tab_fill[s] ends up
+// equal to tab_cnt[s] and is consumed by pass B2.
+__global__ void __launch_bounds__(256) build_alloc_kernel(const uint32_t* __restrict__ dup_slot, uint64_t n_items,
+                                                          const uint32_t* __restrict__ tab_cnt,
+                                                          uint32_t* __restrict__ tab_fill,
+                                                          uint32_t* __restrict__ tab_start,
+                                                          unsigned long long* __restrict__ n_dup) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_items) return;
+  const uint32_t d = __ldg(dup_slot + idx);
+  if (d && atomicAdd(tab_fill + (d - 1), 1u) == 0u)
+    tab_start[d - 1] = (uint32_t)atomicAdd(n_dup, (unsigned long long)__ldg(tab_cnt + (d - 1)));
+}
+
+// Pass B2: scatter the further members into their slot's CSR range.
 __global__ void __launch_bounds__(256) build_fill_kernel(const uint32_t* __restrict__ dup_slot, uint64_t n_items,
                                                          const uint32_t* __restrict__ tab_start,
                                                          uint32_t* __restrict__ tab_fill,
@@ -140,7 +155,7 @@ __global__ void __launch_bounds__(256) build_fill_kernel(const uint32_t* __restr
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_items) return;
   const uint32_t d = __ldg(dup_slot + idx);
-  if (d) items[tab_start[d - 1] + atomicAdd(tab_fill + (d - 1), 1u)] = (uint32_t)idx;
+  if (d) items[tab_start[d - 1] + (atomicSub(tab_fill + (d - 1), 1u) - 1u)] = (uint32_t)idx;
 }
 
 // Member j of the key group in `slot` (j = 0 is stored in the slot, the rest in the CSR).
