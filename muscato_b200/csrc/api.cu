@@ -80,6 +80,7 @@ struct msc_ctx {
   int device = 0;
   int sm_count = 148;
   int scan_grid = 0;
+  const void* scan_fn_sized = nullptr;  // the scan kernel instance scan_grid was computed for
   cudaStream_t stream = nullptr;       // every kernel runs here
   cudaStream_t copy_stream = nullptr;  // input H2D copies: overlap with kernels of the previous input
   cudaEvent_t ev_copy = nullptr, ev_compute = nullptr;
@@ -94,6 +95,7 @@ struct msc_ctx {
   DevBuf rd_ascii, rd_offs, rd_words, rd_x, len_flags, validmask;
   // key table
   int lg_slots = 0, lg_bloom = 0;
+  BloomGeom geom{};
   uint64_t n_keys = 0, n_groups = 0, n_dup = 0;
   DevBuf tab_fp, tab_item0, tab_cnt, tab_start, tab_fill, pass_cnt, bloom, items, dup_slot, fps;
   // zero-fills already issued by a merged prologue launch (consumed by the stage that owns them)
@@ -223,6 +225,7 @@ int enqueue_exclusive_scan(msc_ctx* ctx, const uint32_t* in, const unsigned long
 struct Filler {
   FillJob job{};
   void add(void* p, size_t bytes, unsigned int value = 0) {
+    if (job.n >= kMaxFillJobs) abort();  // programming error: raise kMaxFillJobs
     job.ptr[job.n] = p;
     job.bytes[job.n] = (bytes + 15) & ~(size_t)15;
     job.value[job.n] = value;
@@ -233,8 +236,13 @@ struct Filler {
 // The zero-fills every stage needs before it runs.  A fused run issues them all in ONE prologue
 // launch (add_*_fills + ctx->pro flags); a stage enqueued on its own issues just its own.
 void add_reads_fills(msc_ctx* ctx, Filler& f) {
+  const uint64_t slots = 1ull << ctx->lg_slots;
   f.add(ctx->len_flags.p, (ctx->n_reads + 1) * sizeof(uint32_t));
   f.add(ctx->ctr(C_NKEYS), 4 * sizeof(unsigned long long));  // C_NKEYS, C_NGROUPS, C_NDUP, C_SCRATCH
+  f.add(ctx->tab_fp.p, slots * sizeof(uint64_t));
+  f.add(ctx->tab_cnt.p, slots * sizeof(uint32_t));
+  f.add(ctx->tab_fill.p, slots * sizeof(uint32_t));
+  f.add(ctx->bloom.p, (1ull << ctx->lg_bloom) * sizeof(uint64_t));  // window_keys_kernel sets the bits
 }
 void add_targets_fills(msc_ctx* ctx, Filler& f) {
   f.add(ctx->tg_x.p, ctx->n_words_alloc * sizeof(uint64_t));
@@ -314,8 +322,6 @@ int enqueue_build_reads(msc_ctx* ctx) {
   const int S = ctx->win.S;
   CK(cudaEventRecord(ctx->ev[EV_PACKR0], ctx->stream));
   if (ctx->trace) ctx->trace_mark("start build_reads");
-  const uint64_t slots = 1ull << ctx->lg_slots;
-  const uint64_t bwords = 1ull << ctx->lg_bloom;
   if (!ctx->pro.reads) {
     Filler f;
     add_reads_fills(ctx, f);
@@ -336,16 +342,9 @@ int enqueue_build_reads(msc_ctx* ctx) {
   if (U) {
     window_keys_kernel<<<grid_for(U, 256), 256, 0, ctx->stream>>>(
         ctx->win, ctx->rd_words.as<uint64_t>(), ctx->rd_x.as<uint64_t>(), ctx->len_flags.as<uint32_t>(), U,
-        ctx->validmask.as<uint32_t>(), ctx->fps.as<uint64_t>(), ctx->ctr(C_NKEYS));
+        ctx->validmask.as<uint32_t>(), ctx->fps.as<uint64_t>(), ctx->ctr(C_NKEYS),
+        ctx->bloom.as<unsigned long long>(), ctx->geom);
     LAUNCH_CHECK();
-  }
-  {
-    Filler f;
-    f.add(ctx->tab_fp.p, slots * sizeof(uint64_t));
-    f.add(ctx->tab_cnt.p, slots * sizeof(uint32_t));
-    f.add(ctx->tab_fill.p, slots * sizeof(uint32_t));
-    f.add(ctx->bloom.p, bwords * sizeof(uint64_t));
-    RC(enqueue_fill(ctx, f));
   }
   if (U) {
     BuildArgs a{};
@@ -355,8 +354,6 @@ int enqueue_build_reads(msc_ctx* ctx) {
     a.tab_item0 = ctx->tab_item0.as<uint32_t>();
     a.tab_cnt = ctx->tab_cnt.as<uint32_t>();
     a.lg_slots = ctx->lg_slots;
-    a.bloom = ctx->bloom.as<unsigned long long>();
-    a.lg_bloom = ctx->lg_bloom;
     a.dup_slot = ctx->dup_slot.as<uint32_t>();
     build_insert_kernel<<<grid_for(n_items, 256), 256, 0, ctx->stream>>>(a);
     LAUNCH_CHECK();
@@ -415,12 +412,29 @@ void account_pack_targets(msc_ctx* ctx) {
 }
 
 // ---- enqueue: scan ---------------------------------------------------------------------------
+template <bool K32>
+void (*pick_scan_wn(int wn))(const ScanArgs) {
+  switch (wn) {
+    case 1: return scan_targets_kernel<K32, 1>;
+    case 2: return scan_targets_kernel<K32, 2>;
+    case 3: return scan_targets_kernel<K32, 3>;
+    case 4: return scan_targets_kernel<K32, 4>;
+    case 5: return scan_targets_kernel<K32, 5>;
+    case 6: return scan_targets_kernel<K32, 6>;
+    case 7: return scan_targets_kernel<K32, 7>;
+    default: return scan_targets_kernel<K32, 8>;
+  }
+}
+void (*pick_scan_kernel(bool k32, int wn))(const ScanArgs) { return k32 ? pick_scan_wn<true>(wn) : pick_scan_wn<false>(wn); }
+
 int enqueue_scan(msc_ctx* ctx) {
   if (ctx->cand.cap == 0) CK(ctx->cand.reserve(std::max<uint64_t>(1u << 20, ctx->n_bases / 16) * sizeof(uint2)));
-  if (ctx->scan_grid == 0) {
+  void (*scan_fn)(const ScanArgs) = pick_scan_kernel(ctx->win.W <= 16, ctx->geom.wn);
+  if (ctx->scan_grid == 0 || ctx->scan_fn_sized != (const void*)scan_fn) {
     int blocks_per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_targets_kernel, kScanBlock, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_fn, kScanBlock, 0));
     ctx->scan_grid = ctx->sm_count * std::max(1, blocks_per_sm);
+    ctx->scan_fn_sized = (const void*)scan_fn;
   }
   if (!ctx->pro.scan) {
     Filler f;
@@ -437,7 +451,8 @@ int enqueue_scan(msc_ctx* ctx) {
     a.n_bases = ctx->n_bases;
     a.n_tiles = ctx->n_tiles;
     a.bloom = ctx->bloom.as<uint2>();
-    a.lg_bloom = ctx->lg_bloom;
+    a.geom = ctx->geom;
+    for (int j = 0; j < 8; j++) a.mul[j] = j < ctx->geom.wn ? 1u << (32 - 2 * ctx->geom.m - 2 * j) : 0u;
     a.tab_fp = ctx->tab_fp.as<uint64_t>();
     a.lg_slots = ctx->lg_slots;
     a.cand = ctx->cand.as<uint2>();
@@ -446,7 +461,7 @@ int enqueue_scan(msc_ctx* ctx) {
     a.n_bloom_pass = ctx->ctr(C_BLOOMPASS);
     a.W = ctx->win.W;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ctx->n_tiles, (uint64_t)ctx->scan_grid));
-    scan_targets_kernel<<<grid, kScanBlock, 0, ctx->stream>>>(a);
+    scan_fn<<<grid, kScanBlock, 0, ctx->stream>>>(a);
     LAUNCH_CHECK();
   }
   CK(cudaEventRecord(ctx->ev[EV_SCAN1], ctx->stream));
@@ -849,6 +864,20 @@ static int reads_reserve(msc_ctx* ctx, uint64_t n_reads, uint64_t total) {
     const int lg_l2 = 23;  // 2^23 words = 64 MB
     if (lg > lg_l2) lg = std::max(lg_l2, ceil_log2((kmax * 12ull + 63) / 64));
     ctx->lg_bloom = lg;
+  }
+  // Minimiser geometry of the Bloom addressing (common.cuh): m-mers of the key's first P bases.
+  // 4^m is kept >= 4x the number of sectors so that the minimisers spread over all of them, and
+  // at most 8 m-mers compete (ALU cost per probed position).  MSC_MINIMIZER_M overrides m.
+  {
+    const int P = std::min(ctx->win.W, 16);
+    int m = (ctx->lg_bloom - 2 + 2 + 1) / 2;
+    if (const char* e = getenv("MSC_MINIMIZER_M")) m = atoi(e);
+    m = std::max(m, P - 7);
+    m = std::min(std::max(m, 1), P);
+    ctx->geom.lg_words = ctx->lg_bloom;
+    ctx->geom.m = m;
+    ctx->geom.wn = P - m + 1;
+    ctx->geom.xr = 0x55555555u & (uint32_t)low_bases_mask(ctx->win.W);
   }
   const uint64_t slots = 1ull << ctx->lg_slots;
   CK(ctx->tab_fp.reserve(slots * sizeof(uint64_t)));

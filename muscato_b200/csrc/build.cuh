@@ -44,8 +44,6 @@ struct BuildArgs {
   uint32_t* tab_item0;   // first (read, window) item of the slot's key group
   uint32_t* tab_cnt;     // number of FURTHER items of the group (they go to the CSR `items`)
   int lg_slots;
-  unsigned long long* bloom;
-  int lg_bloom;
   uint32_t* dup_slot;    // per item: 1 + slot if the item is a further member of its group, else 0
 };
 // (The number of further members, n_dup, is the grand total of the tab_cnt scan and the number of
@@ -53,12 +51,14 @@ struct BuildArgs {
 // ~10^6 same-address atomics cost more than the inserts themselves.)
 
 // Pass A1: per read, which windows are valid (length rule + entropy rule) and the fingerprint of
-// each valid window key.  Pure ALU over the packed words; item = read * nwin + window.
+// each valid window key; the key's bits are set in the Bloom front here, where the key itself
+// (needed for the minimiser addressing, common.cuh) is still at hand.  item = read * nwin + window.
 __global__ void __launch_bounds__(256) window_keys_kernel(const WinCfg cfg, const uint64_t* __restrict__ rd_words,
                                                           const uint64_t* __restrict__ rd_x,
                                                           const uint32_t* __restrict__ len_flags, uint64_t n_reads,
                                                           uint32_t* __restrict__ validmask, uint64_t* __restrict__ fps,
-                                                          unsigned long long* __restrict__ n_keys) {
+                                                          unsigned long long* __restrict__ n_keys,
+                                                          unsigned long long* __restrict__ bloom, const BloomGeom geom) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t nk = 0;
   if (r < n_reads) {
@@ -79,6 +79,10 @@ __global__ void __launch_bounds__(256) window_keys_kernel(const WinCfg cfg, cons
           fp = key_fp(key, xm);
           vm |= 1u << k;
           nk++;
+          uint64_t widx;
+          uint32_t mlo, mhi;
+          bloom_locate(key, xm, fp, cfg.W, geom, widx, mlo, mhi);
+          atomicOr(bloom + widx, (unsigned long long)mlo | ((unsigned long long)mhi << 32));
         }
       }
       fps[r * (uint64_t)cfg.nwin + (uint64_t)k] = fp;
@@ -97,8 +101,7 @@ __global__ void __launch_bounds__(256) window_keys_kernel(const WinCfg cfg, cons
   }
 }
 
-// Pass A2: one thread per item.  Claim / find the table slot of the fingerprint and set the
-// Bloom bits.  The first item of a key group lives in the slot itself (most groups have exactly
+// Pass A2: one thread per item.  Claim / find the table slot of the fingerprint.  The first item of a key group lives in the slot itself (most groups have exactly
 // one member); further members are flagged in dup_slot and scattered into the slot's CSR range
 // by pass B.
 __global__ void __launch_bounds__(256) build_insert_kernel(const BuildArgs a) {
@@ -119,9 +122,6 @@ __global__ void __launch_bounds__(256) build_insert_kernel(const BuildArgs a) {
       }
       if (first) {
         a.tab_item0[s] = (uint32_t)idx;
-        const unsigned long long bm =
-            (unsigned long long)bloom_mask_lo(fp) | ((unsigned long long)bloom_mask_hi(fp) << 32);
-        atomicOr(a.bloom + bloom_index(fp, a.lg_bloom), bm);
       } else {
         atomicAdd(a.tab_cnt + s, 1u);
         dup = (uint32_t)s + 1u;

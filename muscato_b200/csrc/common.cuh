@@ -30,10 +30,12 @@ __device__ __forceinline__ uint64_t extract32(const uint64_t* __restrict__ w, ui
 
 // ---------------------------------------------------------------------------
 // Window-key fingerprint.  A W<=32 window is 2W bits (key) plus its X mask (xm, same
-// spacing).  fp is a bijective mix of key when xm==0; windows containing X fold the
-// mask in.  fp only has to be free of false negatives: the confirm kernel re-checks
-// the window bases exactly (cmd/muscato_confirm/main.go:382-393 requires byte equality).
-// fp==0 is reserved for "empty slot".
+// spacing).  An X-free window's fingerprint is the key itself (+1, so that it is never 0): exact
+// and free; the table's home slot comes from one multiplicative hash (table_home).  Windows
+// containing X mix the mask in.  fp only has to be free of false negatives: the confirm kernel
+// re-checks the window bases exactly (cmd/muscato_confirm/main.go:382-393 requires byte
+// equality), so the rare collisions (an X window with an X-free one, the all-G 32-mer with the
+// all-A one) only cost a rejected pair.  fp==0 is reserved for "empty slot".
 // ---------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint64_t fmix64(uint64_t z) {
   z ^= z >> 33;
@@ -45,20 +47,104 @@ __host__ __device__ __forceinline__ uint64_t fmix64(uint64_t z) {
 }
 
 __host__ __device__ __forceinline__ uint64_t key_fp(uint64_t key, uint64_t xm) {
-  uint64_t z = fmix64((key ^ (xm * 0xD6E8FEB86659FD93ull)) + 0x9E3779B97F4A7C15ull);
+  uint64_t z = xm == 0 ? key + 1ull : fmix64((key ^ (xm * 0xD6E8FEB86659FD93ull)) + 0x9E3779B97F4A7C15ull);
   return z ? z : 1ull;
 }
 
+// ---------------------------------------------------------------------------
 // Blocked Bloom front: one 64-bit word per key (a single 8-byte load per probed target
 // position), 2 bits in each 32-bit half.
-__host__ __device__ __forceinline__ uint32_t bloom_mask_lo(uint64_t fp) {
-  return (1u << (unsigned)(fp & 31u)) | (1u << (unsigned)((fp >> 5) & 31u));
+//
+// Addressing is LOCALITY AWARE: the 32-byte sector (4 words) of a key is chosen by the
+// minimiser of the key's first P = min(W,16) bases -- the smallest of its wn = P-m+1 m-mers,
+// lexicographic with the later base more significant, on a relabelled alphabet (every 2-bit code
+// XOR 1, so that poly-A is not the smallest m-mer) -- so the W-mers of consecutive target
+// positions, which share their minimiser for (wn+1)/2 positions on average, probe the same sector
+// and a warp that probes 32 consecutive positions touches ~32*2/(wn+1) sectors instead of 32.
+// The word inside the sector and the bit positions come from a cheap 32-bit hash of the whole
+// key.  Keys whose window contains X (xm != 0) are addressed by their fingerprint instead (no
+// locality; rare).  The filter only has to be free of false negatives: build (window_keys_kernel)
+// and scan use the same functions below.
+// ---------------------------------------------------------------------------
+struct BloomGeom {
+  int lg_words;    // log2(number of 64-bit words), 10..32
+  int m;           // minimiser length in bases, 1..16
+  int wn;          // m-mers per key that compete: P - m + 1, 1..8
+  uint32_t xr;     // alphabet relabelling of the key's low 32 bits: 0x55555555 cut to W bases
+};
+
+// Fingerprint-addressed variant (keys with X).
+__host__ __device__ __forceinline__ uint32_t bloom_mask_lo(uint64_t h) {
+  return (1u << (unsigned)(h & 31u)) | (1u << (unsigned)((h >> 5) & 31u));
 }
-__host__ __device__ __forceinline__ uint32_t bloom_mask_hi(uint64_t fp) {
-  return (1u << (unsigned)((fp >> 10) & 31u)) | (1u << (unsigned)((fp >> 15) & 31u));
+__host__ __device__ __forceinline__ uint32_t bloom_mask_hi(uint64_t h) {
+  return (1u << (unsigned)((h >> 10) & 31u)) | (1u << (unsigned)((h >> 15) & 31u));
 }
-__host__ __device__ __forceinline__ uint64_t bloom_index(uint64_t fp, int lg_words) {
-  return fp >> (64 - lg_words);
+
+// 32-bit hash of an X-free key: prex = low 32 bits of the key ^ xr, khi = its high 32 bits
+// (K32: the key has at most 16 bases, khi == 0).
+template <bool K32>
+__host__ __device__ __forceinline__ uint32_t bloom_hash32(uint32_t prex, uint32_t khi) {
+  uint32_t x = prex;
+  if (!K32) x ^= khi * 0x85EBCA6Bu;
+  x *= 0x9E3779B1u;
+  x ^= x >> 15;
+  x *= 0x2C1B3C6Du;
+  return x;
+}
+
+// The two half masks from the hash: two bits in the low half (a 10-bit pattern index, which the
+// scan serves from a shared-memory table), the same pair rotated in the high half.
+__host__ __device__ __forceinline__ uint32_t bloom_pattern(uint32_t i) {  // i in [0, 1024)
+  return (1u << (i & 31u)) | (1u << ((i >> 5) & 31u));
+}
+__host__ __device__ __forceinline__ void bloom_masks32(uint32_t h, uint32_t& mlo, uint32_t& mhi) {
+  mlo = bloom_pattern((h >> 2) & 1023u);
+  const unsigned r = (h >> 12) & 31u;
+  mhi = (mlo << r) | (mlo >> ((32u - r) & 31u));
+}
+
+// Sector of an X-free key.  m-mer j of prex is brought to the top of a 32-bit word by a left
+// shift -- written as a multiplication by mul[j] = 1 << (32 - 2m - 2j) so that it issues on the
+// FMA pipe (IMAD) instead of the ALU pipe the rest of the probe arithmetic saturates; the bits
+// below the m-mer (earlier bases) only break ties between equal m-mers.
+template <int WN>
+__device__ __forceinline__ uint32_t bloom_min_mmer(uint32_t prex, const uint32_t* __restrict__ mul) {
+  uint32_t v = prex * mul[0];
+#pragma unroll
+  for (int j = 1; j < WN; j++) v = min(v, prex * mul[j]);
+  return v;
+}
+__host__ __device__ __forceinline__ uint32_t bloom_sector_of(uint32_t vmin, int m, int lg_words) {
+  return ((vmin >> (32u - 2u * (unsigned)m)) * 0x9E3779B1u) >> (34 - lg_words);  // lg_sectors = lg_words - 2
+}
+
+__host__ __device__ __forceinline__ uint32_t bloom_sector_rt(uint32_t prex, int wn, int m, int lg_words) {
+  const unsigned s0 = 32u - 2u * (unsigned)m;
+  uint32_t v = prex << s0;
+  for (int j = 1; j < wn; j++) {
+    const uint32_t c = prex << (s0 - 2u * j);
+    v = c < v ? c : v;
+  }
+  return bloom_sector_of(v, m, lg_words);
+}
+
+// Word index and the two 32-bit half masks of a key (build side and the scan's X path; the
+// scan's main path inlines the same arithmetic with WN as a template parameter).
+__host__ __device__ __forceinline__ void bloom_locate(uint64_t key, uint64_t xm, uint64_t fp, int W,
+                                                      const BloomGeom& g, uint64_t& widx, uint32_t& mlo,
+                                                      uint32_t& mhi) {
+  if (xm == 0) {
+    const uint32_t prex = (uint32_t)key ^ g.xr;
+    const uint32_t h = W <= 16 ? bloom_hash32<true>(prex, 0u) : bloom_hash32<false>(prex, (uint32_t)(key >> 32));
+    const uint32_t sec = bloom_sector_rt(prex, g.wn, g.m, g.lg_words);
+    widx = ((uint64_t)sec << 2) | (uint64_t)(h >> 30);
+    bloom_masks32(h, mlo, mhi);
+  } else {
+    widx = fp >> (64 - g.lg_words);
+    mlo = bloom_mask_lo(fp);
+    mhi = bloom_mask_hi(fp);
+  }
 }
 __host__ __device__ __forceinline__ uint64_t table_home(uint64_t fp, int lg_slots) {
   return (fp * 0x9E3779B97F4A7C15ull) >> (64 - lg_slots);

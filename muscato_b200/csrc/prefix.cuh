@@ -38,7 +38,7 @@ __device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_
 
 // One launch that fills up to kMaxFillJobs device buffers with a byte value each (replaces a train of
 // cudaMemsetAsync calls: every memset is its own engine hand-over on the stream).
-constexpr int kMaxFillJobs = 12;
+constexpr int kMaxFillJobs = 20;
 struct FillJob {
   void* ptr[kMaxFillJobs];
   unsigned long long bytes[kMaxFillJobs];  // multiples of 16 (buffers are over-allocated accordingly)

@@ -9,29 +9,41 @@
 // atomics.  Window/target-boundary and position-0 rules (processSeq :294-365) are applied
 // by the confirm kernel, which knows the gene of each candidate.
 //
-// Data movement: target tiles (256 words = 8192 bases + halo) are staged into shared memory
-// by the TMA engine (1-D cp.async.bulk + mbarrier, double buffered); a persistent grid walks
-// the tiles.  The Bloom/table probes are scattered 8-byte reads served from L2 when the
-// filter fits (it is sized 32-64 bits per key) and from HBM sectors otherwise.
+// Data movement: every WARP owns a stream of 32-word tiles (1024 bases + halo) that the TMA
+// engine stages into the warp's shared-memory slice (1-D cp.async.bulk + one mbarrier per
+// buffer, double buffered); warps never wait for each other -- there is no block-wide barrier
+// in the loop, so a warp that is draining hits (latency bound) overlaps with warps that are
+// probing (issue bound).  The Bloom/table probes are scattered 8-byte reads served from L2
+// when the filter fits (it is sized 32-64 bits per key) and from HBM sectors otherwise.
 #pragma once
 #include "common.cuh"
 
 namespace msc {
 
 constexpr int kScanBlock = 256;
-constexpr int kTileWords = 256;                       // one 32-base word per thread per tile
-constexpr int kTileCopyWords = kTileWords + 2;        // halo word + 1 (byte count multiple of 16)
-constexpr int kTileSmemWords = kTileWords + 8;
+constexpr int kScanWarps = kScanBlock / 32;
+constexpr int kTileWords = 256;                       // granularity of the target buffers (8 warp tiles)
+constexpr int kWarpTileWords = 32;                    // one 32-base word per lane
+constexpr int kWarpCopyWords = kWarpTileWords + 2;    // halo word + 1 (byte count multiple of 16)
+constexpr int kWarpSmemWords = kWarpTileWords + 8;    // keeps every buffer 64-byte aligned
 constexpr int kStageCap = 128;                        // per-warp candidate staging (entries)
+#ifndef MSC_SCAN_BATCH
+#define MSC_SCAN_BATCH 8
+#endif
+#ifndef MSC_SCAN_CTAS
+#define MSC_SCAN_CTAS 4
+#endif
+constexpr int kProbeBatch = MSC_SCAN_BATCH;           // Bloom probes in flight per lane
 
 struct ScanArgs {
   const uint64_t* tg_words;
   const uint64_t* tg_x;
   const uint32_t* xsum;
   uint64_t n_bases;
-  uint64_t n_tiles;
+  uint64_t n_tiles;       // 256-word tiles; the buffers are padded to n_tiles * 256 + 64 words
   const uint2* bloom;
-  int lg_bloom;
+  BloomGeom geom;
+  uint32_t mul[8];        // mul[j] = 1 << (32 - 2m - 2j): m-mer j of a key to the top of a word
   const uint64_t* tab_fp;
   int lg_slots;
   uint2* cand;
@@ -46,32 +58,53 @@ __device__ __forceinline__ uint64_t window_at(uint64_t lo, uint64_t hi, unsigned
   return (j == 0 ? lo : ((lo >> (2 * j)) | (hi << (64 - 2 * j)))) & kmask;
 }
 
-// Two phases per tile, so that the scattered probes never serialise behind divergent hit handling:
-//   phase 1  every thread tests its 32 positions against the Bloom front (4 batches of 8
-//            independent 8-byte loads) and keeps a 32-bit pass mask;
+// Two phases per warp tile, so that the scattered probes never serialise behind divergent hit
+// handling:
+//   phase 1  the warp walks the 32 words of its tile; in every step the 32 lanes test the 32
+//            CONSECUTIVE positions of one word against the Bloom front (lane = position), so
+//            that lanes whose W-mers share a minimiser hit the same 32-byte sector and coalesce
+//            into one L1 wavefront / one L2 request (common.cuh, "locality aware").  kProbeBatch steps
+//            are in flight per lane.  The ballot of step i is kept by lane i: after the walk
+//            lane i owns the 32-bit pass mask of word i;
 //   phase 2  the warp compacts its passes into a shared-memory queue and drains it 32 at a time:
 //            lane i re-derives the key of queued position i with two shuffles, looks it up in the
 //            exact table, and the warp appends the found (slot, position) pairs with ONE atomic.
-__global__ void __launch_bounds__(kScanBlock) scan_targets_kernel(const ScanArgs a) {
-  __shared__ alignas(128) uint64_t tile[2][kTileSmemWords];
-  __shared__ alignas(8) uint64_t bar[2];
-  __shared__ uint16_t queue[kScanBlock / 32][1024];
-  __shared__ uint2 stage[kScanBlock / 32][kStageCap];  // found (slot, position) pairs, flushed when nearly full
+// K32: W <= 16, the key arithmetic of phase 1 is 32 bit.  WN: number of competing m-mers.
+template <bool K32, int WN>
+__global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel(const ScanArgs a) {
+  __shared__ alignas(128) uint64_t tiles[kScanWarps][2][kWarpSmemWords];
+  __shared__ alignas(8) uint64_t bars[kScanWarps][2];
+  __shared__ uint16_t queue[kScanWarps][1024];
+  __shared__ uint2 stage[kScanWarps][kStageCap];  // found (slot, position) pairs, flushed when nearly full
+  __shared__ uint32_t pattern[1024];              // bloom_pattern(): the two low-half bits of a key
+  for (int i = threadIdx.x; i < 1024; i += kScanBlock) pattern[i] = bloom_pattern((uint32_t)i);
+  __syncthreads();
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31u, warp = tid >> 5;
-  constexpr uint32_t kBytes = kTileCopyWords * sizeof(uint64_t);
-  if (tid == 0) {
+  constexpr uint32_t kBytes = kWarpCopyWords * sizeof(uint64_t);
+  uint64_t* bar = bars[warp];
+  if (lane == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
     fence_mbar_init();
   }
-  __syncthreads();
+  __syncwarp();
 
   const uint64_t kmask = low_bases_mask(a.W);
-  uint64_t t = blockIdx.x;
-  if (tid == 0 && t < a.n_tiles) {
+  const uint32_t xr = a.geom.xr;
+  const int gm = a.geom.m;
+  const int lg_words = a.geom.lg_words;
+  // Static, balanced split: the stream is cut into units of kProbeBatch words and every warp of
+  // the grid gets a contiguous run of units whose length differs by at most one between warps;
+  // the warp walks its run in tiles of up to 32 words (the last one may be shorter).
+  const uint64_t n_words = (a.n_bases + 31) >> 5;
+  const uint64_t n_units = (n_words + kProbeBatch - 1) / kProbeBatch;
+  const uint64_t n_warps = (uint64_t)kScanWarps * gridDim.x, gw = (uint64_t)blockIdx.x * kScanWarps + warp;
+  uint64_t w0 = (gw * n_units / n_warps) * kProbeBatch;                                  // first word of the current tile
+  const uint64_t w_end = ((gw + 1) * n_units / n_warps) * kProbeBatch;  // end of the run (buffers are padded)
+  if (lane == 0 && w0 < w_end) {
     mbar_arrive_expect_tx(&bar[0], kBytes);
-    bulk_copy_g2s(tile[0], a.tg_words + t * kTileWords, kBytes, &bar[0]);
+    bulk_copy_g2s(tiles[warp][0], a.tg_words + w0, kBytes, &bar[0]);
   }
   uint32_t phases = 0;
   int buf = 0;
@@ -89,55 +122,76 @@ __global__ void __launch_bounds__(kScanBlock) scan_targets_kernel(const ScanArgs
     __syncwarp();
     n_st = 0;
   };
-  for (; t < a.n_tiles; t += gridDim.x) {
-    const uint64_t tn = t + gridDim.x;
-    if (tid == 0 && tn < a.n_tiles) {
+  for (; w0 < w_end; w0 += kWarpTileWords) {
+    const uint64_t wn = w0 + kWarpTileWords;
+    if (lane == 0 && wn < w_end) {
       mbar_arrive_expect_tx(&bar[buf ^ 1], kBytes);
-      bulk_copy_g2s(tile[buf ^ 1], a.tg_words + tn * kTileWords, kBytes, &bar[buf ^ 1]);
+      bulk_copy_g2s(tiles[warp][buf ^ 1], a.tg_words + wn, kBytes, &bar[buf ^ 1]);
     }
+    const int tile_words = (int)min((uint64_t)kWarpTileWords, w_end - w0);  // multiple of kProbeBatch
     mbar_wait(&bar[buf], (phases >> buf) & 1u);
     phases ^= 1u << buf;
+    const uint64_t* tile = tiles[warp][buf];
 
-    const uint64_t lo = tile[buf][tid];
-    const uint64_t hi = tile[buf][tid + 1];
-    const uint64_t w = t * kTileWords + (uint64_t)tid;
-    const uint64_t gbase = w * 32ull;
+    // lane i owns word i of the tile: its pass mask and its X flag
     uint32_t mask = 0;
-    uint64_t xlo = 0, xhi = 0;
-    if (gbase < a.n_bases) {
-      const int npos = (int)min((uint64_t)32, a.n_bases - gbase);
-      // X summary bits of word w and w+1 (xsum is padded).
+    // X summary bits of word w and w+1 (xsum is padded): bit i of xwords = word i of the tile needs the X path
+    unsigned xwords;
+    {
+      const uint64_t w = w0 + (uint64_t)lane;
       const uint32_t xs0 = __ldg(a.xsum + (w >> 5));
       const uint32_t xs1 = __ldg(a.xsum + ((w + 1) >> 5));
-      const bool anyx = ((xs0 >> (unsigned)(w & 31u)) | (xs1 >> (unsigned)((w + 1) & 31u))) & 1u;
-      if (!anyx) {
+      xwords = __ballot_sync(0xffffffffu, ((xs0 >> (unsigned)(w & 31u)) | (xs1 >> (unsigned)((w + 1) & 31u))) & 1u);
+    }
+    if (tile_words < 32) xwords &= (1u << tile_words) - 1u;
+    const unsigned xwords_all = xwords;
+    {
+      const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tile) + (lane >> 4);
+      const unsigned sh = (2u * lane) & 31u;
+#pragma unroll 1
+      for (int ib = 0; ib < tile_words; ib += kProbeBatch) {
+        uint32_t h[kProbeBatch];
+        uint2 bw[kProbeBatch];
 #pragma unroll
-        for (int jb = 0; jb < 32; jb += 8) {
-          uint64_t fp[8];
-          uint2 bw[8];
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            fp[i] = key_fp(window_at(lo, hi, jb + i, kmask), 0ull);
-            bw[i] = __ldg(a.bloom + bloom_index(fp[i], a.lg_bloom));
+        for (int i = 0; i < kProbeBatch; i++) {
+          const int wi = ib + i;  // word of the tile; this lane tests position `lane` of it
+          uint32_t prex;
+          if (K32) {
+            prex = (__funnelshift_r(t32[2 * wi], t32[2 * wi + 1], sh) & (uint32_t)kmask) ^ xr;
+            h[i] = bloom_hash32<true>(prex, 0u);
+          } else {
+            const uint64_t key = window_at(tile[wi], tile[wi + 1], lane, kmask);
+            prex = (uint32_t)key ^ xr;
+            h[i] = bloom_hash32<false>(prex, (uint32_t)(key >> 32));
           }
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const uint32_t mlo = bloom_mask_lo(fp[i]), mhi = bloom_mask_hi(fp[i]);
-            if (((bw[i].x & mlo) == mlo) & ((bw[i].y & mhi) == mhi)) mask |= 1u << (jb + i);
-          }
+          const uint32_t sec = bloom_sector_of(bloom_min_mmer<WN>(prex, a.mul), gm, lg_words);
+          bw[i] = __ldg(a.bloom + __funnelshift_l(h[i], sec, 2));  // (sec << 2) | (h >> 30)
         }
-      } else {
-        // The word (or its successor) contains X: fold the X mask into the key.
-        xlo = __ldg(a.tg_x + w);
-        xhi = __ldg(a.tg_x + w + 1);
-        for (int j = 0; j < 32; j++) {
-          const uint64_t fp = key_fp(window_at(lo, hi, j, kmask), window_at(xlo, xhi, j, kmask));
-          const uint2 bw = __ldg(a.bloom + bloom_index(fp, a.lg_bloom));
-          const uint32_t mlo = bloom_mask_lo(fp), mhi = bloom_mask_hi(fp);
-          if (((bw.x & mlo) == mlo) & ((bw.y & mhi) == mhi)) mask |= 1u << j;
+#pragma unroll
+        for (int i = 0; i < kProbeBatch; i++) {
+          // same masks as bloom_masks32(): pattern table look-up + rotate
+          const uint32_t mlo = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pattern) + (h[i] & 0xFFCu));
+          const uint32_t mhi = __funnelshift_l(mlo, mlo, h[i] >> 12);
+          const unsigned b = __ballot_sync(0xffffffffu, ((~bw[i].x & mlo) | (~bw[i].y & mhi)) == 0u);
+          if ((int)lane == ib + i) mask = b;
         }
       }
-      if (npos < 32) mask &= (1u << npos) - 1u;
+      // Words that contain X (or whose successor does): redo them with the X mask folded in.
+      while (xwords) {
+        const int wi = __ffs(xwords) - 1;
+        xwords &= xwords - 1;
+        const uint64_t xl = __ldg(a.tg_x + w0 + wi), xh = __ldg(a.tg_x + w0 + wi + 1);
+        const uint64_t key = window_at(tile[wi], tile[wi + 1], lane, kmask), xm = window_at(xl, xh, lane, kmask);
+        uint64_t widx;
+        uint32_t mlo, mhi;
+        bloom_locate(key, xm, xm ? key_fp(key, xm) : 0ull, a.W, a.geom, widx, mlo, mhi);
+        const uint2 bwx = __ldg(a.bloom + widx);
+        const unsigned b = __ballot_sync(0xffffffffu, ((bwx.x & mlo) == mlo) & ((bwx.y & mhi) == mhi));
+        if ((int)lane == wi) mask = b;
+      }
+      const uint64_t gbase = (w0 + (uint64_t)lane) * 32ull;
+      if ((int)lane >= tile_words || gbase >= a.n_bases) mask = 0;
+      else if (a.n_bases - gbase < 32) mask &= (1u << (unsigned)(a.n_bases - gbase)) - 1u;
     }
 
     // ---- phase 2: warp-cooperative drain of the Bloom passes -------------------------------
@@ -159,27 +213,50 @@ __global__ void __launch_bounds__(kScanBlock) scan_targets_kernel(const ScanArgs
         q[at++] = (uint16_t)((lane << 5) | j);
       }
       __syncwarp();
-      const uint64_t wbase = (t * kTileWords + (uint64_t)(warp * 32)) * 32ull;  // first position of this warp's words
-      for (uint32_t base = 0; base < total; base += 32) {
-        const uint32_t idx = base + lane;
-        const bool active = idx < total;
-        const uint32_t e = active ? q[idx] : 0u;
-        const unsigned src = e >> 5, j = e & 31u;
-        const uint64_t l = __shfl_sync(0xffffffffu, lo, src), h = __shfl_sync(0xffffffffu, hi, src);
-        const uint64_t xl = __shfl_sync(0xffffffffu, xlo, src), xh = __shfl_sync(0xffffffffu, xhi, src);
-        int64_t slot = -1;
-        if (active) slot = table_find(a.tab_fp, a.lg_slots, key_fp(window_at(l, h, j, kmask), window_at(xl, xh, j, kmask)));
-        const unsigned found = __ballot_sync(0xffffffffu, slot >= 0);
-        if (found) {
-          if (slot >= 0) st[n_st + __popc(found & ((1u << lane) - 1u))] = make_uint2((uint32_t)slot, (uint32_t)(wbase + e));
-          n_st += __popc(found);
-          __syncwarp();
-          if (n_st > kStageCap - 32) flush_stage();
+      const uint64_t wbase = w0 * 32ull;  // first position of this warp tile
+      // kDrain table look-ups in flight per lane: the first probe of each is issued before any
+      // is resolved (the look-ups are independent; a single one costs an L2 / HBM round trip).
+      constexpr int kDrain = 4;
+      for (uint32_t base = 0; base < total; base += 32 * kDrain) {
+        uint64_t fp[kDrain], cur[kDrain], sl[kDrain];
+        uint32_t e[kDrain];
+        const uint64_t smask = (1ull << a.lg_slots) - 1ull;
+#pragma unroll
+        for (int u = 0; u < kDrain; u++) {
+          const uint32_t idx = base + 32 * u + lane;
+          e[u] = idx < total ? q[idx] : 0xffffffffu;
+          fp[u] = 0;
+          cur[u] = 0;
+          sl[u] = 0;
+          if (e[u] != 0xffffffffu) {
+            const unsigned src = e[u] >> 5, j = e[u] & 31u;
+            uint64_t xm = 0;
+            if ((xwords_all >> src) & 1u) xm = window_at(__ldg(a.tg_x + w0 + src), __ldg(a.tg_x + w0 + src + 1), j, kmask);
+            fp[u] = key_fp(window_at(tile[src], tile[src + 1], j, kmask), xm);
+            sl[u] = table_home(fp[u], a.lg_slots);
+            cur[u] = __ldg(a.tab_fp + sl[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kDrain; u++) {
+          if (base + 32 * u >= total) break;  // warp-uniform
+          while (cur[u] != fp[u] && cur[u] != 0ull) {  // linear probing (fp == 0 never enters: cur == 0)
+            sl[u] = (sl[u] + 1) & smask;
+            cur[u] = __ldg(a.tab_fp + sl[u]);
+          }
+          const bool hit = cur[u] != 0ull;  // inactive lanes have cur == fp == 0
+          const unsigned found = __ballot_sync(0xffffffffu, hit);
+          if (found) {
+            if (hit) st[n_st + __popc(found & ((1u << lane) - 1u))] = make_uint2((uint32_t)sl[u], (uint32_t)(wbase + e[u]));
+            n_st += __popc(found);
+            __syncwarp();
+            if (n_st > kStageCap - 32) flush_stage();
+          }
         }
       }
       __syncwarp();
     }
-    __syncthreads();  // all reads of tile[buf] are done before it is refilled
+    __syncwarp();  // all lanes are done with tile[buf] before lane 0 lets the TMA engine refill it
     buf ^= 1;
   }
   if (n_st) flush_stage();
