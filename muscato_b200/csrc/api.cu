@@ -92,7 +92,7 @@ struct msc_ctx {
   // reads
   uint64_t n_reads = 0;
   bool have_reads = false;
-  DevBuf rd_ascii, rd_offs, rd_words, rd_x, len_flags, validmask;
+  DevBuf rd_ascii, rd_offs, rd_words, rd_x, len_flags, validmask, rmeta;
   // key table
   int lg_slots = 0, lg_bloom = 0;
   BloomGeom geom{};
@@ -107,7 +107,7 @@ struct msc_ctx {
   // candidates / pairs
   uint64_t n_cand = 0, n_pairs = 0;
   bool have_cand = false;
-  DevBuf cand, cinfo, sizes, pstart, block_first;
+  DevBuf cand, cinfo, cgene, sizes, pstart, block_first;
   // matches
   uint64_t n_match_pre = 0, n_match = 0;
   bool have_confirm = false, have_combine = false;
@@ -343,7 +343,7 @@ int enqueue_build_reads(msc_ctx* ctx) {
     window_keys_kernel<<<grid_for(U, 256), 256, 0, ctx->stream>>>(
         ctx->win, ctx->rd_words.as<uint64_t>(), ctx->rd_x.as<uint64_t>(), ctx->len_flags.as<uint32_t>(), U,
         ctx->validmask.as<uint32_t>(), ctx->fps.as<uint64_t>(), ctx->ctr(C_NKEYS),
-        ctx->bloom.as<unsigned long long>(), ctx->geom);
+        ctx->bloom.as<unsigned long long>(), ctx->geom, ctx->nmiss.as<int32_t>(), ctx->rmeta.as<uint2>());
     LAUNCH_CHECK();
   }
   if (U) {
@@ -472,15 +472,16 @@ int enqueue_scan(msc_ctx* ctx) {
 int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   const uint64_t ccap = ctx->cand_cap();
   CK(ctx->sizes.reserve((ccap + 1) * sizeof(uint32_t)));
-  CK(ctx->cinfo.reserve((ccap + 1) * sizeof(uint2)));
+  CK(ctx->cinfo.reserve((ccap + 1) * sizeof(uint4)));
+  CK(ctx->cgene.reserve((ccap + 1) * sizeof(uint32_t)));
   CK(ctx->pstart.reserve((ccap + 2) * sizeof(uint64_t)));
   if (ctx->block_first.cap == 0) CK(ctx->block_first.reserve(((size_t)(1u << 16) + 2) * sizeof(uint32_t)));
   if (outbuf.cap == 0) CK(outbuf.reserve((size_t)(1u << 20) * sizeof(uint4)));
   const unsigned pgrid = (unsigned)ctx->sm_count * 8;
   cand_prepare_kernel<<<pgrid, 256, 0, ctx->stream>>>(ctx->cand.as<uint2>(), ctx->ctr(C_NCAND), ccap,
                                                       ctx->tab_cnt.as<uint32_t>(), ctx->tg_off.as<uint32_t>(),
-                                                      ctx->n_targets, ctx->win.W, ctx->cinfo.as<uint2>(),
-                                                      ctx->sizes.as<uint32_t>());
+                                                      ctx->n_targets, ctx->win.W, ctx->cinfo.as<uint4>(),
+                                                      ctx->cgene.as<uint32_t>(), ctx->sizes.as<uint32_t>());
   LAUNCH_CHECK();
   RC(enqueue_exclusive_scan<uint64_t>(ctx, ctx->sizes.as<uint32_t>(), ctx->ctr(C_NCAND), ccap, ctx->pstart.as<uint64_t>(),
                                       true, ctx->ctr(C_NPAIRS)));
@@ -497,8 +498,8 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   }
   ctx->pro.pairs = false;
   ConfirmArgs a{};
-  a.cand = ctx->cand.as<uint2>();
-  a.cinfo = ctx->cinfo.as<uint2>();
+  a.cinfo = ctx->cinfo.as<uint4>();
+  a.cgene = ctx->cgene.as<uint32_t>();
   a.block_first = ctx->block_first.as<uint32_t>();
   a.pstart = ctx->pstart.as<uint64_t>();
   a.n_pairs_ptr = ctx->ctr(C_NPAIRS);
@@ -509,14 +510,12 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   a.pass_cnt = ctx->pass_cnt.as<uint32_t>();
   a.rd_words = ctx->rd_words.as<uint64_t>();
   a.rd_x = ctx->rd_x.as<uint64_t>();
-  a.len_flags = ctx->len_flags.as<uint32_t>();
-  a.validmask = ctx->validmask.as<uint32_t>();
+  a.rmeta = ctx->rmeta.as<uint2>();
   a.tg_words = ctx->tg_words.as<uint64_t>();
   a.tg_x = ctx->tg_x.as<uint64_t>();
   a.xsum = ctx->xsum.as<uint32_t>();
   a.tg_off = ctx->tg_off.as<uint32_t>();
   a.n_targets = ctx->n_targets;
-  a.nmiss = ctx->nmiss.as<int32_t>();
   a.nwin_magic = ctx->win.nwin == 1 ? 0ull : (~0ull / (uint64_t)ctx->win.nwin) + 1ull;
   a.targets_have_x = ctx->ctr(C_TGX);
   a.matches = outbuf.as<uint4>();
@@ -819,7 +818,7 @@ void msc_destroy(msc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->rd_ascii,    &ctx->rd_offs,   &ctx->rd_words, &ctx->rd_x,      &ctx->len_flags, &ctx->validmask,
+  DevBuf* bufs[] = {&ctx->rd_ascii,    &ctx->rd_offs,   &ctx->rd_words, &ctx->rd_x,      &ctx->len_flags, &ctx->validmask, &ctx->rmeta, &ctx->cgene,
                     &ctx->tab_fp,      &ctx->tab_item0, &ctx->tab_cnt,  &ctx->tab_start, &ctx->tab_fill,  &ctx->pass_cnt, &ctx->bloom,
                     &ctx->items,       &ctx->dup_slot,  &ctx->fps,      &ctx->tg_ascii,  &ctx->tg_off,    &ctx->tg_words,
                     &ctx->tg_x,        &ctx->xsum,      &ctx->cand,     &ctx->cinfo,     &ctx->sizes,     &ctx->pstart,
@@ -851,6 +850,7 @@ static int reads_reserve(msc_ctx* ctx, uint64_t n_reads, uint64_t total) {
   CK(ctx->rd_x.reserve((n_reads * S + 2) * sizeof(uint64_t)));
   CK(ctx->len_flags.reserve((n_reads + 1) * sizeof(uint32_t)));
   CK(ctx->validmask.reserve((n_reads + 1) * sizeof(uint32_t)));
+  CK(ctx->rmeta.reserve((n_reads + 1) * sizeof(uint2)));
   const uint64_t kmax = std::max<uint64_t>(n_reads * nwin, 512);
   ctx->lg_slots = ceil_log2(2 * kmax);
   // Bloom front sizing (tuning only, never changes results): aim at 32-64 bits per key, but keep

@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(256) window_keys_kernel(const WinCfg cfg, cons
                                                           const uint32_t* __restrict__ len_flags, uint64_t n_reads,
                                                           uint32_t* __restrict__ validmask, uint64_t* __restrict__ fps,
                                                           unsigned long long* __restrict__ n_keys,
-                                                          unsigned long long* __restrict__ bloom, const BloomGeom geom) {
+                                                          unsigned long long* __restrict__ bloom, const BloomGeom geom,
+                                                          const int32_t* __restrict__ nmiss, uint2* __restrict__ rmeta) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t nk = 0;
   if (r < n_reads) {
@@ -88,6 +89,9 @@ __global__ void __launch_bounds__(256) window_keys_kernel(const WinCfg cfg, cons
       fps[r * (uint64_t)cfg.nwin + (uint64_t)k] = fp;
     }
     validmask[r] = vm;
+    // what the confirm kernel needs of a read in one 8-byte load: length (11 bits), mismatch
+    // budget nmiss(L) (11 bits, host-computed float64 table), has-X flag, valid-window mask
+    rmeta[r] = make_uint2((uint32_t)L | ((uint32_t)__ldg(nmiss + L) << 11) | (lf & 0x80000000u), vm);
   }
   // one counter atomic per block (same-address atomics serialise)
   __shared__ uint32_t s_nk[8];

@@ -18,15 +18,18 @@
 
 namespace msc {
 
-// Per candidate: locate its gene once (binary search in the target offsets), store
-// (gene, window start p inside the gene) and the number of (read, window) items of its key
-// group.  A W-mer that straddles a target boundary is not a window of any target
-// (processSeq only rolls inside one target, cmd/muscato_screen/main.go:319): size 0.
+// Per candidate: locate its gene once (binary search in the target offsets) and store what every
+// pair of the candidate needs in ONE 16-byte record: (table slot, global position of the window,
+// window start p inside the gene, global end of the gene); the gene index is kept aside for the
+// output records.  sizes[] = number of (read, window) items of its key group.  A W-mer that
+// straddles a target boundary is not a window of any target (processSeq only rolls inside one
+// target, cmd/muscato_screen/main.go:319): size 0.
 __global__ void __launch_bounds__(256) cand_prepare_kernel(const uint2* __restrict__ cand,
                                                            const unsigned long long* __restrict__ n_cand_ptr,
                                                            uint64_t cand_cap, const uint32_t* __restrict__ tab_cnt,
                                                            const uint32_t* __restrict__ tg_off, uint64_t n_targets,
-                                                           int W, uint2* __restrict__ cinfo,
+                                                           int W, uint4* __restrict__ cinfo,
+                                                           uint32_t* __restrict__ cgene,
                                                            uint32_t* __restrict__ sizes) {
   const uint64_t n_cand = min((uint64_t)*n_cand_ptr, cand_cap);
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -34,8 +37,8 @@ __global__ void __launch_bounds__(256) cand_prepare_kernel(const uint2* __restri
     const uint64_t g = upper_bound_dev<uint32_t>(tg_off, 0, n_targets + 1, cd.y) - 1;
     const uint32_t goff = __ldg(tg_off + g);
     const uint32_t gend = __ldg(tg_off + g + 1);
-    const uint32_t p = cd.y - goff;
-    cinfo[i] = make_uint2((uint32_t)g, p);
+    cinfo[i] = make_uint4(cd.x, cd.y, cd.y - goff, gend);
+    cgene[i] = (uint32_t)g;
     sizes[i] = ((uint64_t)cd.y + (uint64_t)W <= (uint64_t)gend) ? 1u + __ldg(tab_cnt + cd.x) : 0u;
   }
 }
@@ -59,8 +62,8 @@ __global__ void __launch_bounds__(256) pair_block_starts_kernel(const uint64_t* 
 
 struct ConfirmArgs {
   // candidates and their pair prefix
-  const uint2* cand;
-  const uint2* cinfo;          // (gene, p) per candidate
+  const uint4* cinfo;          // (slot, global window position, p, global gene end) per candidate
+  const uint32_t* cgene;       // gene index per candidate
   const uint32_t* block_first; // first candidate of each 256-pair block (+1 sentinel entry)
   const uint64_t* pstart;  // n_cand + 1
   const unsigned long long* n_pairs_ptr;  // device-side pair count (grand total of the size scan)
@@ -73,8 +76,7 @@ struct ConfirmArgs {
   // reads
   const uint64_t* rd_words;
   const uint64_t* rd_x;
-  const uint32_t* len_flags;
-  const uint32_t* validmask;
+  const uint2* rmeta;  // per read: (L | nmiss(L) << 11 | hasX << 31, valid-window mask), see window_keys_kernel
   // targets
   const uint64_t* tg_words;
   const uint64_t* tg_x;
@@ -82,7 +84,6 @@ struct ConfirmArgs {
   const uint32_t* tg_off;  // n_targets + 1 (base offsets in the concatenated stream)
   uint64_t n_targets;
   // rules
-  const int32_t* nmiss;  // [MRL + 1]
   uint64_t nwin_magic;   // floor(2^64 / nwin) + 1: item / nwin == umul64hi(item, magic) for 32-bit items
   const unsigned long long* targets_have_x;  // device flag: 0 = no target word contains X
   // outputs
@@ -120,46 +121,65 @@ __device__ __forceinline__ bool tg_range_has_x(const uint32_t* __restrict__ xsum
   return false;
 }
 
+// 32 bases of a packed stream starting at bit offset sh (0..62, even) of the word pair (t0, t1).
+__device__ __forceinline__ uint64_t funnel64(uint64_t t0, uint64_t t1, unsigned sh) {
+  return (t0 >> sh) | ((t1 << 1) << (63u - sh));
+}
+
 // One (candidate, read) pair; c = index of its candidate.  MODE is a compile-time copy of
 // ConfirmArgs::mode so that the hot mode-0 kernel carries none of the tap / overflow code.
 // Returns true when the pair yields an output record (`rec`): a match (read, gene, pos, nx) in
 // modes 0/2, an exact-key candidate (gene, p, read, window) in mode 1.  n_pass counts pairs
 // that passed through their window (before cross-window de-duplication).
+//
+// Fast path (no X in the read or in the target range, W < 32): the table's fingerprints are
+// exact there (common.cuh), so the window that produced the pair matches by construction and
+// the pair only needs the fit rule and the full-read mismatch count -- target words are loaded
+// once each (nwords + 1 loads) and funnel-shifted against the read's row.
 template <int MODE>
 __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const ConfirmArgs& a, uint64_t i, uint64_t c,
-                                                 uint4& rec, uint32_t& n_pass) {
-  const uint2 cd = __ldg(a.cand + c);
-  const uint2 ci = __ldg(a.cinfo + c);
-  const uint32_t slot = cd.x;
-  const uint64_t gpos = cd.y;
+                                                 bool targets_have_x, uint4& rec, uint32_t& n_pass) {
+  const uint4 ci = __ldg(a.cinfo + c);
+  const uint32_t slot = ci.x;
+  const uint64_t gpos = ci.y;
+  const int64_t p = (int64_t)ci.z;
   const uint32_t item = group_item(a.tab_item0, a.tab_start, a.items, slot, (uint32_t)(i - __ldg(a.pstart + c)));
   const uint32_t r = cfg.nwin == 1 ? item : (uint32_t)__umul64hi((uint64_t)item, a.nwin_magic);  // item / nwin
   const int k = (int)(item - r * (uint32_t)cfg.nwin);
   const int W = cfg.W;
-  const int q1 = cfg.windows[k], q2 = q1 + W;
-
-  // Gene of this candidate and window start p inside it (cand_prepare_kernel).
-  const uint64_t g = ci.x;
-  const int64_t p = (int64_t)ci.y;
-  const int64_t glen = (int64_t)__ldg(a.tg_off + g + 1) - (int64_t)__ldg(a.tg_off + g);
+  const int q1 = cfg.windows[k];
   const int64_t pos = p - q1;      // jw = jx - q1 >= 0 (cmd/muscato_screen/main.go:345, :355)
   if (pos < 0) return false;
 
-  const uint32_t lf = __ldg(a.len_flags + r);
-  const int L = (int)(lf & 0x7fffffffu);
-  const bool rx = lf >> 31;
+  const uint2 rm = __ldg(a.rmeta + r);
+  const int L = (int)(rm.x & 0x7ffu);
+  const int budget = (int)((rm.x >> 11) & 0x7ffu);
+  const bool rx = rm.x >> 31;
   const uint64_t* row = a.rd_words + (uint64_t)r * cfg.S;
-  const uint64_t* xrow = a.rd_x + (uint64_t)r * cfg.S;
-  const uint64_t kmask = low_bases_mask(W);
   const uint64_t gstart = gpos - (uint64_t)q1;  // global base index of the read's first base
-  const bool tx = __ldg(a.targets_have_x) != 0ull && tg_range_has_x(a.xsum, gstart >> 5, ((gstart + (uint64_t)L) >> 5) + 1);
+  const int64_t glen = (int64_t)ci.w - (int64_t)(gpos - (uint64_t)p);
+  const int64_t lim0 = min((int64_t)(100 - W), glen);  // position-0 record: right = t[W : min(100-q2, len)]
+
+  if (MODE != 1) {
+    // Fit rule (cmd/muscato_confirm/main.go:200-203) on the candidate's clipped right tail:
+    // for p >= 1 it reduces to pos + L <= len(target) (L <= MaxReadLength always holds); the
+    // position-0 record carries right = t[W : min(100 - q2, len)] (the literal 100, Q1).
+    if (p == 0) {
+      if ((int64_t)L > lim0) return false;
+    } else if (gstart + (uint64_t)L > (uint64_t)ci.w) {
+      return false;
+    }
+  }
+
+  const bool tx = targets_have_x && tg_range_has_x(a.xsum, gstart >> 5, ((gstart + (uint64_t)L) >> 5) + 1);
   const bool anyx = rx | tx;
+  const uint64_t kmask = low_bases_mask(W);
+  const uint64_t* xrow = a.rd_x + (uint64_t)r * cfg.S;
 
   // Exact key equality for the window that produced this pair (merge join on the k-mer bytes,
-  // cmd/muscato_confirm/main.go:382-393) rejects fingerprint collisions.  The tap (mode 1) tests
-  // it on its own; the confirm modes fold it into the mismatch loop below (a mismatch inside
-  // [q1, q2) disqualifies the pair), which saves two window extractions per pair.
-  if (MODE == 1) {
+  // cmd/muscato_confirm/main.go:382-393).  Fingerprints of X-free W<32 windows are exact, so only
+  // pairs that involve X (or W == 32) can be fingerprint collisions.
+  if (MODE == 1 || anyx || W == 32) {
     const uint64_t rk = extract32(row, (uint64_t)q1) & kmask;
     const uint64_t tk = extract32(a.tg_words, gpos) & kmask;
     if (rk != tk) return false;
@@ -168,55 +188,51 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
       const uint64_t txm = tx ? (extract32(a.tg_x, gpos) & kmask) : 0ull;
       if (rxm != txm) return false;
     }
-    rec = make_uint4((uint32_t)g, (uint32_t)p, r, (uint32_t)k);
-    return true;
-  }
-
-  // Fit rule (cmd/muscato_confirm/main.go:200-203) on the candidate's clipped right tail.
-  const int64_t lim0 = min((int64_t)(100 - W), glen);  // position-0 record: right = t[W : min(100-q2, len)]
-  if (p == 0) {
-    if ((int64_t)L > lim0) return false;  // len(srgt) = L - W <= min(100 - W, len) - W
-  } else {
-    const int64_t mr = min(p + W + (int64_t)cfg.MRL - q2, glen) - (p + W);
-    if ((int64_t)(L - q2) > mr) return false;
+    if (MODE == 1) {
+      rec = make_uint4(__ldg(a.cgene + c), (uint32_t)p, r, (uint32_t)k);
+      return true;
+    }
   }
 
   // Full-read mismatch count: nx = cdiff(left tails) + cdiff(right tails) (+0 inside the window).
   // Early exit once the budget is exceeded (the count itself is only needed for kept pairs).
   int nx = 0;
-  const int budget = __ldg(a.nmiss + L);
-  const int nwords = (L + 31) >> 5;
-  for (int w = 0; w < nwords; w++) {
-    const uint64_t ra = __ldg(row + w);
-    const uint64_t tb = extract32(a.tg_words, gstart + 32ull * w);
-    uint64_t x = ra ^ tb;
-    uint64_t m = (x | (x >> 1)) & kEvenBits;
-    if (anyx) {
-      const uint64_t xa = rx ? __ldg(xrow + w) : 0ull;
-      const uint64_t xb = tx ? extract32(a.tg_x, gstart + 32ull * w) : 0ull;
-      m = (m & ~(xa | xb)) | (xa ^ xb);  // X==X matches, X vs base mismatches (cdiff compares bytes)
+  {
+    const int nwords = (L + 31) >> 5;
+    const unsigned sh = (unsigned)(gstart & 31u) * 2u;
+    const uint64_t* tw = a.tg_words + (gstart >> 5);
+    const uint64_t* txw = a.tg_x + (gstart >> 5);
+    uint64_t t0 = __ldg(tw);
+    for (int w = 0; w < nwords; w++) {
+      const uint64_t t1 = __ldg(tw + w + 1);
+      const uint64_t x = __ldg(row + w) ^ funnel64(t0, t1, sh);
+      t0 = t1;
+      uint64_t m = (x | (x >> 1)) & kEvenBits;
+      if (anyx) {
+        const uint64_t xa = rx ? __ldg(xrow + w) : 0ull;
+        const uint64_t xb = tx ? funnel64(__ldg(txw + w), __ldg(txw + w + 1), sh) & kEvenBits : 0ull;
+        m = (m & ~(xa | xb)) | (xa ^ xb);  // X==X matches, X vs base mismatches (cdiff compares bytes)
+      }
+      if (w == nwords - 1) m &= low_bases_mask(L - 32 * w);  // row words are zero past L, the target is not
+      nx += __popcll(m);
+      if (nx > budget) return false;
     }
-    m &= low_bases_mask(min(32, L - 32 * w));
-    // bases of window k inside this word must match exactly
-    const int wl = max(q1 - 32 * w, 0), wh = min(q2 - 32 * w, 32);
-    if (wl < wh && (m & (low_bases_mask(wh) & ~low_bases_mask(wl)))) return false;
-    nx += __popcll(m);
-    if (nx > budget) return false;
   }
 
   // The pair passes through window k.
   atomicAdd(a.pass_cnt + slot, 1u);
   n_pass++;
+  const uint32_t g = __ldg(a.cgene + c);
   if (MODE == 2 && a.slot_over[slot]) {
     const unsigned long long at = warp_agg_inc(a.n_over_inst);
-    if (at < a.over_cap) a.over[at] = make_uint4(r, (uint32_t)g, (uint32_t)pos, (uint32_t)nx | ((uint32_t)k << 16));
+    if (at < a.over_cap) a.over[at] = make_uint4(r, g, (uint32_t)pos, (uint32_t)nx | ((uint32_t)k << 16));
     return false;
   }
 
   // Cross-window de-duplication: emit only through the lowest window index that delivers
   // this (read, gene, pos).  Window k' delivers it iff it is valid for the read, its k-mer
   // matches exactly, and -- when it would sit at target position 0 -- the literal-100 rule holds.
-  uint32_t vm = __ldg(a.validmask + r) & ((1u << k) - 1u);
+  uint32_t vm = rm.y & ((1u << k) - 1u);
   while (vm) {
     const int k2 = __ffs(vm) - 1;
     vm &= vm - 1;
@@ -239,7 +255,7 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
   }
 
   atomicMin(a.best + r, (uint32_t)nx);
-  rec = make_uint4(r, (uint32_t)g, (uint32_t)pos, (uint32_t)nx);
+  rec = make_uint4(r, g, (uint32_t)pos, (uint32_t)nx);
   return true;
 }
 
@@ -264,6 +280,7 @@ __global__ void __launch_bounds__(256, 6) confirm_pairs_kernel(const WinCfg cfg,
   const uint64_t n_chunks = (n_blocks256 + kPairsPerThread - 1) / kPairsPerThread;
   uint32_t n_pass = 0;
   uint32_t n_out = 0;  // records staged by this warp (warp-uniform), carried across chunks
+  const bool targets_have_x = *a.targets_have_x != 0ull;
   auto flush_out = [&]() {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(a.n_match, (unsigned long long)n_out);
@@ -293,7 +310,7 @@ __global__ void __launch_bounds__(256, 6) confirm_pairs_kernel(const WinCfg cfg,
           c++;
           c_end = __ldg(a.pstart + c + 1);
         }
-        has = confirm_one_pair<MODE>(cfg, a, i, c, rec, n_pass);
+        has = confirm_one_pair<MODE>(cfg, a, i, c, targets_have_x, rec, n_pass);
       }
       const unsigned m = __ballot_sync(0xffffffffu, has);
       if (has) my_out[n_out + __popc(m & ((1u << lane) - 1u))] = rec;
