@@ -79,7 +79,7 @@ struct msc_ctx {
   WinCfg win{};
   int device = 0;
   int sm_count = 148;
-  int scan_grid = 0;
+  int scan_grid = 0, confirm_grid = 0;
   const void* scan_fn_sized = nullptr;  // the scan kernel instance scan_grid was computed for
   cudaStream_t stream = nullptr;       // every kernel runs here
   cudaStream_t copy_stream = nullptr;  // input H2D copies: overlap with kernels of the previous input
@@ -107,7 +107,7 @@ struct msc_ctx {
   // candidates / pairs
   uint64_t n_cand = 0, n_pairs = 0;
   bool have_cand = false;
-  DevBuf cand, cinfo, cgene, sizes, pstart, block_first;
+  DevBuf cand, cinfo, sizes, pstart, block_first;
   // matches
   uint64_t n_match_pre = 0, n_match = 0;
   bool have_confirm = false, have_combine = false;
@@ -472,16 +472,16 @@ int enqueue_scan(msc_ctx* ctx) {
 int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   const uint64_t ccap = ctx->cand_cap();
   CK(ctx->sizes.reserve((ccap + 1) * sizeof(uint32_t)));
-  CK(ctx->cinfo.reserve((ccap + 1) * sizeof(uint4)));
-  CK(ctx->cgene.reserve((ccap + 1) * sizeof(uint32_t)));
+  CK(ctx->cinfo.reserve((ccap + 1) * 2 * sizeof(uint4)));
   CK(ctx->pstart.reserve((ccap + 2) * sizeof(uint64_t)));
-  if (ctx->block_first.cap == 0) CK(ctx->block_first.reserve(((size_t)(1u << 16) + 2) * sizeof(uint32_t)));
+  if (ctx->block_first.cap == 0) CK(ctx->block_first.reserve(((size_t)(1u << 19) + 2) * sizeof(uint32_t)));
   if (outbuf.cap == 0) CK(outbuf.reserve((size_t)(1u << 20) * sizeof(uint4)));
   const unsigned pgrid = (unsigned)ctx->sm_count * 8;
   cand_prepare_kernel<<<pgrid, 256, 0, ctx->stream>>>(ctx->cand.as<uint2>(), ctx->ctr(C_NCAND), ccap,
-                                                      ctx->tab_cnt.as<uint32_t>(), ctx->tg_off.as<uint32_t>(),
+                                                      ctx->tab_cnt.as<uint32_t>(), ctx->tab_item0.as<uint32_t>(),
+                                                      ctx->tab_start.as<uint32_t>(), ctx->tg_off.as<uint32_t>(),
                                                       ctx->n_targets, ctx->win.W, ctx->cinfo.as<uint4>(),
-                                                      ctx->cgene.as<uint32_t>(), ctx->sizes.as<uint32_t>());
+                                                      ctx->sizes.as<uint32_t>());
   LAUNCH_CHECK();
   RC(enqueue_exclusive_scan<uint64_t>(ctx, ctx->sizes.as<uint32_t>(), ctx->ctr(C_NCAND), ccap, ctx->pstart.as<uint64_t>(),
                                       true, ctx->ctr(C_NPAIRS)));
@@ -499,13 +499,10 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   ctx->pro.pairs = false;
   ConfirmArgs a{};
   a.cinfo = ctx->cinfo.as<uint4>();
-  a.cgene = ctx->cgene.as<uint32_t>();
   a.block_first = ctx->block_first.as<uint32_t>();
   a.pstart = ctx->pstart.as<uint64_t>();
   a.n_pairs_ptr = ctx->ctr(C_NPAIRS);
   a.block_cap = ctx->block_cap();
-  a.tab_item0 = ctx->tab_item0.as<uint32_t>();
-  a.tab_start = ctx->tab_start.as<uint32_t>();
   a.items = ctx->items.as<uint32_t>();
   a.pass_cnt = ctx->pass_cnt.as<uint32_t>();
   a.rd_words = ctx->rd_words.as<uint64_t>();
@@ -533,7 +530,12 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
     a.over_cap = ctx->pair_mode2.over_cap;
     a.n_over_inst = ctx->ctr(C_NLONG);
   }
-  const unsigned cgrid = (unsigned)ctx->sm_count * 8;
+  if (ctx->confirm_grid == 0) {  // persistent grid: exactly the resident CTAs
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, confirm_pairs_kernel<0>, 256, 0));
+    ctx->confirm_grid = ctx->sm_count * std::max(1, per_sm);
+  }
+  const unsigned cgrid = (unsigned)ctx->confirm_grid;
   if (mode == 0) confirm_pairs_kernel<0><<<cgrid, 256, 0, ctx->stream>>>(ctx->win, a);
   else if (mode == 1) confirm_pairs_kernel<1><<<cgrid, 256, 0, ctx->stream>>>(ctx->win, a);
   else confirm_pairs_kernel<2><<<cgrid, 256, 0, ctx->stream>>>(ctx->win, a);
@@ -616,7 +618,7 @@ int finish_scan(msc_ctx* ctx) {
 
 int finish_pairs(msc_ctx* ctx, DevBuf& outbuf, uint64_t* n_out) {
   ctx->n_pairs = ctx->h_counters[C_NPAIRS];
-  const uint64_t n_blocks = (ctx->n_pairs + 255) / 256;
+  const uint64_t n_blocks = (ctx->n_pairs + kPairBlock - 1) / kPairBlock;
   bool retry = false;
   if (n_blocks > ctx->block_cap()) {
     CK(ctx->block_first.reserve((n_blocks + 2) * sizeof(uint32_t)));
@@ -818,7 +820,7 @@ void msc_destroy(msc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->rd_ascii,    &ctx->rd_offs,   &ctx->rd_words, &ctx->rd_x,      &ctx->len_flags, &ctx->validmask, &ctx->rmeta, &ctx->cgene,
+  DevBuf* bufs[] = {&ctx->rd_ascii,    &ctx->rd_offs,   &ctx->rd_words, &ctx->rd_x,      &ctx->len_flags, &ctx->validmask, &ctx->rmeta,
                     &ctx->tab_fp,      &ctx->tab_item0, &ctx->tab_cnt,  &ctx->tab_start, &ctx->tab_fill,  &ctx->pass_cnt, &ctx->bloom,
                     &ctx->items,       &ctx->dup_slot,  &ctx->fps,      &ctx->tg_ascii,  &ctx->tg_off,    &ctx->tg_words,
                     &ctx->tg_x,        &ctx->xsum,      &ctx->cand,     &ctx->cinfo,     &ctx->sizes,     &ctx->pstart,

@@ -18,18 +18,23 @@
 
 namespace msc {
 
+// Pairs are addressed in blocks of kPairBlock consecutive pair indices (block_first[]).
+constexpr int kPairBlockShift = 5;
+constexpr int kPairBlock = 1 << kPairBlockShift;
+
 // Per candidate: locate its gene once (binary search in the target offsets) and store what every
-// pair of the candidate needs in ONE 16-byte record: (table slot, global position of the window,
-// window start p inside the gene, global end of the gene); the gene index is kept aside for the
-// output records.  sizes[] = number of (read, window) items of its key group.  A W-mer that
-// straddles a target boundary is not a window of any target (processSeq only rolls inside one
-// target, cmd/muscato_screen/main.go:319): size 0.
+// pair of the candidate needs in ONE 32-byte sector (two uint4): (table slot, global position of
+// the window, window start p inside the gene, global end of the gene) and (first item of the key
+// group, CSR start of the further items, gene index, -).  sizes[] = number of (read, window)
+// items of its key group.  A W-mer that straddles a target boundary is not a window of any target
+// (processSeq only rolls inside one target, cmd/muscato_screen/main.go:319): size 0.
 __global__ void __launch_bounds__(256) cand_prepare_kernel(const uint2* __restrict__ cand,
                                                            const unsigned long long* __restrict__ n_cand_ptr,
                                                            uint64_t cand_cap, const uint32_t* __restrict__ tab_cnt,
+                                                           const uint32_t* __restrict__ tab_item0,
+                                                           const uint32_t* __restrict__ tab_start,
                                                            const uint32_t* __restrict__ tg_off, uint64_t n_targets,
                                                            int W, uint4* __restrict__ cinfo,
-                                                           uint32_t* __restrict__ cgene,
                                                            uint32_t* __restrict__ sizes) {
   const uint64_t n_cand = min((uint64_t)*n_cand_ptr, cand_cap);
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -37,14 +42,16 @@ __global__ void __launch_bounds__(256) cand_prepare_kernel(const uint2* __restri
     const uint64_t g = upper_bound_dev<uint32_t>(tg_off, 0, n_targets + 1, cd.y) - 1;
     const uint32_t goff = __ldg(tg_off + g);
     const uint32_t gend = __ldg(tg_off + g + 1);
-    cinfo[i] = make_uint4(cd.x, cd.y, cd.y - goff, gend);
-    cgene[i] = (uint32_t)g;
-    sizes[i] = ((uint64_t)cd.y + (uint64_t)W <= (uint64_t)gend) ? 1u + __ldg(tab_cnt + cd.x) : 0u;
+    const uint32_t further = __ldg(tab_cnt + cd.x);
+    cinfo[2 * i] = make_uint4(cd.x, cd.y, cd.y - goff, gend);
+    cinfo[2 * i + 1] = make_uint4(__ldg(tab_item0 + cd.x), further ? __ldg(tab_start + cd.x) : 0u, (uint32_t)g, 0u);
+    sizes[i] = ((uint64_t)cd.y + (uint64_t)W <= (uint64_t)gend) ? 1u + further : 0u;
   }
 }
 
-// First candidate of every 256-pair block of the confirm kernel (one parallel binary search
-// per block instead of a serial one inside the block).  Entry n_blocks is a sentinel.
+// First candidate of every kPairBlock-pair block of the confirm kernel (one parallel binary
+// search per block, so that the search inside the kernel only spans the block's few
+// candidates).  Entry n_blocks is a sentinel.
 __global__ void __launch_bounds__(256) pair_block_starts_kernel(const uint64_t* __restrict__ pstart,
                                                                 const unsigned long long* __restrict__ n_cand_ptr,
                                                                 uint64_t cand_cap,
@@ -53,24 +60,21 @@ __global__ void __launch_bounds__(256) pair_block_starts_kernel(const uint64_t* 
   const uint64_t n_cand = min((uint64_t)*n_cand_ptr, cand_cap);
   const uint64_t n_pairs = *n_pairs_ptr;
   if (n_pairs == 0) return;
-  const uint64_t n_blocks = min((uint64_t)((n_pairs + 255) / 256), block_cap);
+  const uint64_t n_blocks = min((uint64_t)((n_pairs + kPairBlock - 1) >> kPairBlockShift), block_cap);
   for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= n_blocks; b += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t first = min((uint64_t)(b * 256ull), (uint64_t)(n_pairs - 1));
+    const uint64_t first = min((uint64_t)(b << kPairBlockShift), (uint64_t)(n_pairs - 1));
     block_first[b] = (uint32_t)(upper_bound_dev<uint64_t>(pstart, 0, n_cand, first) - 1);
   }
 }
 
 struct ConfirmArgs {
   // candidates and their pair prefix
-  const uint4* cinfo;          // (slot, global window position, p, global gene end) per candidate
-  const uint32_t* cgene;       // gene index per candidate
-  const uint32_t* block_first; // first candidate of each 256-pair block (+1 sentinel entry)
+  const uint4* cinfo;          // two per candidate, see cand_prepare_kernel
+  const uint32_t* block_first; // first candidate of each kPairBlock-pair block (+1 sentinel entry)
   const uint64_t* pstart;  // n_cand + 1
   const unsigned long long* n_pairs_ptr;  // device-side pair count (grand total of the size scan)
-  uint64_t block_cap;                     // capacity of block_first (in 256-pair blocks)
+  uint64_t block_cap;                     // capacity of block_first (in kPairBlock-pair blocks)
   // key table
-  const uint32_t* tab_item0;
-  const uint32_t* tab_start;
   const uint32_t* items;
   uint32_t* pass_cnt;  // per slot: pairs that passed (MaxMatches pre-check)
   // reads
@@ -138,12 +142,15 @@ __device__ __forceinline__ uint64_t funnel64(uint64_t t0, uint64_t t1, unsigned 
 // once each (nwords + 1 loads) and funnel-shifted against the read's row.
 template <int MODE>
 __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const ConfirmArgs& a, uint64_t i, uint64_t c,
-                                                 bool targets_have_x, uint4& rec, uint32_t& n_pass) {
-  const uint4 ci = __ldg(a.cinfo + c);
+                                                 uint64_t c_start, bool targets_have_x, uint4& rec,
+                                                 uint32_t& n_pass) {
+  const uint4 ci = __ldg(a.cinfo + 2 * c);
+  const uint4 cj = __ldg(a.cinfo + 2 * c + 1);  // (first item, CSR start, gene, -)
   const uint32_t slot = ci.x;
   const uint64_t gpos = ci.y;
   const int64_t p = (int64_t)ci.z;
-  const uint32_t item = group_item(a.tab_item0, a.tab_start, a.items, slot, (uint32_t)(i - __ldg(a.pstart + c)));
+  const uint32_t j = (uint32_t)(i - c_start);
+  const uint32_t item = j == 0 ? cj.x : __ldg(a.items + cj.y + (j - 1));
   const uint32_t r = cfg.nwin == 1 ? item : (uint32_t)__umul64hi((uint64_t)item, a.nwin_magic);  // item / nwin
   const int k = (int)(item - r * (uint32_t)cfg.nwin);
   const int W = cfg.W;
@@ -189,7 +196,7 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
       if (rxm != txm) return false;
     }
     if (MODE == 1) {
-      rec = make_uint4(__ldg(a.cgene + c), (uint32_t)p, r, (uint32_t)k);
+      rec = make_uint4(cj.z, (uint32_t)p, r, (uint32_t)k);
       return true;
     }
   }
@@ -202,30 +209,49 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
     const unsigned sh = (unsigned)(gstart & 31u) * 2u;
     const uint64_t* tw = a.tg_words + (gstart >> 5);
     const uint64_t* txw = a.tg_x + (gstart >> 5);
-    uint64_t t0 = __ldg(tw);
-    for (int w = 0; w < nwords; w++) {
-      const uint64_t t1 = __ldg(tw + w + 1);
-      const uint64_t x = __ldg(row + w) ^ funnel64(t0, t1, sh);
-      t0 = t1;
-      uint64_t m = (x | (x >> 1)) & kEvenBits;
-      if (anyx) {
-        const uint64_t xa = rx ? __ldg(xrow + w) : 0ull;
-        const uint64_t xb = tx ? funnel64(__ldg(txw + w), __ldg(txw + w + 1), sh) & kEvenBits : 0ull;
-        m = (m & ~(xa | xb)) | (xa ^ xb);  // X==X matches, X vs base mismatches (cdiff compares bytes)
+    if (!anyx && nwords <= 4) {
+      // Short reads without X (the norm): all loads are issued before the first compare, so the
+      // early exit costs no dependent round trips.
+      uint64_t rw[4], t[5];
+#pragma unroll
+      for (int w = 0; w < 4; w++) rw[w] = w < nwords ? __ldg(row + w) : 0ull;
+#pragma unroll
+      for (int w = 0; w < 5; w++) t[w] = w <= nwords ? __ldg(tw + w) : 0ull;
+#pragma unroll
+      for (int w = 0; w < 4; w++) {
+        if (w < nwords) {
+          const uint64_t x = rw[w] ^ funnel64(t[w], t[w + 1], sh);
+          uint64_t m = (x | (x >> 1)) & kEvenBits;
+          if (w == nwords - 1) m &= low_bases_mask(L - 32 * w);  // row words are zero past L, the target is not
+          nx += __popcll(m);
+        }
       }
-      if (w == nwords - 1) m &= low_bases_mask(L - 32 * w);  // row words are zero past L, the target is not
-      nx += __popcll(m);
       if (nx > budget) return false;
+    } else {
+      uint64_t t0 = __ldg(tw);
+      for (int w = 0; w < nwords; w++) {
+        const uint64_t t1 = __ldg(tw + w + 1);
+        const uint64_t x = __ldg(row + w) ^ funnel64(t0, t1, sh);
+        t0 = t1;
+        uint64_t m = (x | (x >> 1)) & kEvenBits;
+        if (anyx) {
+          const uint64_t xa = rx ? __ldg(xrow + w) : 0ull;
+          const uint64_t xb = tx ? funnel64(__ldg(txw + w), __ldg(txw + w + 1), sh) & kEvenBits : 0ull;
+          m = (m & ~(xa | xb)) | (xa ^ xb);  // X==X matches, X vs base mismatches (cdiff compares bytes)
+        }
+        if (w == nwords - 1) m &= low_bases_mask(L - 32 * w);
+        nx += __popcll(m);
+        if (nx > budget) return false;
+      }
     }
   }
 
   // The pair passes through window k.
   atomicAdd(a.pass_cnt + slot, 1u);
   n_pass++;
-  const uint32_t g = __ldg(a.cgene + c);
   if (MODE == 2 && a.slot_over[slot]) {
     const unsigned long long at = warp_agg_inc(a.n_over_inst);
-    if (at < a.over_cap) a.over[at] = make_uint4(r, g, (uint32_t)pos, (uint32_t)nx | ((uint32_t)k << 16));
+    if (at < a.over_cap) a.over[at] = make_uint4(r, cj.z, (uint32_t)pos, (uint32_t)nx | ((uint32_t)k << 16));
     return false;
   }
 
@@ -255,7 +281,7 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
   }
 
   atomicMin(a.best + r, (uint32_t)nx);
-  rec = make_uint4(r, g, (uint32_t)pos, (uint32_t)nx);
+  rec = make_uint4(r, cj.z, (uint32_t)pos, (uint32_t)nx);
   return true;
 }
 
@@ -270,14 +296,17 @@ constexpr int kPairsPerThread = 4;
 constexpr int kChunkPairs = kPairsPerThread * 256;
 constexpr int kOutStage = 128;  // per-warp output staging (records); flushed when nearly full
 
+#ifndef MSC_CONFIRM_CTAS
+#define MSC_CONFIRM_CTAS 5
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(256, 6) confirm_pairs_kernel(const WinCfg cfg, const ConfirmArgs a) {
+__global__ void __launch_bounds__(256, MSC_CONFIRM_CTAS) confirm_pairs_kernel(const WinCfg cfg, const ConfirmArgs a) {
   __shared__ uint4 s_out[8][kOutStage];
   const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
   uint4* my_out = s_out[wid];
   const uint64_t n_pairs = *a.n_pairs_ptr;
-  const uint64_t n_blocks256 = min((uint64_t)((n_pairs + 255) / 256), a.block_cap);
-  const uint64_t n_chunks = (n_blocks256 + kPairsPerThread - 1) / kPairsPerThread;
+  const uint64_t n_blocks = min((uint64_t)((n_pairs + kPairBlock - 1) >> kPairBlockShift), a.block_cap);
+  const uint64_t n_chunks = ((n_blocks << kPairBlockShift) + kChunkPairs - 1) / kChunkPairs;
   uint32_t n_pass = 0;
   uint32_t n_out = 0;  // records staged by this warp (warp-uniform), carried across chunks
   const bool targets_have_x = *a.targets_have_x != 0ull;
@@ -292,12 +321,13 @@ __global__ void __launch_bounds__(256, 6) confirm_pairs_kernel(const WinCfg cfg,
   };
   for (uint64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
     const uint64_t i0 = ch * (uint64_t)kChunkPairs + (uint64_t)threadIdx.x * kPairsPerThread;
-    const bool live = i0 < n_pairs && (i0 >> 8) < n_blocks256;
-    uint64_t c = 0, c_end = 0;
+    const bool live = i0 < n_pairs && (i0 >> kPairBlockShift) < n_blocks;
+    uint64_t c = 0, c_start = 0, c_end = 0;
     if (live) {
-      const uint64_t b = i0 >> 8;
+      const uint64_t b = i0 >> kPairBlockShift;
       const uint64_t clo = __ldg(a.block_first + b), chi = __ldg(a.block_first + b + 1);
       c = upper_bound_dev<uint64_t>(a.pstart, clo, chi + 1, i0) - 1;
+      c_start = __ldg(a.pstart + c);
       c_end = __ldg(a.pstart + c + 1);
     }
 #pragma unroll 1
@@ -308,9 +338,10 @@ __global__ void __launch_bounds__(256, 6) confirm_pairs_kernel(const WinCfg cfg,
       if (live && i < n_pairs) {
         while (c_end <= i) {  // next candidate with at least one pair
           c++;
+          c_start = c_end;
           c_end = __ldg(a.pstart + c + 1);
         }
-        has = confirm_one_pair<MODE>(cfg, a, i, c, targets_have_x, rec, n_pass);
+        has = confirm_one_pair<MODE>(cfg, a, i, c, c_start, targets_have_x, rec, n_pass);
       }
       const unsigned m = __ballot_sync(0xffffffffu, has);
       if (has) my_out[n_out + __popc(m & ((1u << lane) - 1u))] = rec;
