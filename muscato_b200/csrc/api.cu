@@ -83,7 +83,12 @@ struct msc_ctx {
   const void* scan_fn_sized = nullptr;  // the scan kernel instance scan_grid was computed for
   cudaStream_t stream = nullptr;       // every kernel runs here
   cudaStream_t copy_stream = nullptr;  // input H2D copies: overlap with kernels of the previous input
-  cudaEvent_t ev_copy = nullptr, ev_compute = nullptr;
+  cudaEvent_t ev_copy = nullptr;
+  // "the kernels that read the upload destinations have been enqueued up to here": an upload only
+  // waits for those (pack_reads for the read buffers, pack_targets for the target buffers; every
+  // other reader of tg_off is followed by a host synchronisation before its call returns), so a
+  // target upload overlaps with the key-table build of the reads that were just set.
+  cudaEvent_t ev_rd_free = nullptr, ev_tg_free = nullptr;
   bool pend_reads = false, pend_targets = false;  // enqueued builds whose counters/timers are not read yet
   cudaEvent_t ev[EV_COUNT] = {};
   std::string err;
@@ -120,7 +125,7 @@ struct msc_ctx {
   } pair_mode2;
   // misc
   DevBuf counters, tile_sums, scan_state, nmiss;
-  uint32_t scan_epoch = 0;
+  unsigned long long scan_arrivals = 0;  // arrivals the scan kernel's grid barrier has seen so far (never reset)
   unsigned long long* h_counters = nullptr;  // pinned mirror
   // MSC_TRACE=1: an event after every launch, per-launch device times printed at each sync
   bool trace = false;
@@ -198,24 +203,18 @@ int ceil_log2(uint64_t v) {
 
 // Exclusive scan of uint32 in[] -> OutT out[] (+ out[n] = total when write_end).  The element
 // count is n_host, or the device counter *n_ptr clamped to n_host.  The grand total goes to
-// *total (a device counter).  Three launches, no host involvement.
+// *total (a device counter).  One launch, no host involvement.
 template <typename OutT>
 int enqueue_exclusive_scan(msc_ctx* ctx, const uint32_t* in, const unsigned long long* n_ptr, uint64_t n_host, OutT* out,
                            bool write_end, unsigned long long* total) {
-  const uint64_t max_tiles = std::max<uint64_t>(1, (n_host + kScanTile - 1) / kScanTile);
-  const size_t had = ctx->tile_sums.cap;
-  CK(ctx->tile_sums.reserve((max_tiles + 1) * sizeof(uint64_t)));
-  ctx->scan_epoch = (ctx->scan_epoch + 1) % kScanEpochs;
-  if (ctx->tile_sums.cap != had || ctx->scan_epoch == 0) {
-    // fresh (or epoch-wrapped) descriptor array: make every descriptor invalid once
-    CK(cudaMemsetAsync(ctx->tile_sums.p, 0, ctx->tile_sums.cap, ctx->stream));
-    if (ctx->scan_epoch == 0) ctx->scan_epoch = 1;
-  }
-  const unsigned grid = (unsigned)std::min<uint64_t>(max_tiles, (uint64_t)ctx->sm_count * 8);
-  scan_onepass_kernel<OutT><<<grid, kScanThreads, 0, ctx->stream>>>(in, n_ptr, n_host, out, write_end ? 1 : 0, total,
-                                                                    ctx->tile_sums.as<uint64_t>(),
-                                                                    ctx->scan_state.as<unsigned long long>(),
-                                                                    ctx->scan_epoch);
+  // one block per SM: the whole grid is resident, which the kernel's grid barrier relies on
+  const unsigned grid = (unsigned)std::min(ctx->sm_count, kScanThreads);
+  if (ctx->tile_sums.cap == 0) CK(ctx->tile_sums.reserve((size_t)kScanThreads * sizeof(uint64_t)));
+  ctx->scan_arrivals += grid;
+  scan_resident_kernel<OutT><<<grid, kScanThreads, 0, ctx->stream>>>(in, n_ptr, n_host, out, write_end ? 1 : 0, total,
+                                                                     ctx->tile_sums.as<uint64_t>(),
+                                                                     ctx->scan_state.as<unsigned long long>(),
+                                                                     ctx->scan_arrivals);
   LAUNCH_CHECK();
   return MSC_OK;
 }
@@ -287,14 +286,13 @@ int sync_counters(msc_ctx* ctx) {
   return MSC_OK;
 }
 
-// Input upload on the copy stream.  The copy waits for everything already enqueued on the
-// compute stream (the destination may still be read by earlier kernels); the compute stream
+// Input upload on the copy stream.  The copy waits for the kernels that may still read its
+// destination (ev_rd_free / ev_tg_free); the compute stream
 // waits for the copy; the HOST only waits for the copy, because the caller's buffers are
 // borrowed for the duration of the call -- the kernels that consume the data keep running while
 // the caller prepares (or uploads) its next input.
-int begin_upload(msc_ctx* ctx) {
-  CK(cudaEventRecord(ctx->ev_compute, ctx->stream));
-  CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_compute, 0));
+int begin_upload(msc_ctx* ctx, cudaEvent_t dest_free) {
+  CK(cudaStreamWaitEvent(ctx->copy_stream, dest_free, 0));
   return MSC_OK;
 }
 int end_upload(msc_ctx* ctx) {
@@ -336,6 +334,7 @@ int enqueue_build_reads(msc_ctx* ctx) {
         ctx->rd_x.as<uint64_t>(), ctx->len_flags.as<uint32_t>());
     LAUNCH_CHECK();
   }
+  CK(cudaEventRecord(ctx->ev_rd_free, ctx->stream));
   CK(cudaEventRecord(ctx->ev[EV_PACKR1], ctx->stream));
 
   const uint64_t n_items = U * (uint64_t)ctx->win.nwin;
@@ -399,6 +398,7 @@ int enqueue_pack_targets(msc_ctx* ctx) {
       ctx->tg_ascii.as<uint8_t>(), ctx->n_bases, ctx->tg_words.as<uint64_t>(), ctx->n_words_alloc,
       ctx->tg_x.as<uint64_t>(), ctx->xsum.as<uint32_t>(), ctx->ctr(C_TGX));
   LAUNCH_CHECK();
+  CK(cudaEventRecord(ctx->ev_tg_free, ctx->stream));
   CK(cudaEventRecord(ctx->ev[EV_PACKT1], ctx->stream));
   ctx->have_cand = ctx->have_confirm = ctx->have_combine = false;
   ctx->pend_targets = true;
@@ -544,7 +544,7 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
     // MaxMatches pre-check (cmd/muscato_confirm/main.go:233-242, :424-448): truncation can only
     // happen in a key group with more than MaxMatches passing pairs.
     const uint64_t slots = 1ull << ctx->lg_slots;
-    overflow_count_kernel<<<grid_for(slots, 256), 256, 0, ctx->stream>>>(
+    overflow_count_kernel<<<(unsigned)ctx->sm_count * 4, 256, 0, ctx->stream>>>(
         ctx->pass_cnt.as<uint32_t>(), slots, (unsigned long long)ctx->cfg.max_matches, ctx->ctr(C_NPASS),
         ctx->ctr(C_NOVER));
     LAUNCH_CHECK();
@@ -788,7 +788,8 @@ msc_ctx* msc_create(const msc_config* config, char* errbuf, uint64_t errlen) {
   bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming) == cudaSuccess;
-  ok = ok && cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_rd_free, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_tg_free, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < EV_COUNT; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
   ok = ok && ctx->counters.reserve(C_COUNT * sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaMallocHost(&ctx->h_counters, C_COUNT * sizeof(unsigned long long)) == cudaSuccess;
@@ -806,6 +807,8 @@ msc_ctx* msc_create(const msc_config* config, char* errbuf, uint64_t errlen) {
   ok = ok && cudaMemset(ctx->scan_state.p, 0, 2 * sizeof(unsigned long long)) == cudaSuccess;
   // every event is recorded once so that cudaEventElapsedTime never sees a virgin event
   for (int i = 0; ok && i < EV_COUNT; i++) ok = cudaEventRecord(ctx->ev[i], ctx->stream) == cudaSuccess;
+  ok = ok && cudaEventRecord(ctx->ev_rd_free, ctx->stream) == cudaSuccess;
+  ok = ok && cudaEventRecord(ctx->ev_tg_free, ctx->stream) == cudaSuccess;
   ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
   if (!ok) {
     std::string m = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -832,7 +835,8 @@ void msc_destroy(msc_ctx* ctx) {
     if (e) cudaEventDestroy(e);
   for (auto& te : ctx->trace_ev) cudaEventDestroy(te.second);
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
-  if (ctx->ev_compute) cudaEventDestroy(ctx->ev_compute);
+  if (ctx->ev_rd_free) cudaEventDestroy(ctx->ev_rd_free);
+  if (ctx->ev_tg_free) cudaEventDestroy(ctx->ev_tg_free);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -906,22 +910,35 @@ int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint
   uint64_t total = 0;
   if (n_reads) {
     if (offs[0] != 0) return ctx->fail(MSC_ERR_INPUT, "reads: offs[0] must be 0");
-    const uint64_t mrl = (uint64_t)ctx->win.MRL;
-    for (uint64_t i = 0; i < n_reads; i++) {
-      if (offs[i + 1] < offs[i]) return ctx->fail(MSC_ERR_INPUT, "reads: offsets not monotone at %llu", (unsigned long long)i);
-      if (offs[i + 1] - offs[i] > mrl)
-        return ctx->fail(MSC_ERR_INPUT, "reads: read %llu is longer than MaxReadLength (prep_reads truncates, "
-                         "cmd/muscato_prep_reads/main.go:67-69)", (unsigned long long)i);
-    }
     total = offs[n_reads];
+    if (total > n_reads * (uint64_t)ctx->win.MRL)
+      return ctx->fail(MSC_ERR_INPUT, "reads: more bytes than n_reads * MaxReadLength (prep_reads truncates, "
+                       "cmd/muscato_prep_reads/main.go:67-69)");
   }
   RC(reads_reserve(ctx, n_reads, total));
-  RC(begin_upload(ctx));
+  ctx->have_reads = false;
+  RC(begin_upload(ctx, ctx->ev_rd_free));
   if (total) CK(cudaMemcpyAsync(ctx->rd_ascii.p, ascii, total, cudaMemcpyHostToDevice, ctx->copy_stream));
   if (n_reads) CK(cudaMemcpyAsync(ctx->rd_offs.p, offs, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->copy_stream));
   else CK(cudaMemsetAsync(ctx->rd_offs.p, 0, sizeof(uint64_t), ctx->copy_stream));
   RC(end_upload(ctx));
   ctx->st.h2d_bytes += total + (n_reads + 1) * sizeof(uint64_t);
+  // The offsets are validated while the copy is in flight; no kernel that indexes the ASCII
+  // buffer through them is enqueued before they are known to be sane.
+  {
+    const uint64_t mrl = (uint64_t)ctx->win.MRL;
+    uint64_t bad = 0;
+    for (uint64_t i = 0; i < n_reads; i++) bad |= (uint64_t)(offs[i + 1] < offs[i]) | (uint64_t)(offs[i + 1] - offs[i] > mrl);
+    if (bad) {
+      RC(wait_upload(ctx));
+      for (uint64_t i = 0; i < n_reads; i++) {
+        if (offs[i + 1] < offs[i]) return ctx->fail(MSC_ERR_INPUT, "reads: offsets not monotone at %llu", (unsigned long long)i);
+        if (offs[i + 1] - offs[i] > mrl)
+          return ctx->fail(MSC_ERR_INPUT, "reads: read %llu is longer than MaxReadLength (prep_reads truncates, "
+                           "cmd/muscato_prep_reads/main.go:67-69)", (unsigned long long)i);
+      }
+    }
+  }
   ctx->have_reads = true;
   RC(enqueue_build_reads(ctx));  // runs behind the copy; its counters are booked at the next sync
   RC(wait_upload(ctx));          // the caller's buffers are only borrowed for the call
@@ -991,7 +1008,7 @@ int msc_set_targets(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, ui
   CK(ctx->tg_words.reserve(ctx->n_words_alloc * sizeof(uint64_t)));
   CK(ctx->tg_x.reserve(ctx->n_words_alloc * sizeof(uint64_t)));
   CK(ctx->xsum.reserve((ctx->n_words_alloc / 32 + 4) * sizeof(uint32_t)));
-  RC(begin_upload(ctx));
+  RC(begin_upload(ctx, ctx->ev_tg_free));
   if (total) CK(cudaMemcpyAsync(ctx->tg_ascii.p, ascii, total, cudaMemcpyHostToDevice, ctx->copy_stream));
   CK(cudaMemcpyAsync(ctx->tg_off.p, off32.data(), (n_targets + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream));
   RC(end_upload(ctx));

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) combine_scatter_kernel(const uint4* __res
 // Order inside each read group: (gene, pos) ascending, so that the library's output is
 // deterministic without a host-side sort.  Short groups (the norm) are sorted by one thread in
 // registers; longer ones are queued for segment_rank_sort_kernel.
-constexpr int kShortSegment = 16;
+constexpr int kShortSegment = 8;
 
 __device__ __forceinline__ bool match_less(const uint4& a, const uint4& b) {
   return a.y != b.y ? a.y < b.y : a.z < b.z;
@@ -79,20 +79,23 @@ __global__ void __launch_bounds__(256) segment_sort_short_kernel(uint4* __restri
 // the sorted segment is copied back.  Groups of up to kRankSmem members are ranked out of shared
 // memory (broadcast reads); larger ones fall back to global memory.
 constexpr int kRankThreads = 256;
-constexpr int kRankSmem = 4096;
+constexpr int kRankSmem = 2048;
 
 __global__ void __launch_bounds__(kRankThreads) segment_rank_sort_kernel(
     uint4* __restrict__ m, uint4* __restrict__ scratch, const uint32_t* __restrict__ rstart,
     const uint32_t* __restrict__ long_list, const unsigned long long* __restrict__ n_long) {
   __shared__ uint64_t keys[kRankSmem];
+  __shared__ uint2 rest[kRankSmem];
   const uint64_t nl = *n_long;
   for (uint64_t s = blockIdx.x; s < nl; s += gridDim.x) {
     const uint32_t r = long_list[s];
     const uint32_t lo = rstart[r], hi = rstart[r + 1], n = hi - lo;
     if (n <= (uint32_t)kRankSmem) {
+      // the whole group is staged in shared memory and written back in rank order: no scratch pass
       for (uint32_t i = threadIdx.x; i < n; i += kRankThreads) {
         const uint4 a = m[lo + i];
         keys[i] = ((uint64_t)a.y << 32) | (uint64_t)a.z;
+        rest[i] = make_uint2(a.x, a.w);
       }
       __syncthreads();
       for (uint32_t i = threadIdx.x; i < n; i += kRankThreads) {
@@ -100,8 +103,9 @@ __global__ void __launch_bounds__(kRankThreads) segment_rank_sort_kernel(
         uint32_t rank = 0;
 #pragma unroll 8
         for (uint32_t j = 0; j < n; j++) rank += keys[j] < k ? 1u : 0u;
-        scratch[lo + rank] = m[lo + i];
+        m[lo + rank] = make_uint4(rest[i].x, (uint32_t)(k >> 32), (uint32_t)k, rest[i].y);
       }
+      __syncthreads();
     } else {
       for (uint32_t i = lo + threadIdx.x; i < hi; i += kRankThreads) {
         const uint4 a = m[i];
@@ -109,10 +113,10 @@ __global__ void __launch_bounds__(kRankThreads) segment_rank_sort_kernel(
         for (uint32_t j = lo; j < hi; j++) rank += match_less(m[j], a) ? 1u : 0u;
         scratch[lo + rank] = a;
       }
+      __syncthreads();
+      for (uint32_t i = lo + threadIdx.x; i < hi; i += kRankThreads) m[i] = scratch[i];
+      __syncthreads();
     }
-    __syncthreads();
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += kRankThreads) m[i] = scratch[i];
-    __syncthreads();
   }
 }
 
@@ -138,9 +142,10 @@ __global__ void __launch_bounds__(256) overflow_count_kernel(const uint32_t* __r
                                                              unsigned long long max_matches,
                                                              const unsigned long long* __restrict__ n_pass,
                                                              unsigned long long* __restrict__ n_over) {
-  if (*n_pass <= max_matches) return;  // no group can exceed MaxMatches
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t over = (i < n_slots && (unsigned long long)pass_cnt[i] > max_matches) ? 1u : 0u;
+  if (*n_pass <= max_matches) return;  // no group can exceed MaxMatches (the usual case: nothing to read)
+  uint32_t over = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t)gridDim.x * blockDim.x)
+    over += (unsigned long long)pass_cnt[i] > max_matches ? 1u : 0u;
   over = __reduce_add_sync(0xffffffffu, over);
   if ((threadIdx.x & 31u) == 0 && over) atomicAdd(n_over, (unsigned long long)over);
 }

@@ -22,12 +22,15 @@ __device__ __forceinline__ void pack4(uint32_t v, uint32_t& bits, uint32_t& xbit
   const uint32_t sel = (t & 0xffu) | ((t >> 8) & 0xff00u);
   const uint32_t expect = __byte_perm(0x47544341u, 0u, sel);  // bytes: 0:'A' 1:'C' 2:'T' 3:'G'
   const uint32_t diff = v ^ expect;
-  const uint32_t nz = ((diff | ((diff & 0x7f7f7f7fu) + 0x7f7f7f7fu)) >> 7) & 0x01010101u;  // 1 per invalid byte
-  c &= ~(nz * 3u);
+  xbits = 0u;
+  if (diff) {  // some byte is not A/C/G/T (rare): clear its code, set its X bit
+    const uint32_t nz = ((diff | ((diff & 0x7f7f7f7fu) + 0x7f7f7f7fu)) >> 7) & 0x01010101u;  // 1 per invalid byte
+    c &= ~(nz * 3u);
+    t = nz | (nz >> 6);
+    xbits = (t | (t >> 12)) & 0xffu;
+  }
   t = c | (c >> 6);
   bits = (t | (t >> 12)) & 0xffu;
-  t = nz | (nz >> 6);
-  xbits = (t | (t >> 12)) & 0xffu;
 }
 
 // 16 ASCII bases held in a uint4 -> 32 packed bits (+ 32 X-plane bits).

@@ -7,8 +7,8 @@
 
 namespace msc {
 
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 16;
+constexpr int kScanThreads = 512;
+constexpr int kScanItems = 4;  // one 16-byte load per thread and round
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 __device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_t* total, uint64_t* warp_sums) {
@@ -66,102 +66,84 @@ __device__ __forceinline__ uint64_t scan_count(const unsigned long long* n_ptr, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Single-launch exclusive scan (decoupled look-back).  Tiles are handed out by an atomic ticket,
-// so a tile only ever waits on tiles held by blocks that are already running.  Each tile
-// publishes one 64-bit descriptor {status:2 | epoch:14 | value:48}: first its aggregate, then
-// its inclusive prefix; warp 0 of the block walks back over the predecessors 32 at a time.  The
-// epoch makes descriptors of earlier scans invisible, so the descriptor array is never cleared
-// between scans; the ticket / completion counters reset themselves when the last block leaves.
+// Single-launch exclusive scan on a grid that is resident as a whole (one block per SM).  Block b
+// owns a contiguous slice: it sums the slice, publishes the sum, waits at a grid-wide barrier
+// (a counter that only ever grows: launch k waits for k * gridDim.x arrivals, so it never has to
+// be reset), derives its offset from the sums of the blocks before it and scans the slice.  The
+// input is read twice with coalesced 16-byte loads; for the array sizes of this pipeline
+// (10^6..10^8 counters) that beats a decoupled look-back chain, whose per-tile hand-over latency
+// dominates below ~10^7 elements.
 // ---------------------------------------------------------------------------------------------
-constexpr uint64_t kDescValueMask = (1ull << 48) - 1ull;
-constexpr uint32_t kScanEpochs = 1u << 14;
-constexpr uint64_t kDescAggregate = 1ull, kDescInclusive = 2ull;
-
-__device__ __forceinline__ uint64_t desc_pack(uint64_t status, uint32_t epoch, uint64_t value) {
-  return (status << 62) | ((uint64_t)epoch << 48) | (value & kDescValueMask);
-}
-
 template <typename OutT>
-__global__ void __launch_bounds__(kScanThreads) scan_onepass_kernel(const uint32_t* __restrict__ in,
-                                                                    const unsigned long long* n_ptr, uint64_t n_host,
-                                                                    OutT* __restrict__ out, int write_end,
-                                                                    unsigned long long* __restrict__ total_out,
-                                                                    uint64_t* desc, unsigned long long* state,
-                                                                    uint32_t epoch) {
+__global__ void __launch_bounds__(kScanThreads) scan_resident_kernel(const uint32_t* __restrict__ in,
+                                                                     const unsigned long long* n_ptr, uint64_t n_host,
+                                                                     OutT* __restrict__ out, int write_end,
+                                                                     unsigned long long* __restrict__ total_out,
+                                                                     uint64_t* block_sums, unsigned long long* barrier,
+                                                                     unsigned long long barrier_target) {
   __shared__ uint64_t warp_sums[kScanThreads / 32];
-  __shared__ uint64_t s_total, s_tile, s_excl;
-  const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  __shared__ uint64_t s_total, s_off;
   const uint64_t n = scan_count(n_ptr, n_host);
-  const uint64_t ntiles = (n + kScanTile - 1) / kScanTile;
-  if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
-    if (write_end) out[0] = (OutT)0;
-    *total_out = 0ull;
+  const uint64_t G = gridDim.x, b = blockIdx.x;
+  const uint64_t per = (((n + G - 1) / G) + 3) & ~3ull;  // slice length, multiple of 4
+  const uint64_t lo = min(n, b * per), hi = min(n, lo + per);
+
+  // phase 1: slice sum
+  uint64_t s = 0;
+  for (uint64_t i = lo + (uint64_t)threadIdx.x * 4; i < hi; i += kScanTile) {
+    if (i + 4 <= hi) {
+      const uint4 v = *reinterpret_cast<const uint4*>(in + i);
+      s += (uint64_t)v.x + v.y + v.z + v.w;
+    } else {
+      for (uint64_t j = i; j < hi; j++) s += in[j];
+    }
   }
-  while (true) {
-    if (threadIdx.x == 0) s_tile = atomicAdd(&state[0], 1ull);
-    __syncthreads();
-    const uint64_t tile = s_tile;
-    if (tile >= ntiles) break;
-    const uint64_t base = tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
-    uint32_t v[kScanItems];
-    uint64_t s = 0;
-#pragma unroll
-    for (int i = 0; i < kScanItems; i++) {
-      v[i] = base + i < n ? in[base + i] : 0u;
-      s += v[i];
-    }
-    const uint64_t in_block = block_exclusive_scan_u64(s, &s_total, warp_sums);
-    if (wid == 0) {
-      const uint64_t agg = s_total;
-      uint64_t excl = 0;
-      if (tile > 0) {
-        if (lane == 0) *reinterpret_cast<volatile uint64_t*>(desc + tile) = desc_pack(kDescAggregate, epoch, agg);
-        int64_t back = (int64_t)tile - 1;
-        while (true) {
-          const int64_t p = back - (int64_t)lane;
-          uint64_t status = kDescInclusive, val = 0;
-          if (p >= 0) {
-            uint64_t d;
-            do {
-              d = *reinterpret_cast<volatile uint64_t*>(desc + p);
-            } while (((d >> 48) & (kScanEpochs - 1)) != epoch || (d >> 62) == 0);
-            status = d >> 62;
-            val = d & kDescValueMask;
-          }
-          const unsigned incl = __ballot_sync(0xffffffffu, status == kDescInclusive);
-          const int first = incl ? __ffs(incl) - 1 : 31;
-          uint64_t c = (int)lane <= first ? val : 0ull;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-          excl += c;
-          if (incl) break;
-          back -= 32;
-        }
-      }
-      if (lane == 0) {
-        *reinterpret_cast<volatile uint64_t*>(desc + tile) = desc_pack(kDescInclusive, epoch, excl + agg);
-        s_excl = excl;
-        if (tile + 1 == ntiles) {
-          *total_out = excl + agg;
-          if (write_end) out[n] = (OutT)(excl + agg);
-        }
-      }
-    }
-    __syncthreads();
-    uint64_t run = s_excl + in_block;
-#pragma unroll
-    for (int i = 0; i < kScanItems; i++) {
-      if (base + i < n) out[base + i] = (OutT)run;
-      run += v[i];
-    }
-    __syncthreads();
-  }
+  (void)block_exclusive_scan_u64(s, &s_total, warp_sums);
   if (threadIdx.x == 0) {
+    *reinterpret_cast<volatile uint64_t*>(block_sums + b) = s_total;
     __threadfence();
-    if (atomicAdd(&state[1], 1ull) == (unsigned long long)gridDim.x - 1ull) {
-      state[0] = 0ull;  // every block has stopped taking tickets: ready for the next scan
-      state[1] = 0ull;
+    atomicAdd(barrier, 1ull);
+    while (*reinterpret_cast<volatile unsigned long long*>(barrier) < barrier_target) {}
+    __threadfence();
+  }
+  __syncthreads();
+
+  // phase 2: offset of this slice = sum of the earlier slices (gridDim.x <= kScanThreads)
+  {
+    const uint64_t v = threadIdx.x < G ? __ldcg(block_sums + threadIdx.x) : 0ull;
+    const uint64_t ex = block_exclusive_scan_u64(v, &s_total, warp_sums);
+    if (threadIdx.x == b) s_off = ex;
+    __syncthreads();
+    if (b == 0 && threadIdx.x == 0) {
+      *total_out = s_total;
+      if (write_end) out[n] = (OutT)s_total;
     }
+  }
+  uint64_t run0 = s_off;
+  const uint64_t grand = s_total;
+  (void)grand;
+  __syncthreads();
+
+  // phase 3: scan of the slice
+  for (uint64_t base = lo; base < hi; base += kScanTile) {
+    const uint64_t i = base + (uint64_t)threadIdx.x * 4;
+    uint32_t v[4] = {0u, 0u, 0u, 0u};
+    if (i + 4 <= hi) {
+      const uint4 q = *reinterpret_cast<const uint4*>(in + i);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+      for (int j = 0; j < 4; j++)
+        if (i + j < hi) v[j] = in[i + j];
+    }
+    const uint64_t t = (uint64_t)v[0] + v[1] + v[2] + v[3];
+    uint64_t run = run0 + block_exclusive_scan_u64(t, &s_total, warp_sums);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (i + j < hi) out[i + j] = (OutT)run;
+      run += v[j];
+    }
+    run0 += s_total;
+    __syncthreads();  // s_total / warp_sums are reused by the next round
   }
 }
 
