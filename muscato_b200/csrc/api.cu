@@ -102,13 +102,13 @@ struct msc_ctx {
   int lg_slots = 0, lg_bloom = 0;
   BloomGeom geom{};
   uint64_t n_keys = 0, n_groups = 0, n_dup = 0;
-  DevBuf tab_fp, tab_item0, tab_cnt, tab_start, tab_fill, pass_cnt, bloom, items, dup_slot, fps;
+  DevBuf tab_fp, tab_item0, tab_cnt, tab_start, tab_fill, pass_cnt, bloom, items, dup_slot;
   // zero-fills already issued by a merged prologue launch (consumed by the stage that owns them)
   struct { bool reads = false, targets = false, scan = false, pairs = false, combine = false; } pro;
   // targets
   uint64_t n_targets = 0, n_bases = 0, n_words_alloc = 0, n_tiles = 0;
   bool have_targets = false;
-  DevBuf tg_ascii, tg_off, tg_words, tg_x, xsum;
+  DevBuf tg_ascii, tg_off, tg_words, tg_x, xsum, blk2gene;
   // candidates / pairs
   uint64_t n_cand = 0, n_pairs = 0;
   bool have_cand = false;
@@ -339,22 +339,23 @@ int enqueue_build_reads(msc_ctx* ctx) {
 
   const uint64_t n_items = U * (uint64_t)ctx->win.nwin;
   if (U) {
-    window_keys_kernel<<<grid_for(U, 256), 256, 0, ctx->stream>>>(
-        ctx->win, ctx->rd_words.as<uint64_t>(), ctx->rd_x.as<uint64_t>(), ctx->len_flags.as<uint32_t>(), U,
-        ctx->validmask.as<uint32_t>(), ctx->fps.as<uint64_t>(), ctx->ctr(C_NKEYS),
-        ctx->bloom.as<unsigned long long>(), ctx->geom, ctx->nmiss.as<int32_t>(), ctx->rmeta.as<uint2>());
-    LAUNCH_CHECK();
-  }
-  if (U) {
     BuildArgs a{};
-    a.n_items = n_items;
-    a.fps = ctx->fps.as<uint64_t>();
+    a.rd_words = ctx->rd_words.as<uint64_t>();
+    a.rd_x = ctx->rd_x.as<uint64_t>();
+    a.len_flags = ctx->len_flags.as<uint32_t>();
+    a.n_reads = U;
+    a.nmiss = ctx->nmiss.as<int32_t>();
+    a.validmask = ctx->validmask.as<uint32_t>();
+    a.rmeta = ctx->rmeta.as<uint2>();
+    a.n_keys = ctx->ctr(C_NKEYS);
     a.tab_fp = ctx->tab_fp.as<uint64_t>();
     a.tab_item0 = ctx->tab_item0.as<uint32_t>();
     a.tab_cnt = ctx->tab_cnt.as<uint32_t>();
     a.lg_slots = ctx->lg_slots;
     a.dup_slot = ctx->dup_slot.as<uint32_t>();
-    build_insert_kernel<<<grid_for(n_items, 256), 256, 0, ctx->stream>>>(a);
+    a.bloom = ctx->bloom.as<unsigned long long>();
+    a.geom = ctx->geom;
+    build_keys_insert_kernel<<<grid_for(U, 256), 256, 0, ctx->stream>>>(ctx->win, a);
     LAUNCH_CHECK();
   }
   if (U) {
@@ -480,8 +481,8 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   cand_prepare_kernel<<<pgrid, 256, 0, ctx->stream>>>(ctx->cand.as<uint2>(), ctx->ctr(C_NCAND), ccap,
                                                       ctx->tab_cnt.as<uint32_t>(), ctx->tab_item0.as<uint32_t>(),
                                                       ctx->tab_start.as<uint32_t>(), ctx->tg_off.as<uint32_t>(),
-                                                      ctx->n_targets, ctx->win.W, ctx->cinfo.as<uint4>(),
-                                                      ctx->sizes.as<uint32_t>());
+                                                      ctx->blk2gene.as<uint32_t>(), ctx->win.W,
+                                                      ctx->cinfo.as<uint4>(), ctx->sizes.as<uint32_t>());
   LAUNCH_CHECK();
   RC(enqueue_exclusive_scan<uint64_t>(ctx, ctx->sizes.as<uint32_t>(), ctx->ctr(C_NCAND), ccap, ctx->pstart.as<uint64_t>(),
                                       true, ctx->ctr(C_NPAIRS)));
@@ -523,7 +524,6 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   a.mode = mode;
   if (mode == 2) {
     a.slot_over = ctx->pair_mode2.slot_over;
-    a.fps = ctx->fps.as<uint64_t>();
     a.tab_fp = ctx->tab_fp.as<uint64_t>();
     a.lg_slots = ctx->lg_slots;
     a.over = ctx->pair_mode2.over;
@@ -825,8 +825,8 @@ void msc_destroy(msc_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->rd_ascii,    &ctx->rd_offs,   &ctx->rd_words, &ctx->rd_x,      &ctx->len_flags, &ctx->validmask, &ctx->rmeta,
                     &ctx->tab_fp,      &ctx->tab_item0, &ctx->tab_cnt,  &ctx->tab_start, &ctx->tab_fill,  &ctx->pass_cnt, &ctx->bloom,
-                    &ctx->items,       &ctx->dup_slot,  &ctx->fps,      &ctx->tg_ascii,  &ctx->tg_off,    &ctx->tg_words,
-                    &ctx->tg_x,        &ctx->xsum,      &ctx->cand,     &ctx->cinfo,     &ctx->sizes,     &ctx->pstart,
+                    &ctx->items,       &ctx->dup_slot,  &ctx->tg_ascii,  &ctx->tg_off,    &ctx->tg_words,
+                    &ctx->tg_x,        &ctx->xsum,      &ctx->blk2gene,  &ctx->cand,     &ctx->cinfo,     &ctx->sizes,     &ctx->pstart,
                     &ctx->block_first, &ctx->match_pre, &ctx->best,     &ctx->rcount,    &ctx->rstart,    &ctx->rfill,
                     &ctx->match_out,   &ctx->long_list, &ctx->counters,  &ctx->tile_sums, &ctx->scan_state, &ctx->nmiss};
   for (DevBuf* b : bufs) b->release();
@@ -895,7 +895,6 @@ static int reads_reserve(msc_ctx* ctx, uint64_t n_reads, uint64_t total) {
   CK(ctx->bloom.reserve((1ull << ctx->lg_bloom) * sizeof(uint64_t)));
   CK(ctx->items.reserve((n_reads * nwin + 1) * sizeof(uint32_t)));
   CK(ctx->dup_slot.reserve((n_reads * nwin + 1) * sizeof(uint32_t)));
-  CK(ctx->fps.reserve((n_reads * nwin + 1) * sizeof(uint64_t)));
   CK(ctx->best.reserve((n_reads + 1) * sizeof(uint32_t)));
   // rd_words / rd_x rows are read one word past their end by extract32: keep the pad defined.
   CK(cudaMemsetAsync(ctx->rd_words.as<uint64_t>() + n_reads * S, 0, 2 * sizeof(uint64_t), ctx->stream));
@@ -1008,11 +1007,24 @@ int msc_set_targets(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, ui
   CK(ctx->tg_words.reserve(ctx->n_words_alloc * sizeof(uint64_t)));
   CK(ctx->tg_x.reserve(ctx->n_words_alloc * sizeof(uint64_t)));
   CK(ctx->xsum.reserve((ctx->n_words_alloc / 32 + 4) * sizeof(uint32_t)));
+  // position -> target index at 2^kGeneBlockShift-base granularity (cand_prepare_kernel)
+  const uint64_t n_blk = (total >> kGeneBlockShift) + 2;
+  std::vector<uint32_t> blk(n_blk, n_targets ? (uint32_t)(n_targets - 1) : 0u);
+  {
+    uint64_t g = 0;
+    for (uint64_t b = 0; b < n_blk && n_targets; b++) {
+      const uint64_t pos = b << kGeneBlockShift;
+      while (g + 1 < n_targets && off32[g + 1] <= pos) g++;
+      blk[b] = (uint32_t)g;
+    }
+  }
+  CK(ctx->blk2gene.reserve(n_blk * sizeof(uint32_t)));
   RC(begin_upload(ctx, ctx->ev_tg_free));
+  CK(cudaMemcpyAsync(ctx->blk2gene.p, blk.data(), n_blk * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream));
   if (total) CK(cudaMemcpyAsync(ctx->tg_ascii.p, ascii, total, cudaMemcpyHostToDevice, ctx->copy_stream));
   CK(cudaMemcpyAsync(ctx->tg_off.p, off32.data(), (n_targets + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream));
   RC(end_upload(ctx));
-  ctx->st.h2d_bytes += total + (n_targets + 1) * sizeof(uint32_t);
+  ctx->st.h2d_bytes += total + (n_targets + 1) * sizeof(uint32_t) + n_blk * sizeof(uint32_t);
   ctx->have_targets = true;
   RC(enqueue_pack_targets(ctx));
   RC(wait_upload(ctx));  // off32 is a local; the caller's buffers are only borrowed

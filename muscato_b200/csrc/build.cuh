@@ -38,60 +38,104 @@ __device__ __forceinline__ int dinuc_count(uint64_t key, uint64_t xm, int W) {
 }
 
 struct BuildArgs {
-  uint64_t n_items;      // n_reads * nwin
-  const uint64_t* fps;   // per item: key fingerprint, 0 = window not valid for the read
+  // reads
+  const uint64_t* rd_words;
+  const uint64_t* rd_x;
+  const uint32_t* len_flags;
+  uint64_t n_reads;
+  const int32_t* nmiss;  // [MRL + 1], host-computed float64 table (cmd/muscato_confirm/main.go:198)
+  // per read outputs
+  uint32_t* validmask;
+  uint2* rmeta;
+  unsigned long long* n_keys;
+  // key table
   uint64_t* tab_fp;
   uint32_t* tab_item0;   // first (read, window) item of the slot's key group
   uint32_t* tab_cnt;     // number of FURTHER items of the group (they go to the CSR `items`)
   int lg_slots;
   uint32_t* dup_slot;    // per item: 1 + slot if the item is a further member of its group, else 0
+  // Bloom front
+  unsigned long long* bloom;
+  BloomGeom geom;
 };
-// (The number of further members, n_dup, is the grand total of the tab_cnt scan and the number of
-// distinct fingerprints is n_keys - n_dup: no per-warp counter atomics in the insert kernel --
-// ~10^6 same-address atomics cost more than the inserts themselves.)
+// (The number of further members, n_dup, is the grand total of the bump allocation in pass B1 and
+// the number of distinct fingerprints is n_keys - n_dup: no per-warp counter atomics in the insert
+// kernel -- ~10^6 same-address atomics cost more than the inserts themselves.)
 
-// Pass A1: per read, which windows are valid (length rule + entropy rule) and the fingerprint of
-// each valid window key; the key's bits are set in the Bloom front here, where the key itself
-// (needed for the minimiser addressing, common.cuh) is still at hand.  item = read * nwin + window.
-__global__ void __launch_bounds__(256) window_keys_kernel(const WinCfg cfg, const uint64_t* __restrict__ rd_words,
-                                                          const uint64_t* __restrict__ rd_x,
-                                                          const uint32_t* __restrict__ len_flags, uint64_t n_reads,
-                                                          uint32_t* __restrict__ validmask, uint64_t* __restrict__ fps,
-                                                          unsigned long long* __restrict__ n_keys,
-                                                          unsigned long long* __restrict__ bloom, const BloomGeom geom,
-                                                          const int32_t* __restrict__ nmiss, uint2* __restrict__ rmeta) {
+constexpr int kInsertBatch = 2;  // table claims in flight per thread
+
+// Pass A: one thread per read.  Which windows are valid (length rule + entropy rule), the
+// fingerprint of each valid window key, its Bloom bits, and the claim of its table slot: the
+// first item of a key group lives in the slot itself (most groups have exactly one member);
+// further members are flagged in dup_slot and scattered into the slot's CSR range by pass B.
+// The atomicCAS of up to kInsertBatch windows are issued before any of them is resolved -- the
+// build is bound by the round trip of those atomics, not by their number.
+// item = read * nwin + window.
+__global__ void __launch_bounds__(256, 6) build_keys_insert_kernel(const WinCfg cfg, const BuildArgs a) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t nk = 0;
-  if (r < n_reads) {
-    const uint32_t lf = len_flags[r];
+  if (r < a.n_reads) {
+    const uint32_t lf = a.len_flags[r];
     const int L = (int)(lf & 0x7fffffffu);
     const bool hasx = lf >> 31;
-    const uint64_t* row = rd_words + r * (uint64_t)cfg.S;
-    const uint64_t* xrow = rd_x + r * (uint64_t)cfg.S;
+    const uint64_t* row = a.rd_words + r * (uint64_t)cfg.S;
+    const uint64_t* xrow = a.rd_x + r * (uint64_t)cfg.S;
     const uint64_t kmask = low_bases_mask(cfg.W);
+    const uint64_t smask = (1ull << a.lg_slots) - 1ull;
     uint32_t vm = 0;
-    for (int k = 0; k < cfg.nwin; k++) {
-      const int q1 = cfg.windows[k], q2 = q1 + cfg.W;
-      uint64_t fp = 0;
-      if (L >= q2) {  // cmd/muscato_window_reads/main.go:109-112, cmd/muscato_screen/main.go:177-179
-        const uint64_t key = extract32(row, (uint64_t)q1) & kmask;
-        const uint64_t xm = hasx ? (extract32(xrow, (uint64_t)q1) & kmask) : 0ull;
-        if (cfg.min_dinuc <= 0 || dinuc_count(key, xm, cfg.W) >= cfg.min_dinuc) {  // :183-185 / :116-118
-          fp = key_fp(key, xm);
-          vm |= 1u << k;
-          nk++;
-          uint64_t widx;
-          uint32_t mlo, mhi;
-          bloom_locate(key, xm, fp, cfg.W, geom, widx, mlo, mhi);
-          atomicOr(bloom + widx, (unsigned long long)mlo | ((unsigned long long)mhi << 32));
+    for (int k0 = 0; k0 < cfg.nwin; k0 += kInsertBatch) {
+      uint64_t fp[kInsertBatch], sl[kInsertBatch];
+      unsigned long long cur[kInsertBatch];
+#pragma unroll
+      for (int u = 0; u < kInsertBatch; u++) {
+        const int k = k0 + u;
+        fp[u] = 0;
+        sl[u] = 0;
+        cur[u] = 0;
+        if (k < cfg.nwin) {
+          const int q1 = cfg.windows[k], q2 = q1 + cfg.W;
+          if (L >= q2) {  // cmd/muscato_window_reads/main.go:109-112, cmd/muscato_screen/main.go:177-179
+            const uint64_t key = extract32(row, (uint64_t)q1) & kmask;
+            const uint64_t xm = hasx ? (extract32(xrow, (uint64_t)q1) & kmask) : 0ull;
+            if (cfg.min_dinuc <= 0 || dinuc_count(key, xm, cfg.W) >= cfg.min_dinuc) {  // :183-185 / :116-118
+              fp[u] = key_fp(key, xm);
+              vm |= 1u << k;
+              nk++;
+              uint64_t widx;
+              uint32_t mlo, mhi;
+              bloom_locate(key, xm, fp[u], cfg.W, a.geom, widx, mlo, mhi);
+              atomicOr(a.bloom + widx, (unsigned long long)mlo | ((unsigned long long)mhi << 32));
+              sl[u] = table_home(fp[u], a.lg_slots);
+              cur[u] = atomicCAS(reinterpret_cast<unsigned long long*>(a.tab_fp + sl[u]), 0ull, (unsigned long long)fp[u]);
+            }
+          }
         }
       }
-      fps[r * (uint64_t)cfg.nwin + (uint64_t)k] = fp;
+#pragma unroll
+      for (int u = 0; u < kInsertBatch; u++) {
+        const int k = k0 + u;
+        if (k >= cfg.nwin) break;
+        const uint64_t item = r * (uint64_t)cfg.nwin + (uint64_t)k;
+        uint32_t dup = 0;
+        if (fp[u]) {
+          while (cur[u] != 0ull && cur[u] != fp[u]) {  // linear probing
+            sl[u] = (sl[u] + 1) & smask;
+            cur[u] = atomicCAS(reinterpret_cast<unsigned long long*>(a.tab_fp + sl[u]), 0ull, (unsigned long long)fp[u]);
+          }
+          if (cur[u] == 0ull) {
+            a.tab_item0[sl[u]] = (uint32_t)item;
+          } else {
+            atomicAdd(a.tab_cnt + sl[u], 1u);
+            dup = (uint32_t)sl[u] + 1u;
+          }
+        }
+        a.dup_slot[item] = dup;
+      }
     }
-    validmask[r] = vm;
+    a.validmask[r] = vm;
     // what the confirm kernel needs of a read in one 8-byte load: length (11 bits), mismatch
-    // budget nmiss(L) (11 bits, host-computed float64 table), has-X flag, valid-window mask
-    rmeta[r] = make_uint2((uint32_t)L | ((uint32_t)__ldg(nmiss + L) << 11) | (lf & 0x80000000u), vm);
+    // budget nmiss(L) (11 bits), has-X flag, valid-window mask
+    a.rmeta[r] = make_uint2((uint32_t)L | ((uint32_t)__ldg(a.nmiss + L) << 11) | (lf & 0x80000000u), vm);
   }
   // one counter atomic per block (same-address atomics serialise)
   __shared__ uint32_t s_nk[8];
@@ -101,37 +145,7 @@ __global__ void __launch_bounds__(256) window_keys_kernel(const WinCfg cfg, cons
   if (threadIdx.x == 0) {
     uint32_t t = 0;
     for (int w = 0; w < 8; w++) t += s_nk[w];
-    if (t) atomicAdd(n_keys, (unsigned long long)t);
-  }
-}
-
-// Pass A2: one thread per item.  Claim / find the table slot of the fingerprint.  The first item of a key group lives in the slot itself (most groups have exactly
-// one member); further members are flagged in dup_slot and scattered into the slot's CSR range
-// by pass B.
-__global__ void __launch_bounds__(256) build_insert_kernel(const BuildArgs a) {
-  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < a.n_items) {
-    const uint64_t fp = __ldg(a.fps + idx);
-    uint32_t dup = 0;
-    if (fp) {
-      const uint64_t smask = (1ull << a.lg_slots) - 1ull;
-      uint64_t s = table_home(fp, a.lg_slots);
-      bool first = false;
-      while (true) {
-        const unsigned long long cur =
-            atomicCAS(reinterpret_cast<unsigned long long*>(a.tab_fp + s), 0ull, (unsigned long long)fp);
-        if (cur == 0ull) { first = true; break; }
-        if (cur == fp) break;
-        s = (s + 1) & smask;
-      }
-      if (first) {
-        a.tab_item0[s] = (uint32_t)idx;
-      } else {
-        atomicAdd(a.tab_cnt + s, 1u);
-        dup = (uint32_t)s + 1u;
-      }
-    }
-    a.dup_slot[idx] = dup;
+    if (t) atomicAdd(a.n_keys, (unsigned long long)t);
   }
 }
 

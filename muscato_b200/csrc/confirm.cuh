@@ -22,7 +22,9 @@ namespace msc {
 constexpr int kPairBlockShift = 5;
 constexpr int kPairBlock = 1 << kPairBlockShift;
 
-// Per candidate: locate its gene once (binary search in the target offsets) and store what every
+constexpr int kGeneBlockShift = 10;  // granularity of the position -> target index (msc_set_targets)
+
+// Per candidate: locate its gene once (block index + short binary search in the target offsets) and store what every
 // pair of the candidate needs in ONE 32-byte sector (two uint4): (table slot, global position of
 // the window, window start p inside the gene, global end of the gene) and (first item of the key
 // group, CSR start of the further items, gene index, -).  sizes[] = number of (read, window)
@@ -33,13 +35,16 @@ __global__ void __launch_bounds__(256) cand_prepare_kernel(const uint2* __restri
                                                            uint64_t cand_cap, const uint32_t* __restrict__ tab_cnt,
                                                            const uint32_t* __restrict__ tab_item0,
                                                            const uint32_t* __restrict__ tab_start,
-                                                           const uint32_t* __restrict__ tg_off, uint64_t n_targets,
-                                                           int W, uint4* __restrict__ cinfo,
-                                                           uint32_t* __restrict__ sizes) {
+                                                           const uint32_t* __restrict__ tg_off,
+                                                           const uint32_t* __restrict__ blk2gene, int W,
+                                                           uint4* __restrict__ cinfo, uint32_t* __restrict__ sizes) {
   const uint64_t n_cand = min((uint64_t)*n_cand_ptr, cand_cap);
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint2 cd = cand[i];
-    const uint64_t g = upper_bound_dev<uint32_t>(tg_off, 0, n_targets + 1, cd.y) - 1;
+    // blk2gene[b] = target that holds base b << kGeneBlockShift: the search spans the few targets
+    // that start inside the candidate's block instead of the whole offset table
+    const uint64_t g_lo = __ldg(blk2gene + (cd.y >> kGeneBlockShift)), g_hi = __ldg(blk2gene + (cd.y >> kGeneBlockShift) + 1);
+    const uint64_t g = upper_bound_dev<uint32_t>(tg_off, g_lo + 1, g_hi + 1, cd.y) - 1;
     const uint32_t goff = __ldg(tg_off + g);
     const uint32_t gend = __ldg(tg_off + g + 1);
     const uint32_t further = __ldg(tab_cnt + cd.x);
@@ -104,7 +109,6 @@ struct ConfirmArgs {
   // order-dependent truncation (cmd/muscato_confirm/main.go:233-242, :424-448); the
   // cross-window de-duplication only counts windows whose group is not flagged.
   const uint8_t* slot_over;
-  const uint64_t* fps;     // per (read, window) key fingerprint (0 = window not valid)
   const uint64_t* tab_fp;
   int lg_slots;
   uint4* over;
@@ -274,7 +278,7 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
     }
     if (MODE == 2) {
       // a window whose key group is subject to truncation does not "own" the pair
-      const int64_t s2 = table_find(a.tab_fp, a.lg_slots, __ldg(a.fps + (uint64_t)r * cfg.nwin + k2));
+      const int64_t s2 = table_find(a.tab_fp, a.lg_slots, key_fp(rk, rx ? (extract32(xrow, (uint64_t)q1b) & kmask) : 0ull));
       if (s2 >= 0 && a.slot_over[s2]) continue;
     }
     return false;  // an earlier window owns this pair
