@@ -376,11 +376,11 @@ def run_ours(args, rank, local_rank, world):
     alg_bytes = shard_bases / 4.0 + 16.0 * n_cand   # T/4 + 16*H (Bloom front is L2-resident)
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
     # DRAM traffic of the scan kernel per launch from the committed `ncu --set full` capture of this
-    # exact workload (profiles/ncu_full_r01_final_cold.txt: dram__bytes_read.sum 45.27 MB +
-    # dram__bytes_write.sum 1.20 MB, cold caches as ncu flushes them; 8.0 MB with warm caches,
-    # profiles/ncu_full_r01_v4_warm.txt).
+    # exact workload (profiles/ncu_full_r01_v8_cold.txt: dram__bytes_read.sum 45.76 MB +
+    # dram__bytes_write.sum 0.95 MB, cold caches as ncu flushes them; 9.3 MB with warm caches,
+    # profiles/ncu_full_r01_v8_warm.txt).
     default_workload = (world == 1 and args.reads == WORK["num_read"] and args.genes == WORK["num_gene"])
-    scan_traffic = 46.5e6 if default_workload else None
+    scan_traffic = 46.7e6 if default_workload else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
         "ms_per_step": 1000.0 * t_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -397,7 +397,7 @@ def run_ours(args, rank, local_rank, world):
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_ms,
                      "positions_per_s": shard_bases / (scan_ms * 1e-3),
                      "note": "Bloom front + key table are L2-resident at this size, so SURVEY 8(d) counts T/4 + 16*H only; "
-                             "the kernel is bound by one scattered 8-byte probe per target position, not by the stream"},
+                             "the kernel is bound by the per-position probe arithmetic (ALU pipe) and its L1/L2 sector traffic, not by the stream"},
         "pairs_confirmed_per_s": st["n_pairs"] * world / max(1e-9, st["ms_confirm"] / K * 1e-3),
         "stage_ms_per_step": {k: st[k] / K for k in ("ms_pack_reads", "ms_build", "ms_pack_targets", "ms_scan",
                                                       "ms_expand", "ms_confirm", "ms_combine")},

@@ -544,7 +544,7 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
     // MaxMatches pre-check (cmd/muscato_confirm/main.go:233-242, :424-448): truncation can only
     // happen in a key group with more than MaxMatches passing pairs.
     const uint64_t slots = 1ull << ctx->lg_slots;
-    overflow_count_kernel<<<(unsigned)ctx->sm_count * 4, 256, 0, ctx->stream>>>(
+    overflow_count_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, ctx->stream>>>(
         ctx->pass_cnt.as<uint32_t>(), slots, (unsigned long long)ctx->cfg.max_matches, ctx->ctr(C_NPASS),
         ctx->ctr(C_NOVER));
     LAUNCH_CHECK();

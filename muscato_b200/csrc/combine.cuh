@@ -74,10 +74,10 @@ __global__ void __launch_bounds__(256) segment_sort_short_kernel(uint4* __restri
     if (i < (int)n) m[lo + i] = v[i];
 }
 
-// One block per long read group: every element counts the elements that precede it (keys are
-// unique inside a group after de-duplication) and is written at that rank into `scratch`, then
-// the sorted segment is copied back.  Groups of up to kRankSmem members are ranked out of shared
-// memory (broadcast reads); larger ones fall back to global memory.
+// One block per long read group.  Groups of up to kRankSmem members are sorted in shared memory
+// (bitonic network); larger ones fall back to a rank sort in global memory: every element counts
+// the elements that precede it (keys are unique inside a group after de-duplication) and is
+// written at that rank into `scratch`, then the sorted segment is copied back.
 constexpr int kRankThreads = 256;
 constexpr int kRankSmem = 2048;
 
@@ -91,20 +91,39 @@ __global__ void __launch_bounds__(kRankThreads) segment_rank_sort_kernel(
     const uint32_t r = long_list[s];
     const uint32_t lo = rstart[r], hi = rstart[r + 1], n = hi - lo;
     if (n <= (uint32_t)kRankSmem) {
-      // the whole group is staged in shared memory and written back in rank order: no scratch pass
-      for (uint32_t i = threadIdx.x; i < n; i += kRankThreads) {
-        const uint4 a = m[lo + i];
-        keys[i] = ((uint64_t)a.y << 32) | (uint64_t)a.z;
-        rest[i] = make_uint2(a.x, a.w);
+      // bitonic sort of (gene, pos) keys in shared memory (padded to a power of two with +inf keys)
+      uint32_t np2 = 2;
+      while (np2 < n) np2 <<= 1;
+      for (uint32_t i = threadIdx.x; i < np2; i += kRankThreads) {
+        if (i < n) {
+          const uint4 a = m[lo + i];
+          keys[i] = ((uint64_t)a.y << 32) | (uint64_t)a.z;
+          rest[i] = make_uint2(a.x, a.w);
+        } else {
+          keys[i] = ~0ull;
+          rest[i] = make_uint2(0u, 0u);
+        }
       }
       __syncthreads();
-      for (uint32_t i = threadIdx.x; i < n; i += kRankThreads) {
-        const uint64_t k = keys[i];
-        uint32_t rank = 0;
-#pragma unroll 8
-        for (uint32_t j = 0; j < n; j++) rank += keys[j] < k ? 1u : 0u;
-        m[lo + rank] = make_uint4(rest[i].x, (uint32_t)(k >> 32), (uint32_t)k, rest[i].y);
+      for (uint32_t k = 2; k <= np2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          for (uint32_t t = threadIdx.x; t < np2 / 2; t += kRankThreads) {
+            const uint32_t i = ((t / j) * 2u * j) + (t % j);
+            const bool up = (i & k) == 0;
+            const uint64_t x = keys[i], y = keys[i + j];
+            if ((x > y) == up) {
+              keys[i] = y;
+              keys[i + j] = x;
+              const uint2 r0 = rest[i];
+              rest[i] = rest[i + j];
+              rest[i + j] = r0;
+            }
+          }
+          __syncthreads();
+        }
       }
+      for (uint32_t i = threadIdx.x; i < n; i += kRankThreads)
+        m[lo + i] = make_uint4(rest[i].x, (uint32_t)(keys[i] >> 32), (uint32_t)keys[i], rest[i].y);
       __syncthreads();
     } else {
       for (uint32_t i = lo + threadIdx.x; i < hi; i += kRankThreads) {
@@ -143,9 +162,12 @@ __global__ void __launch_bounds__(256) overflow_count_kernel(const uint32_t* __r
                                                              const unsigned long long* __restrict__ n_pass,
                                                              unsigned long long* __restrict__ n_over) {
   if (*n_pass <= max_matches) return;  // no group can exceed MaxMatches (the usual case: nothing to read)
-  uint32_t over = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t)gridDim.x * blockDim.x)
-    over += (unsigned long long)pass_cnt[i] > max_matches ? 1u : 0u;
+  uint32_t over = 0;  // n_slots is a power of two >= 1024: 16-byte loads
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots / 4; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(pass_cnt) + i);
+    over += ((unsigned long long)v.x > max_matches) + ((unsigned long long)v.y > max_matches) +
+            ((unsigned long long)v.z > max_matches) + ((unsigned long long)v.w > max_matches);
+  }
   over = __reduce_add_sync(0xffffffffu, over);
   if ((threadIdx.x & 31u) == 0 && over) atomicAdd(n_over, (unsigned long long)over);
 }
