@@ -106,6 +106,30 @@ int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint
 int msc_set_reads_device(msc_ctx* ctx, const uint8_t* d_ascii, const uint64_t* d_offs, uint64_t n_reads,
                          uint64_t total_bytes);
 
+/* Device-side prepReads: replaces, for the sequence column,
+ * `muscato_prep_reads | sort | muscato_uniqify` (cmd/muscato/main.go:152-221).  raw read i is
+ * raw_ascii[raw_offs[i] .. raw_offs[i+1]) as it stands in the fastq file (any bytes, any length).
+ * On the device: bytes outside A/C/G/T become X and reads are cut to MaxReadLength
+ * (cmd/muscato_prep_reads/main.go:33-44, :67-69), reads shorter than min_read_length are skipped
+ * (:59-62), the sequences are sorted bytewise (a proper prefix sorts first, as `LC_ALL=C sort` does
+ * with the '\t' that follows the sequence) and equal sequences are collapsed
+ * (cmd/muscato_uniqify/main.go:113-135).  The unique reads are installed as the context's read
+ * set exactly as msc_set_reads would (pack + key table).  n_kept = reads that passed the length
+ * filter, n_unique = distinct sequences. */
+int msc_prep_reads(msc_ctx* ctx, const uint8_t* raw_ascii, const uint64_t* raw_offs, uint64_t n_raw,
+                   int32_t min_read_length, uint64_t* n_kept, uint64_t* n_unique);
+
+/* Grouping left by msc_prep_reads: perm[0..n_kept) = raw read indices in sorted order,
+ * group_start[u]..group_start[u+1] = the members of unique read u (n_unique + 1 entries): count =
+ * group size, names = the members' names (the host joins them in bytewise name order, which is
+ * what sorting the `seq\tname` lines gives).  Buffers are caller-owned. */
+int msc_fetch_read_groups(msc_ctx* ctx, uint32_t* perm, uint32_t* group_start);
+
+/* The unique reads themselves (X-substituted, truncated), reads_sorted order: ascii needs
+ * msc_unique_reads_bytes() bytes, offs n_unique + 1 entries. */
+uint64_t msc_unique_reads_bytes(msc_ctx* ctx);
+int msc_fetch_unique_reads(msc_ctx* ctx, uint8_t* ascii, uint64_t* offs);
+
 /* Targets in GeneFileName order (gene id = index, cmd/muscato_screen/main.go:440-452):
  * target g is ascii[offs[g] .. offs[g+1]).  Total length < 2^32 - 4096 bases per call
  * (shard larger databases by target range).  Uploads and 2-bit packs on the device. */

@@ -75,6 +75,11 @@ _SIGS = [
     ("msc_last_error", C.c_char_p, [C.c_void_p]),
     ("msc_set_reads", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     ("msc_set_reads_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    ("msc_prep_reads", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32,
+                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("msc_fetch_read_groups", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("msc_unique_reads_bytes", C.c_uint64, [C.c_void_p]),
+    ("msc_fetch_unique_reads", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("msc_set_targets", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     ("msc_rebuild", C.c_int, [C.c_void_p, C.c_int]),
     ("msc_screen", C.c_int, [C.c_void_p]),

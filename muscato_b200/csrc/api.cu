@@ -25,6 +25,7 @@
 #include "confirm.cuh"
 #include "pack.cuh"
 #include "prefix.cuh"
+#include "readprep.cuh"
 #include "scan.cuh"
 
 using namespace msc;
@@ -63,7 +64,8 @@ struct DevBuf {
 enum Counter {
   C_NKEYS = 0, C_NGROUPS, C_NDUP, C_SCRATCH, C_NCAND, C_BLOOMPASS, C_NMATCH, C_NPASS, C_NOVER, C_NOUT, C_NPAIRS,
   C_PAD0, C_NLONG, C_PAD1, C_TGX,  // C_NLONG, C_TGX at even indices; C_TGX = "some target word has X"
-  C_COUNT = 16  // groups that are cleared together start at even indices (16-byte aligned)
+  C_PAD2, C_PREP_KEPT, C_PREP_UNIQ, C_PREP_BYTES, C_PAD3,  // C_PREP_KEPT at an even index (16)
+  C_COUNT = 24  // groups that are cleared together start at even indices (16-byte aligned)
 };
 
 // Stage boundary events.
@@ -123,6 +125,10 @@ struct msc_ctx {
     uint4* over = nullptr;
     uint64_t over_cap = 0;
   } pair_mode2;
+  // device-side read prep (msc_prep_reads): sorted permutation of the raw reads and group starts
+  uint64_t prep_kept = 0, prep_unique = 0, prep_bytes = 0;
+  bool have_prep = false;
+  DevBuf prep_perm, prep_gstart;
   // misc
   DevBuf counters, tile_sums, scan_state, nmiss;
   unsigned long long scan_arrivals = 0;  // arrivals the scan kernel's grid barrier has seen so far (never reset)
@@ -826,7 +832,7 @@ void msc_destroy(msc_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->rd_ascii,    &ctx->rd_offs,   &ctx->rd_words, &ctx->rd_x,      &ctx->len_flags, &ctx->validmask, &ctx->rmeta,
                     &ctx->tab_fp,      &ctx->tab_item0, &ctx->tab_cnt,  &ctx->tab_start, &ctx->tab_fill,  &ctx->pass_cnt, &ctx->bloom,
                     &ctx->items,       &ctx->dup_slot,  &ctx->tg_ascii,  &ctx->tg_off,    &ctx->tg_words,
-                    &ctx->tg_x,        &ctx->xsum,      &ctx->blk2gene,  &ctx->cand,     &ctx->cinfo,     &ctx->sizes,     &ctx->pstart,
+                    &ctx->tg_x,        &ctx->xsum,      &ctx->blk2gene,  &ctx->prep_perm, &ctx->prep_gstart, &ctx->cand,     &ctx->cinfo,     &ctx->sizes,     &ctx->pstart,
                     &ctx->block_first, &ctx->match_pre, &ctx->best,     &ctx->rcount,    &ctx->rstart,    &ctx->rfill,
                     &ctx->match_out,   &ctx->long_list, &ctx->counters,  &ctx->tile_sums, &ctx->scan_state, &ctx->nmiss};
   for (DevBuf* b : bufs) b->release();
@@ -916,6 +922,7 @@ int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint
   }
   RC(reads_reserve(ctx, n_reads, total));
   ctx->have_reads = false;
+  ctx->have_prep = false;
   RC(begin_upload(ctx, ctx->ev_rd_free));
   if (total) CK(cudaMemcpyAsync(ctx->rd_ascii.p, ascii, total, cudaMemcpyHostToDevice, ctx->copy_stream));
   if (n_reads) CK(cudaMemcpyAsync(ctx->rd_offs.p, offs, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -978,6 +985,159 @@ int msc_set_reads_device(msc_ctx* ctx, const uint8_t* d_ascii, const uint64_t* d
   RC(enqueue_build_reads(ctx));
   RC(sync_counters(ctx));  // d_ascii / d_offs are only borrowed for the call
   if (!ctx->cfg.keep_ascii) ctx->rd_ascii.release();
+  return MSC_OK;
+}
+
+int msc_prep_reads(msc_ctx* ctx, const uint8_t* raw_ascii, const uint64_t* raw_offs, uint64_t n_raw,
+                   int32_t min_read_length, uint64_t* n_kept_out, uint64_t* n_unique_out) {
+  if (!ctx) return MSC_ERR_STATE;
+  if (n_raw && (!raw_offs || (!raw_ascii && raw_offs[n_raw] != raw_offs[0]))) return ctx->fail(MSC_ERR_INPUT, "raw reads: NULL buffer");
+  if (n_raw >= 0xffffffffull) return ctx->fail(MSC_ERR_INPUT, "raw reads: more than 2^32-1 reads in one call");
+  CK(cudaSetDevice(ctx->device));
+  uint64_t total = 0;
+  if (n_raw) {
+    if (raw_offs[0] != 0) return ctx->fail(MSC_ERR_INPUT, "raw reads: offs[0] must be 0");
+    uint64_t bad = 0;
+    for (uint64_t i = 0; i < n_raw; i++) bad |= (uint64_t)(raw_offs[i + 1] < raw_offs[i]);
+    if (bad) return ctx->fail(MSC_ERR_INPUT, "raw reads: offsets not monotone");
+    total = raw_offs[n_raw];
+  }
+  ctx->have_prep = false;
+  ctx->have_reads = false;
+  const int MRL = ctx->win.MRL;
+  const int n_planes = (MRL + 1) / 2;
+  const uint64_t n = n_raw;
+  const uint32_t n_chunks = (uint32_t)std::max<uint64_t>(1, (n + kRadixChunk - 1) / kRadixChunk);
+  DevBuf d_raw, d_offs, planes, idx_a, idx_b, keep, hist, hoff, head, head_scan, ulen, uoffs;
+  auto release_all = [&]() {
+    DevBuf* t[] = {&d_raw, &d_offs, &planes, &idx_a, &idx_b, &keep, &hist, &hoff, &head, &head_scan, &ulen, &uoffs};
+    for (DevBuf* b : t) b->release();
+  };
+#define PCK(call)                                                                                          \
+  do {                                                                                                     \
+    cudaError_t e__ = (call);                                                                              \
+    if (e__ != cudaSuccess) {                                                                              \
+      release_all();                                                                                       \
+      return ctx->fail(MSC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    }                                                                                                      \
+  } while (0)
+#define PRC(call)           \
+  do {                      \
+    int rc__ = (call);      \
+    if (rc__) {             \
+      release_all();        \
+      return rc__;          \
+    }                       \
+  } while (0)
+  PCK(d_raw.reserve(total + 64));
+  PCK(d_offs.reserve((n + 1) * sizeof(uint64_t)));
+  PCK(planes.reserve((size_t)n_planes * std::max<uint64_t>(n, 1)));
+  PCK(idx_a.reserve((n + 1) * sizeof(uint32_t)));
+  PCK(idx_b.reserve((n + 1) * sizeof(uint32_t)));
+  PCK(keep.reserve((n + 1) * sizeof(uint32_t)));
+  PCK(hist.reserve((size_t)256 * n_chunks * sizeof(uint32_t)));
+  PCK(hoff.reserve(((size_t)256 * n_chunks + 1) * sizeof(uint32_t)));
+  PCK(head.reserve((n + 1) * sizeof(uint32_t)));
+  PCK(head_scan.reserve((n + 2) * sizeof(uint32_t)));
+  PCK(ulen.reserve((n + 1) * sizeof(uint32_t)));
+  PCK(uoffs.reserve((n + 2) * sizeof(uint64_t)));
+  PCK(ctx->prep_perm.reserve((n + 1) * sizeof(uint32_t)));
+  PCK(ctx->prep_gstart.reserve((n + 2) * sizeof(uint32_t)));
+  if (total) PCK(cudaMemcpyAsync(d_raw.p, raw_ascii, total, cudaMemcpyHostToDevice, ctx->stream));
+  if (n) PCK(cudaMemcpyAsync(d_offs.p, raw_offs, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->st.h2d_bytes += total + (n + 1) * sizeof(uint64_t);
+  {
+    Filler f;
+    f.add(ctx->ctr(C_PREP_KEPT), 4 * sizeof(unsigned long long));  // C_PREP_KEPT, C_PREP_UNIQ, C_PREP_BYTES, C_PAD3
+    PRC(enqueue_fill(ctx, f));
+  }
+  uint32_t* cur = idx_a.as<uint32_t>();
+  uint32_t* nxt = idx_b.as<uint32_t>();
+  if (n) {
+    prep_encode_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(d_raw.as<uint8_t>(), d_offs.as<uint64_t>(), n, MRL,
+                                                                  (int)min_read_length, n_planes, planes.as<uint8_t>(),
+                                                                  keep.as<uint32_t>(), ctx->ctr(C_PREP_KEPT));
+    LAUNCH_CHECK();
+    iota_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(cur, n);
+    LAUNCH_CHECK();
+    // stable LSD radix sort of the read indices, one byte plane (two symbols) per pass
+    for (int b = n_planes - 1; b >= 0; b--) {
+      const uint8_t* plane = planes.as<uint8_t>() + (size_t)b * n;
+      radix_hist_kernel<<<n_chunks, kRadixThreads, 0, ctx->stream>>>(cur, plane, n, n_chunks, hist.as<uint32_t>());
+      LAUNCH_CHECK();
+      PRC(enqueue_exclusive_scan<uint32_t>(ctx, hist.as<uint32_t>(), nullptr, (uint64_t)256 * n_chunks, hoff.as<uint32_t>(),
+                                           false, ctx->ctr(C_PAD3)));
+      radix_scatter_kernel<<<n_chunks, kRadixThreads, 0, ctx->stream>>>(cur, plane, n, n_chunks, hoff.as<uint32_t>(), nxt);
+      LAUNCH_CHECK();
+      std::swap(cur, nxt);
+    }
+    prep_heads_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(cur, planes.as<uint8_t>(), n, ctx->ctr(C_PREP_KEPT), n_planes,
+                                                                 head.as<uint32_t>());
+    LAUNCH_CHECK();
+    PRC(enqueue_exclusive_scan<uint32_t>(ctx, head.as<uint32_t>(), ctx->ctr(C_PREP_KEPT), n, head_scan.as<uint32_t>(), true,
+                                         ctx->ctr(C_PREP_UNIQ)));
+    prep_groups_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(cur, head.as<uint32_t>(), head_scan.as<uint32_t>(),
+                                                                  ctx->ctr(C_PREP_KEPT), d_offs.as<uint64_t>(), MRL,
+                                                                  ctx->ctr(C_PREP_UNIQ), ctx->prep_gstart.as<uint32_t>(),
+                                                                  ulen.as<uint32_t>());
+    LAUNCH_CHECK();
+    PRC(enqueue_exclusive_scan<uint64_t>(ctx, ulen.as<uint32_t>(), ctx->ctr(C_PREP_UNIQ), n, uoffs.as<uint64_t>(), true,
+                                         ctx->ctr(C_PREP_BYTES)));
+    PCK(cudaMemcpyAsync(ctx->prep_perm.p, cur, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  PRC(sync_counters(ctx));
+  ctx->prep_kept = n ? ctx->h_counters[C_PREP_KEPT] : 0;
+  ctx->prep_unique = n ? ctx->h_counters[C_PREP_UNIQ] : 0;
+  ctx->prep_bytes = n ? ctx->h_counters[C_PREP_BYTES] : 0;
+  const uint64_t U = ctx->prep_unique;
+  if (!n || !ctx->prep_kept) PCK(cudaMemsetAsync(ctx->prep_gstart.p, 0, 2 * sizeof(uint32_t), ctx->stream));
+  PRC(reads_reserve(ctx, U, ctx->prep_bytes));
+  if (U) {
+    prep_gather_kernel<<<grid_for(U * 32, 256), 256, 0, ctx->stream>>>(d_raw.as<uint8_t>(), d_offs.as<uint64_t>(), ctx->prep_perm.as<uint32_t>(),
+                                                                     ctx->prep_gstart.as<uint32_t>(), uoffs.as<uint64_t>(),
+                                                                     ctx->ctr(C_PREP_UNIQ), ctx->rd_ascii.as<uint8_t>());
+    LAUNCH_CHECK();
+    PCK(cudaMemcpyAsync(ctx->rd_offs.p, uoffs.p, (U + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    PCK(cudaMemsetAsync(ctx->rd_offs.p, 0, sizeof(uint64_t), ctx->stream));
+  }
+  ctx->have_reads = true;
+  ctx->have_prep = true;
+  PRC(enqueue_build_reads(ctx));
+  PRC(sync_counters(ctx));  // the temporaries are released below
+  release_all();
+#undef PCK
+#undef PRC
+  if (n_kept_out) *n_kept_out = ctx->prep_kept;
+  if (n_unique_out) *n_unique_out = U;
+  return MSC_OK;
+}
+
+int msc_fetch_read_groups(msc_ctx* ctx, uint32_t* perm, uint32_t* group_start) {
+  if (!ctx) return MSC_ERR_STATE;
+  if (!ctx->have_prep) return ctx->fail(MSC_ERR_STATE, "msc_fetch_read_groups: run msc_prep_reads first");
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->prep_kept && !perm) return ctx->fail(MSC_ERR_INPUT, "msc_fetch_read_groups: NULL perm");
+  if (!group_start) return ctx->fail(MSC_ERR_INPUT, "msc_fetch_read_groups: NULL group_start");
+  if (ctx->prep_kept) CK(cudaMemcpyAsync(perm, ctx->prep_perm.p, ctx->prep_kept * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(group_start, ctx->prep_gstart.p, (ctx->prep_unique + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->st.d2h_bytes += ctx->prep_kept * sizeof(uint32_t) + (ctx->prep_unique + 1) * sizeof(uint32_t);
+  return MSC_OK;
+}
+
+uint64_t msc_unique_reads_bytes(msc_ctx* ctx) { return (ctx && ctx->have_prep) ? ctx->prep_bytes : 0; }
+
+int msc_fetch_unique_reads(msc_ctx* ctx, uint8_t* ascii, uint64_t* offs) {
+  if (!ctx) return MSC_ERR_STATE;
+  if (!ctx->have_prep) return ctx->fail(MSC_ERR_STATE, "msc_fetch_unique_reads: run msc_prep_reads first");
+  if (!ctx->cfg.keep_ascii) return ctx->fail(MSC_ERR_STATE, "msc_fetch_unique_reads needs keep_ascii=1");
+  if (!offs || (ctx->prep_bytes && !ascii)) return ctx->fail(MSC_ERR_INPUT, "msc_fetch_unique_reads: NULL buffer");
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->prep_bytes) CK(cudaMemcpyAsync(ascii, ctx->rd_ascii.p, ctx->prep_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(offs, ctx->rd_offs.p, (ctx->prep_unique + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->st.d2h_bytes += ctx->prep_bytes + (ctx->prep_unique + 1) * sizeof(uint64_t);
   return MSC_OK;
 }
 

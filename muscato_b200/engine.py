@@ -88,6 +88,35 @@ class HotPath:
         self.n_reads = len(o) - 1
         self._check(self._lib.msc_set_reads(self._ctx, a.ctypes.data, o.ctypes.data, self.n_reads))
 
+    def prep_reads(self, raw_seqs: SeqInput, min_read_length: int = 0):
+        """Device-side prepReads (prep_reads | sort | uniqify of the sequence column,
+        cmd/muscato/main.go:152-221): sorts and collapses the raw fastq sequences on the GPU and
+        installs the unique reads as the read set.  Returns (n_kept, n_unique)."""
+        a, o = self._as_arrays(raw_seqs)
+        kept, uniq = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._lib.msc_prep_reads(self._ctx, a.ctypes.data, o.ctypes.data, len(o) - 1, int(min_read_length),
+                                             C.byref(kept), C.byref(uniq)))
+        self.n_reads = int(uniq.value)
+        self._n_kept = int(kept.value)
+        return self._n_kept, self.n_reads
+
+    def read_groups(self):
+        """(perm, group_start) of the last prep_reads: perm = raw read indices in sorted order,
+        unique read u = perm[group_start[u]:group_start[u + 1]]."""
+        perm = np.empty(max(1, self._n_kept), dtype=np.uint32)
+        gs = np.empty(self.n_reads + 1, dtype=np.uint32)
+        self._check(self._lib.msc_fetch_read_groups(self._ctx, perm.ctypes.data, gs.ctypes.data))
+        return perm[: self._n_kept], gs
+
+    def unique_reads(self):
+        """The unique reads of the last prep_reads as a list of bytes (needs keep_ascii)."""
+        nb = int(self._lib.msc_unique_reads_bytes(self._ctx))
+        a = np.empty(max(1, nb), dtype=np.uint8)
+        o = np.empty(self.n_reads + 1, dtype=np.uint64)
+        self._check(self._lib.msc_fetch_unique_reads(self._ctx, a.ctypes.data, o.ctypes.data))
+        buf = a.tobytes()
+        return [buf[int(o[i]):int(o[i + 1])] for i in range(self.n_reads)]
+
     def set_targets(self, seqs: SeqInput):
         a, o = self._as_arrays(seqs)
         self.n_targets = len(o) - 1

@@ -167,3 +167,42 @@ def prep_reads_uniqify(fastq: bytes, min_len: int, max_len: int):
     if cur is not None:
         flush()
     return seqs, counts, names
+
+
+def parse_fastq(fastq: bytes):
+    """(names, sequences) of a fastq file as the reference reads it: 4-line records, the header and
+    sequence lines right-trimmed of '\\r' (utils/fastq.go:40-70; cmd/muscato_prep_reads/main.go:46-58)."""
+    lines = fastq.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    names, seqs = [], []
+    for i in range(0, len(lines) - len(lines) % 4, 4):
+        names.append(lines[i].rstrip(b"\r"))
+        seqs.append(lines[i + 1].rstrip(b"\r"))
+    return names, seqs
+
+
+def uniqify_from_groups(raw_names: Sequence[bytes], raw_seqs: Sequence[bytes], perm, group_start, max_len: int):
+    """Host half of the device-side prepReads (msc_prep_reads): the device returns the sorted
+    permutation of the raw reads and the group boundaries; counts and names are joined here.
+    Inside a group the `seq\\tname` lines are in bytewise name order (cmd/muscato/main.go:183-199),
+    the name column is the text before its first tab (cmd/muscato_uniqify/main.go:100-110) and the
+    joined names are cut to 996 bytes + "..." (:89-93).  Returns (seqs, counts, names)."""
+    seqs, counts, names = [], [], []
+    for u in range(len(group_start) - 1):
+        members = [int(perm[j]) for j in range(int(group_start[u]), int(group_start[u + 1]))]
+        nm = []
+        for r in members:
+            n = raw_names[r]
+            if len(n) > 1000:
+                n = n[:995] + b"..."
+            nm.append(n)
+        nm.sort()
+        na = b";".join(n.split(b"\t")[0] for n in nm)
+        if len(na) > 1000:
+            na = na[:996] + b"..."
+        s = raw_seqs[members[0]][:max_len]
+        seqs.append(bytes(c if c in b"ATCG" else 0x58 for c in s))
+        counts.append(b"%d" % len(members))
+        names.append(na)
+    return seqs, counts, names

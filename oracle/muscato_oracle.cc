@@ -1034,6 +1034,8 @@ int main(int argc, char** argv) {
     nonmatch(c);
   } else if (cmd == "upstream") {
     upstream(c);
+  } else if (cmd == "prep_reads") {  // prepReads alone: TempDir/reads_sorted.txt
+    prep_reads(c);
   } else if (cmd == "windows") {  // windowReads + sortWindows on an existing TempDir/reads_sorted.txt
     window_reads(c);
     sort_windows(c);
