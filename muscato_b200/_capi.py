@@ -63,6 +63,7 @@ class msc_stats(C.Structure):
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved_f"}
         d["bloom_pass"] = float(self.reserved_f[0])
+        d["ms_prep"] = float(self.reserved_f[1])  # device time of msc_prep_reads (sort + collapse), H2D excluded
         return d
 
 

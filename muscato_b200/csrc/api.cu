@@ -129,6 +129,14 @@ struct msc_ctx {
   uint64_t prep_kept = 0, prep_unique = 0, prep_bytes = 0;
   bool have_prep = false;
   DevBuf prep_perm, prep_gstart;
+  struct PrepTmp {  // scratch of msc_prep_reads, kept between calls
+    DevBuf d_raw, d_offs, planes, idx_a, idx_b, keep, hist, hoff, head, head_scan, ulen, uoffs;
+    void release_all() {
+      DevBuf* t[] = {&d_raw, &d_offs, &planes, &idx_a, &idx_b, &keep, &hist, &hoff, &head, &head_scan, &ulen, &uoffs};
+      for (DevBuf* b : t) b->release();
+    }
+  } prep;
+  cudaEvent_t ev_prep0 = nullptr, ev_prep1 = nullptr;
   // misc
   DevBuf counters, tile_sums, scan_state, nmiss;
   unsigned long long scan_arrivals = 0;  // arrivals the scan kernel's grid barrier has seen so far (never reset)
@@ -836,6 +844,9 @@ void msc_destroy(msc_ctx* ctx) {
                     &ctx->block_first, &ctx->match_pre, &ctx->best,     &ctx->rcount,    &ctx->rstart,    &ctx->rfill,
                     &ctx->match_out,   &ctx->long_list, &ctx->counters,  &ctx->tile_sums, &ctx->scan_state, &ctx->nmiss};
   for (DevBuf* b : bufs) b->release();
+  ctx->prep.release_all();
+  if (ctx->ev_prep0) cudaEventDestroy(ctx->ev_prep0);
+  if (ctx->ev_prep1) cudaEventDestroy(ctx->ev_prep1);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
@@ -1008,11 +1019,14 @@ int msc_prep_reads(msc_ctx* ctx, const uint8_t* raw_ascii, const uint64_t* raw_o
   const int n_planes = (MRL + 1) / 2;
   const uint64_t n = n_raw;
   const uint32_t n_chunks = (uint32_t)std::max<uint64_t>(1, (n + kRadixChunk - 1) / kRadixChunk);
-  DevBuf d_raw, d_offs, planes, idx_a, idx_b, keep, hist, hoff, head, head_scan, ulen, uoffs;
-  auto release_all = [&]() {
-    DevBuf* t[] = {&d_raw, &d_offs, &planes, &idx_a, &idx_b, &keep, &hist, &hoff, &head, &head_scan, &ulen, &uoffs};
-    for (DevBuf* b : t) b->release();
-  };
+  DevBuf &d_raw = ctx->prep.d_raw, &d_offs = ctx->prep.d_offs, &planes = ctx->prep.planes, &idx_a = ctx->prep.idx_a,
+         &idx_b = ctx->prep.idx_b, &keep = ctx->prep.keep, &hist = ctx->prep.hist, &hoff = ctx->prep.hoff,
+         &head = ctx->prep.head, &head_scan = ctx->prep.head_scan, &ulen = ctx->prep.ulen, &uoffs = ctx->prep.uoffs;
+  auto release_all = [&]() {};  // the scratch stays with the context (msc_destroy releases it)
+  if (!ctx->ev_prep0) {
+    CK(cudaEventCreate(&ctx->ev_prep0));
+    CK(cudaEventCreate(&ctx->ev_prep1));
+  }
 #define PCK(call)                                                                                          \
   do {                                                                                                     \
     cudaError_t e__ = (call);                                                                              \
@@ -1046,6 +1060,7 @@ int msc_prep_reads(msc_ctx* ctx, const uint8_t* raw_ascii, const uint64_t* raw_o
   if (total) PCK(cudaMemcpyAsync(d_raw.p, raw_ascii, total, cudaMemcpyHostToDevice, ctx->stream));
   if (n) PCK(cudaMemcpyAsync(d_offs.p, raw_offs, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   ctx->st.h2d_bytes += total + (n + 1) * sizeof(uint64_t);
+  PCK(cudaEventRecord(ctx->ev_prep0, ctx->stream));
   {
     Filler f;
     f.add(ctx->ctr(C_PREP_KEPT), 4 * sizeof(unsigned long long));  // C_PREP_KEPT, C_PREP_UNIQ, C_PREP_BYTES, C_PAD3
@@ -1101,11 +1116,16 @@ int msc_prep_reads(msc_ctx* ctx, const uint8_t* raw_ascii, const uint64_t* raw_o
   } else {
     PCK(cudaMemsetAsync(ctx->rd_offs.p, 0, sizeof(uint64_t), ctx->stream));
   }
+  PCK(cudaEventRecord(ctx->ev_prep1, ctx->stream));
   ctx->have_reads = true;
   ctx->have_prep = true;
   PRC(enqueue_build_reads(ctx));
-  PRC(sync_counters(ctx));  // the temporaries are released below
-  release_all();
+  PRC(sync_counters(ctx));  // the caller's buffers are only borrowed for the call
+  {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev_prep0, ctx->ev_prep1) == cudaSuccess) ctx->st.reserved_f[1] += ms;  // "ms_prep"
+    else (void)cudaGetLastError();
+  }
 #undef PCK
 #undef PRC
   if (n_kept_out) *n_kept_out = ctx->prep_kept;
