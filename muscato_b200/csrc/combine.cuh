@@ -87,9 +87,29 @@ __global__ void __launch_bounds__(kRankThreads) segment_rank_sort_kernel(
   __shared__ uint64_t keys[kRankSmem];
   __shared__ uint2 rest[kRankSmem];
   const uint64_t nl = *n_long;
+  // pass 1: groups of up to 32 members, one WARP per group: every lane holds one member and
+  // counts the members that precede it with 32 shuffles (no shared memory, no block barrier)
+  {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t gw = ((uint64_t)blockIdx.x * kRankThreads + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * kRankThreads) >> 5;
+    for (uint64_t s = gw; s < nl; s += nw) {
+      const uint32_t r = long_list[s];
+      const uint32_t lo = rstart[r], n = rstart[r + 1] - lo;
+      if (n > 32u) continue;
+      uint4 a = make_uint4(0u, 0u, 0u, 0u);
+      if (lane < n) a = m[lo + lane];
+      const uint64_t k = lane < n ? (((uint64_t)a.y << 32) | (uint64_t)a.z) : ~0ull;
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < n; j++) rank += __shfl_sync(0xffffffffu, k, j) < k ? 1u : 0u;
+      __syncwarp();
+      if (lane < n) m[lo + rank] = a;
+    }
+  }
+  // pass 2: larger groups, one block per group
   for (uint64_t s = blockIdx.x; s < nl; s += gridDim.x) {
     const uint32_t r = long_list[s];
     const uint32_t lo = rstart[r], hi = rstart[r + 1], n = hi - lo;
+    if (n <= 32u) continue;  // block-uniform
     if (n <= (uint32_t)kRankSmem) {
       // bitonic sort of (gene, pos) keys in shared memory (padded to a power of two with +inf keys)
       uint32_t np2 = 2;

@@ -26,11 +26,11 @@ __device__ __forceinline__ void pack4(uint32_t v, uint32_t& bits, uint32_t& xbit
   if (diff) {  // some byte is not A/C/G/T (rare): clear its code, set its X bit
     const uint32_t nz = ((diff | ((diff & 0x7f7f7f7fu) + 0x7f7f7f7fu)) >> 7) & 0x01010101u;  // 1 per invalid byte
     c &= ~(nz * 3u);
-    t = nz | (nz >> 6);
-    xbits = (t | (t >> 12)) & 0xffu;
+    xbits = (nz * 0x01041040u) >> 24;
   }
-  t = c | (c >> 6);
-  bits = (t | (t >> 12)) & 0xffu;
+  // gather the four 2-bit fields (bits 0, 8, 16, 24) into one byte: the partial products of the
+  // multiplication land on disjoint bit pairs, the wanted ones in the top byte (IMAD: FMA pipe)
+  bits = (c * 0x01041040u) >> 24;
 }
 
 // 16 ASCII bases held in a uint4 -> 32 packed bits (+ 32 X-plane bits).
