@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kRankThreads) segment_rank_sort_kernel(
       for (uint32_t k = 2; k <= np2; k <<= 1) {
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
           for (uint32_t t = threadIdx.x; t < np2 / 2; t += kRankThreads) {
-            const uint32_t i = ((t / j) * 2u * j) + (t % j);
+            const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));  // j is a power of two
             const bool up = (i & k) == 0;
             const uint64_t x = keys[i], y = keys[i + j];
             if ((x > y) == up) {

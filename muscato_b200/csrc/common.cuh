@@ -162,6 +162,11 @@ __device__ __forceinline__ int64_t table_find(const uint64_t* __restrict__ tab_f
   }
 }
 
+// One 256-bit read-only global load (sm_100: LDG.E.256) of a 32-byte aligned record.
+__device__ __forceinline__ void ldg256(const void* p, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d) {
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+
 // ---------------------------------------------------------------------------
 // PTX wrappers: mbarrier + 1-D bulk async copy (TMA engine; SASS: UBLKCP / SYNCS).
 // ---------------------------------------------------------------------------

@@ -148,8 +148,14 @@ template <int MODE>
 __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const ConfirmArgs& a, uint64_t i, uint64_t c,
                                                  uint64_t c_start, bool targets_have_x, uint4& rec,
                                                  uint32_t& n_pass) {
-  const uint4 ci = __ldg(a.cinfo + 2 * c);
-  const uint4 cj = __ldg(a.cinfo + 2 * c + 1);  // (first item, CSR start, gene, -)
+  // the candidate's 32-byte record in one 256-bit load: (slot, position, p, gene end | first item, CSR start, gene, -)
+  uint4 ci, cj;
+  {
+    uint64_t q0, q1, q2, q3;
+    ldg256(a.cinfo + 2 * c, q0, q1, q2, q3);
+    ci = make_uint4((uint32_t)q0, (uint32_t)(q0 >> 32), (uint32_t)q1, (uint32_t)(q1 >> 32));
+    cj = make_uint4((uint32_t)q2, (uint32_t)(q2 >> 32), (uint32_t)q3, (uint32_t)(q3 >> 32));
+  }
   const uint32_t slot = ci.x;
   const uint64_t gpos = ci.y;
   const int64_t p = (int64_t)ci.z;
@@ -217,10 +223,32 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
       // Short reads without X (the norm): all loads are issued before the first compare, so the
       // early exit costs no dependent round trips.
       uint64_t rw[4], t[5];
+      if ((cfg.S & 1) == 0) {
+        // 16-byte loads: rows of an even number of words are 16-byte aligned, and the 5 target
+        // words lie inside the 6 words that start at the even word index below them (buffers are
+        // padded): 5 requests per pair instead of 9
+        if ((cfg.S & 3) == 0) {  // 32-byte aligned rows: one 256-bit load
+          ldg256(row, rw[0], rw[1], rw[2], rw[3]);
+        } else {
+          const ulonglong2* r2 = reinterpret_cast<const ulonglong2*>(row);
+          const ulonglong2 ra = __ldg(r2), rb = nwords > 2 ? __ldg(r2 + 1) : make_ulonglong2(0ull, 0ull);
+          rw[0] = ra.x; rw[1] = ra.y; rw[2] = rb.x; rw[3] = rb.y;
+        }
+        const uint64_t wi = gstart >> 5;
+        const ulonglong2* t2 = reinterpret_cast<const ulonglong2*>(a.tg_words + (wi & ~1ull));
+        const ulonglong2 ta = __ldg(t2), tb = __ldg(t2 + 1), tc = __ldg(t2 + 2);
+        const bool odd = wi & 1ull;
+        t[0] = odd ? ta.y : ta.x;
+        t[1] = odd ? tb.x : ta.y;
+        t[2] = odd ? tb.y : tb.x;
+        t[3] = odd ? tc.x : tb.y;
+        t[4] = odd ? tc.y : tc.x;
+      } else {
 #pragma unroll
-      for (int w = 0; w < 4; w++) rw[w] = w < nwords ? __ldg(row + w) : 0ull;
+        for (int w = 0; w < 4; w++) rw[w] = w < nwords ? __ldg(row + w) : 0ull;
 #pragma unroll
-      for (int w = 0; w < 5; w++) t[w] = w <= nwords ? __ldg(tw + w) : 0ull;
+        for (int w = 0; w < 5; w++) t[w] = w <= nwords ? __ldg(tw + w) : 0ull;
+      }
 #pragma unroll
       for (int w = 0; w < 4; w++) {
         if (w < nwords) {
