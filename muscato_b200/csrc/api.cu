@@ -379,7 +379,7 @@ int enqueue_build_reads(msc_ctx* ctx) {
     LAUNCH_CHECK();
     build_fill_kernel<<<grid_for(n_items, 256), 256, 0, ctx->stream>>>(
         ctx->dup_slot.as<uint32_t>(), n_items, ctx->tab_start.as<uint32_t>(), ctx->tab_fill.as<uint32_t>(),
-        ctx->items.as<uint32_t>());
+        ctx->rmeta.as<uint2>(), (uint32_t)ctx->win.nwin, ctx->items.as<uint4>());
     LAUNCH_CHECK();
   }
   CK(cudaEventRecord(ctx->ev[EV_BUILD1], ctx->stream));
@@ -495,7 +495,8 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   cand_prepare_kernel<<<pgrid, 256, 0, ctx->stream>>>(ctx->cand.as<uint2>(), ctx->ctr(C_NCAND), ccap,
                                                       ctx->tab_cnt.as<uint32_t>(), ctx->tab_item0.as<uint32_t>(),
                                                       ctx->tab_start.as<uint32_t>(), ctx->tg_off.as<uint32_t>(),
-                                                      ctx->blk2gene.as<uint32_t>(), ctx->win.W,
+                                                      ctx->blk2gene.as<uint32_t>(), ctx->win.W, ctx->rmeta.as<uint2>(),
+                                                      ctx->win.nwin == 1 ? 0ull : (~0ull / (uint64_t)ctx->win.nwin) + 1ull,
                                                       ctx->cinfo.as<uint4>(), ctx->sizes.as<uint32_t>());
   LAUNCH_CHECK();
   RC(enqueue_exclusive_scan<uint64_t>(ctx, ctx->sizes.as<uint32_t>(), ctx->ctr(C_NCAND), ccap, ctx->pstart.as<uint64_t>(),
@@ -518,11 +519,11 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   a.pstart = ctx->pstart.as<uint64_t>();
   a.n_pairs_ptr = ctx->ctr(C_NPAIRS);
   a.block_cap = ctx->block_cap();
-  a.items = ctx->items.as<uint32_t>();
+  a.items = ctx->items.as<uint4>();
+  a.cand = ctx->cand.as<uint2>();
   a.pass_cnt = ctx->pass_cnt.as<uint32_t>();
   a.rd_words = ctx->rd_words.as<uint64_t>();
   a.rd_x = ctx->rd_x.as<uint64_t>();
-  a.rmeta = ctx->rmeta.as<uint2>();
   a.tg_words = ctx->tg_words.as<uint64_t>();
   a.tg_x = ctx->tg_x.as<uint64_t>();
   a.xsum = ctx->xsum.as<uint32_t>();
@@ -910,7 +911,7 @@ static int reads_reserve(msc_ctx* ctx, uint64_t n_reads, uint64_t total) {
   CK(ctx->tab_fill.reserve(slots * sizeof(uint32_t)));
   CK(ctx->pass_cnt.reserve(slots * sizeof(uint32_t)));
   CK(ctx->bloom.reserve((1ull << ctx->lg_bloom) * sizeof(uint64_t)));
-  CK(ctx->items.reserve((n_reads * nwin + 1) * sizeof(uint32_t)));
+  CK(ctx->items.reserve((n_reads * nwin + 1) * sizeof(uint4)));
   CK(ctx->dup_slot.reserve((n_reads * nwin + 1) * sizeof(uint32_t)));
   CK(ctx->best.reserve((n_reads + 1) * sizeof(uint32_t)));
   // rd_words / rd_x rows are read one word past their end by extract32: keep the pad defined.
@@ -1350,9 +1351,9 @@ int msc_dump_keys(msc_ctx* ctx, msc_key_rec** out, uint64_t* n) {
   for (uint64_t sl = 0; sl < slots; sl++)
     if (fps[sl]) items.push_back(item0[sl]);
   {
-    std::vector<uint32_t> dups(ctx->n_dup);
-    if (ctx->n_dup) CK(cudaMemcpy(dups.data(), ctx->items.p, ctx->n_dup * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    items.insert(items.end(), dups.begin(), dups.end());
+    std::vector<uint4> dups(ctx->n_dup);  // CSR entries: (item, read record)
+    if (ctx->n_dup) CK(cudaMemcpy(dups.data(), ctx->items.p, ctx->n_dup * sizeof(uint4), cudaMemcpyDeviceToHost));
+    for (const uint4& e : dups) items.push_back(e.x);
   }
   if (items.size() != ctx->n_keys)
     return ctx->fail(MSC_ERR_STATE, "key table inconsistent: %llu items for %llu keys", (unsigned long long)items.size(),

@@ -165,22 +165,21 @@ __global__ void __launch_bounds__(256) build_alloc_kernel(const uint32_t* __rest
     tab_start[d - 1] = (uint32_t)atomicAdd(n_dup, (unsigned long long)__ldg(tab_cnt + (d - 1)));
 }
 
-// Pass B2: scatter the further members into their slot's CSR range.
+// Pass B2: scatter the further members into their slot's CSR range.  A CSR entry is 16 bytes:
+// (item, read record) -- the confirm kernel gets the read's length / budget / window mask with
+// the item itself instead of through one more dependent look-up.
 __global__ void __launch_bounds__(256) build_fill_kernel(const uint32_t* __restrict__ dup_slot, uint64_t n_items,
                                                          const uint32_t* __restrict__ tab_start,
                                                          uint32_t* __restrict__ tab_fill,
-                                                         uint32_t* __restrict__ items) {
+                                                         const uint2* __restrict__ rmeta, uint32_t nwin,
+                                                         uint4* __restrict__ items) {
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_items) return;
   const uint32_t d = __ldg(dup_slot + idx);
-  if (d) items[tab_start[d - 1] + (atomicSub(tab_fill + (d - 1), 1u) - 1u)] = (uint32_t)idx;
-}
-
-// Member j of the key group in `slot` (j = 0 is stored in the slot, the rest in the CSR).
-__device__ __forceinline__ uint32_t group_item(const uint32_t* __restrict__ tab_item0,
-                                               const uint32_t* __restrict__ tab_start,
-                                               const uint32_t* __restrict__ items, uint32_t slot, uint32_t j) {
-  return j == 0 ? __ldg(tab_item0 + slot) : __ldg(items + __ldg(tab_start + slot) + (j - 1));
+  if (d) {
+    const uint2 rm = __ldg(rmeta + (uint32_t)idx / nwin);
+    items[tab_start[d - 1] + (atomicSub(tab_fill + (d - 1), 1u) - 1u)] = make_uint4((uint32_t)idx, rm.x, rm.y, 0u);
+  }
 }
 
 }  // namespace msc

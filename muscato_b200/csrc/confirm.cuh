@@ -25,9 +25,10 @@ constexpr int kPairBlock = 1 << kPairBlockShift;
 constexpr int kGeneBlockShift = 10;  // granularity of the position -> target index (msc_set_targets)
 
 // Per candidate: locate its gene once (block index + short binary search in the target offsets) and store what every
-// pair of the candidate needs in ONE 32-byte sector (two uint4): (table slot, global position of
-// the window, window start p inside the gene, global end of the gene) and (first item of the key
-// group, CSR start of the further items, gene index, -).  sizes[] = number of (read, window)
+// pair of the candidate needs in ONE 32-byte sector (two uint4): (global position of the window,
+// window start p inside the gene, global end of the gene, read record .x of the first item) and
+// (first item of the key group, CSR start of the further items, gene index, read record .y of
+// the first item).  The table slot stays in cand[] (only pairs that pass need it).  sizes[] = number of (read, window)
 // items of its key group.  A W-mer that straddles a target boundary is not a window of any target
 // (processSeq only rolls inside one target, cmd/muscato_screen/main.go:319): size 0.
 __global__ void __launch_bounds__(256) cand_prepare_kernel(const uint2* __restrict__ cand,
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256) cand_prepare_kernel(const uint2* __restri
                                                            const uint32_t* __restrict__ tab_start,
                                                            const uint32_t* __restrict__ tg_off,
                                                            const uint32_t* __restrict__ blk2gene, int W,
+                                                           const uint2* __restrict__ rmeta, uint64_t nwin_magic,
                                                            uint4* __restrict__ cinfo, uint32_t* __restrict__ sizes) {
   const uint64_t n_cand = min((uint64_t)*n_cand_ptr, cand_cap);
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -48,8 +50,10 @@ __global__ void __launch_bounds__(256) cand_prepare_kernel(const uint2* __restri
     const uint32_t goff = __ldg(tg_off + g);
     const uint32_t gend = __ldg(tg_off + g + 1);
     const uint32_t further = __ldg(tab_cnt + cd.x);
-    cinfo[2 * i] = make_uint4(cd.x, cd.y, cd.y - goff, gend);
-    cinfo[2 * i + 1] = make_uint4(__ldg(tab_item0 + cd.x), further ? __ldg(tab_start + cd.x) : 0u, (uint32_t)g, 0u);
+    const uint32_t item0 = __ldg(tab_item0 + cd.x);
+    const uint2 rm0 = __ldg(rmeta + (nwin_magic ? (uint32_t)__umul64hi((uint64_t)item0, nwin_magic) : item0));
+    cinfo[2 * i] = make_uint4(cd.y, cd.y - goff, gend, rm0.x);
+    cinfo[2 * i + 1] = make_uint4(item0, further ? __ldg(tab_start + cd.x) : 0u, (uint32_t)g, rm0.y);
     sizes[i] = ((uint64_t)cd.y + (uint64_t)W <= (uint64_t)gend) ? 1u + further : 0u;
   }
 }
@@ -75,17 +79,17 @@ __global__ void __launch_bounds__(256) pair_block_starts_kernel(const uint64_t* 
 struct ConfirmArgs {
   // candidates and their pair prefix
   const uint4* cinfo;          // two per candidate, see cand_prepare_kernel
+  const uint2* cand;           // (slot, position): the slot is only needed by pairs that pass
   const uint32_t* block_first; // first candidate of each kPairBlock-pair block (+1 sentinel entry)
   const uint64_t* pstart;  // n_cand + 1
   const unsigned long long* n_pairs_ptr;  // device-side pair count (grand total of the size scan)
   uint64_t block_cap;                     // capacity of block_first (in kPairBlock-pair blocks)
   // key table
-  const uint32_t* items;
+  const uint4* items;          // CSR of further group members: (item, read record)
   uint32_t* pass_cnt;  // per slot: pairs that passed (MaxMatches pre-check)
   // reads
   const uint64_t* rd_words;
   const uint64_t* rd_x;
-  const uint2* rmeta;  // per read: (L | nmiss(L) << 11 | hasX << 31, valid-window mask), see window_keys_kernel
   // targets
   const uint64_t* tg_words;
   const uint64_t* tg_x;
@@ -148,7 +152,8 @@ template <int MODE>
 __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const ConfirmArgs& a, uint64_t i, uint64_t c,
                                                  uint64_t c_start, bool targets_have_x, uint4& rec,
                                                  uint32_t& n_pass) {
-  // the candidate's 32-byte record in one 256-bit load: (slot, position, p, gene end | first item, CSR start, gene, -)
+  // the candidate's 32-byte record in one 256-bit load:
+  // (position, p, gene end, read record .x of item 0 | item 0, CSR start, gene, read record .y of item 0)
   uint4 ci, cj;
   {
     uint64_t q0, q1, q2, q3;
@@ -156,11 +161,18 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
     ci = make_uint4((uint32_t)q0, (uint32_t)(q0 >> 32), (uint32_t)q1, (uint32_t)(q1 >> 32));
     cj = make_uint4((uint32_t)q2, (uint32_t)(q2 >> 32), (uint32_t)q3, (uint32_t)(q3 >> 32));
   }
-  const uint32_t slot = ci.x;
-  const uint64_t gpos = ci.y;
-  const int64_t p = (int64_t)ci.z;
+  const uint64_t gpos = ci.x;
+  const int64_t p = (int64_t)ci.y;
+  const uint32_t gend = ci.z;
   const uint32_t j = (uint32_t)(i - c_start);
-  const uint32_t item = j == 0 ? cj.x : __ldg(a.items + cj.y + (j - 1));
+  // (item, read record): member 0 comes with the candidate record, further members from the CSR
+  uint32_t item = cj.x;
+  uint2 rm = make_uint2(ci.w, cj.w);
+  if (j) {
+    const uint4 e = __ldg(a.items + cj.y + (j - 1));
+    item = e.x;
+    rm = make_uint2(e.y, e.z);
+  }
   const uint32_t r = cfg.nwin == 1 ? item : (uint32_t)__umul64hi((uint64_t)item, a.nwin_magic);  // item / nwin
   const int k = (int)(item - r * (uint32_t)cfg.nwin);
   const int W = cfg.W;
@@ -168,13 +180,12 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
   const int64_t pos = p - q1;      // jw = jx - q1 >= 0 (cmd/muscato_screen/main.go:345, :355)
   if (pos < 0) return false;
 
-  const uint2 rm = __ldg(a.rmeta + r);
   const int L = (int)(rm.x & 0x7ffu);
   const int budget = (int)((rm.x >> 11) & 0x7ffu);
   const bool rx = rm.x >> 31;
   const uint64_t* row = a.rd_words + (uint64_t)r * cfg.S;
   const uint64_t gstart = gpos - (uint64_t)q1;  // global base index of the read's first base
-  const int64_t glen = (int64_t)ci.w - (int64_t)(gpos - (uint64_t)p);
+  const int64_t glen = (int64_t)gend - (int64_t)(gpos - (uint64_t)p);
   const int64_t lim0 = min((int64_t)(100 - W), glen);  // position-0 record: right = t[W : min(100-q2, len)]
 
   if (MODE != 1) {
@@ -183,7 +194,7 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
     // position-0 record carries right = t[W : min(100 - q2, len)] (the literal 100, Q1).
     if (p == 0) {
       if ((int64_t)L > lim0) return false;
-    } else if (gstart + (uint64_t)L > (uint64_t)ci.w) {
+    } else if (gstart + (uint64_t)L > (uint64_t)gend) {
       return false;
     }
   }
@@ -279,6 +290,7 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
   }
 
   // The pair passes through window k.
+  const uint32_t slot = __ldg(a.cand + c).x;
   atomicAdd(a.pass_cnt + slot, 1u);
   n_pass++;
   if (MODE == 2 && a.slot_over[slot]) {
