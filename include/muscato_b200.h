@@ -177,6 +177,13 @@ int msc_fetch_matches(msc_ctx* ctx, msc_match** out, uint64_t* n);
  * *n receives the number of matches; MSC_ERR_NOMEM if they do not fit. */
 int msc_fetch_matches_into(msc_ctx* ctx, msc_match* dst, uint64_t capacity, uint64_t* n);
 
+/* Reads without any confirmed match, ascending (= reads_sorted order, the order of the non-match
+ * fastq): what muscato_nonmatch (cmd/muscato_nonmatch/main.go:57-113) derives from results.txt with
+ * a Bloom filter, taken exactly from the per-read best array on the device.  Valid after
+ * msc_confirm (with several target shards: after the MIN all-reduce of msc_best_device).
+ * *n receives the count; MSC_ERR_NOMEM if it exceeds `capacity` (ids may be NULL to query *n). */
+int msc_fetch_nonmatch(msc_ctx* ctx, uint32_t* ids, uint64_t capacity, uint64_t* n);
+
 /* msc_screen + msc_confirm + msc_combine enqueued back to back on the context's stream with a
  * single host synchronisation at the end (intermediate counts stay on the device). */
 int msc_run(msc_ctx* ctx);

@@ -90,6 +90,7 @@ _SIGS = [
     ("msc_matches_device", C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),
     ("msc_fetch_matches", C.c_int, [C.c_void_p, C.POINTER(C.POINTER(msc_match)), C.POINTER(C.c_uint64)]),
     ("msc_fetch_matches_into", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    ("msc_fetch_nonmatch", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     ("msc_run", C.c_int, [C.c_void_p]),
     ("msc_rebuild_and_run", C.c_int, [C.c_void_p, C.c_int]),
     ("msc_run_stages", C.c_int, [C.c_void_p, C.c_int, C.c_int]),

@@ -128,7 +128,7 @@ struct msc_ctx {
   // device-side read prep (msc_prep_reads): sorted permutation of the raw reads and group starts
   uint64_t prep_kept = 0, prep_unique = 0, prep_bytes = 0;
   bool have_prep = false;
-  DevBuf prep_perm, prep_gstart;
+  DevBuf prep_perm, prep_gstart, nm_flag, nm_pos, nm_list;
   struct PrepTmp {  // scratch of msc_prep_reads, kept between calls
     DevBuf d_raw, d_offs, planes, idx_a, idx_b, keep, hist, hoff, head, head_scan, ulen, uoffs;
     void release_all() {
@@ -841,7 +841,7 @@ void msc_destroy(msc_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->rd_ascii,    &ctx->rd_offs,   &ctx->rd_words, &ctx->rd_x,      &ctx->len_flags, &ctx->validmask, &ctx->rmeta,
                     &ctx->tab_fp,      &ctx->tab_item0, &ctx->tab_cnt,  &ctx->tab_start, &ctx->tab_fill,  &ctx->pass_cnt, &ctx->bloom,
                     &ctx->items,       &ctx->dup_slot,  &ctx->tg_ascii,  &ctx->tg_off,    &ctx->tg_words,
-                    &ctx->tg_x,        &ctx->xsum,      &ctx->blk2gene,  &ctx->prep_perm, &ctx->prep_gstart, &ctx->cand,     &ctx->cinfo,     &ctx->sizes,     &ctx->pstart,
+                    &ctx->tg_x,        &ctx->xsum,      &ctx->blk2gene,  &ctx->prep_perm, &ctx->prep_gstart, &ctx->nm_flag, &ctx->nm_pos, &ctx->nm_list, &ctx->cand,     &ctx->cinfo,     &ctx->sizes,     &ctx->pstart,
                     &ctx->block_first, &ctx->match_pre, &ctx->best,     &ctx->rcount,    &ctx->rstart,    &ctx->rfill,
                     &ctx->match_out,   &ctx->long_list, &ctx->counters,  &ctx->tile_sums, &ctx->scan_state, &ctx->nmiss};
   for (DevBuf* b : bufs) b->release();
@@ -1293,6 +1293,39 @@ int msc_fetch_matches_into(msc_ctx* ctx, msc_match* dst, uint64_t capacity, uint
     CK(cudaMemcpyAsync(dst, ctx->match_out.p, ctx->n_match * sizeof(msc_match), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->st.d2h_bytes += ctx->n_match * sizeof(msc_match);
+  }
+  return MSC_OK;
+}
+
+int msc_fetch_nonmatch(msc_ctx* ctx, uint32_t* ids, uint64_t capacity, uint64_t* n) {
+  if (!ctx || !n) return MSC_ERR_STATE;
+  if (!ctx->have_confirm) return ctx->fail(MSC_ERR_STATE, "msc_fetch_nonmatch: run msc_confirm first");
+  CK(cudaSetDevice(ctx->device));
+  const uint64_t U = ctx->n_reads;
+  *n = 0;
+  if (!U) return MSC_OK;
+  CK(ctx->nm_flag.reserve((U + 4) * sizeof(uint32_t)));
+  CK(ctx->nm_pos.reserve((U + 4) * sizeof(uint32_t)));
+  CK(ctx->nm_list.reserve((U + 4) * sizeof(uint32_t)));
+  nonmatch_flag_kernel<<<grid_for(U, 256), 256, 0, ctx->stream>>>(ctx->best.as<uint32_t>(), U, MSC_NO_MATCH,
+                                                                   ctx->nm_flag.as<uint32_t>());
+  LAUNCH_CHECK();
+  RC(enqueue_exclusive_scan<uint32_t>(ctx, ctx->nm_flag.as<uint32_t>(), nullptr, U, ctx->nm_pos.as<uint32_t>(), true,
+                                      ctx->ctr(C_PAD2)));
+  nonmatch_scatter_kernel<<<grid_for(U, 256), 256, 0, ctx->stream>>>(ctx->nm_flag.as<uint32_t>(), ctx->nm_pos.as<uint32_t>(), U,
+                                                                      ctx->nm_list.as<uint32_t>());
+  LAUNCH_CHECK();
+  RC(sync_counters(ctx));
+  const uint64_t cnt = ctx->h_counters[C_PAD2];
+  *n = cnt;
+  if (!ids) return MSC_OK;
+  if (cnt > capacity)
+    return ctx->fail(MSC_ERR_NOMEM, "msc_fetch_nonmatch: %llu reads do not fit %llu slots", (unsigned long long)cnt,
+                     (unsigned long long)capacity);
+  if (cnt) {
+    CK(cudaMemcpyAsync(ids, ctx->nm_list.p, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->st.d2h_bytes += cnt * sizeof(uint32_t);
   }
   return MSC_OK;
 }

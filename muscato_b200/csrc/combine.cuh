@@ -159,6 +159,22 @@ __global__ void __launch_bounds__(kRankThreads) segment_rank_sort_kernel(
   }
 }
 
+// Non-match writer support (cmd/muscato_nonmatch/main.go:57-113 keeps the reads
+// whose sequence is absent from column 1 of the results): a read matched iff its best mismatch
+// count was ever set.  flag -> exclusive scan -> ordered scatter yields the unmatched read ids in
+// reads_sorted order, which is the order of the non-match fastq.
+__global__ void __launch_bounds__(256) nonmatch_flag_kernel(const uint32_t* __restrict__ best, uint64_t n_reads,
+                                                            uint32_t no_match, uint32_t* __restrict__ flag) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_reads) flag[r] = best[r] == no_match ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) nonmatch_scatter_kernel(const uint32_t* __restrict__ flag,
+                                                               const uint32_t* __restrict__ pos, uint64_t n_reads,
+                                                               uint32_t* __restrict__ list) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_reads && flag[r]) list[pos[r]] = (uint32_t)r;
+}
+
 // Flag the key groups whose passing-pair count exceeds MaxMatches (mode-2 input).
 __global__ void __launch_bounds__(256) overflow_flag_kernel(const uint32_t* __restrict__ pass_cnt, uint64_t n_slots,
                                                             unsigned long long max_matches,

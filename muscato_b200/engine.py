@@ -183,6 +183,14 @@ class HotPath:
         finally:
             self._lib.msc_free(out)
 
+    def nonmatch_ids(self) -> np.ndarray:
+        """Ids of the reads without a confirmed match, ascending (device-side, msc_fetch_nonmatch)."""
+        n = C.c_uint64(0)
+        self._check(self._lib.msc_fetch_nonmatch(self._ctx, None, 0, C.byref(n)))
+        ids = np.empty(max(1, int(n.value)), dtype=np.uint32)
+        self._check(self._lib.msc_fetch_nonmatch(self._ctx, ids.ctypes.data, len(ids), C.byref(n)))
+        return ids[: int(n.value)]
+
     def fetch_into(self, dst_ptr: int, capacity: int) -> int:
         """Copy the matches into a caller-owned (e.g. pinned) buffer of `capacity` 16-byte records."""
         n = C.c_uint64(0)

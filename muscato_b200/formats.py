@@ -126,6 +126,18 @@ def nonmatch_fastq(matches: np.ndarray, reads: Sequence[bytes], counts: Sequence
     return b"".join(out)
 
 
+def nonmatch_fastq_from_ids(ids, reads: Sequence[bytes], counts: Sequence[bytes], names: Sequence[bytes]) -> bytes:
+    """Same file as nonmatch_fastq(), from the unmatched read ids the device reports
+    (msc_fetch_nonmatch) instead of a scan over the matches."""
+    out = []
+    for i in ids:
+        i = int(i)
+        nm = _fields(names[i])
+        first = nm[0] if nm else b""
+        out.append(first + b"#" + counts[i] + b"\n" + reads[i] + b"\n+\n" + b"!" * len(reads[i]) + b"\n")
+    return b"".join(out)
+
+
 def prep_reads_uniqify(fastq: bytes, min_len: int, max_len: int):
     """prepReads = muscato_prep_reads | sort | muscato_uniqify (cmd/muscato/main.go:152-221;
     cmd/muscato_prep_reads/main.go:46-92; cmd/muscato_uniqify/main.go:77-135).

@@ -31,8 +31,13 @@ def run_cuda(cfg: Config, reads, targets, taps=False):
         hp.confirm()
         hp.combine()
         m = hp.fetch()
+        nm = hp.nonmatch_ids()
         st = hp.stats()
     assert_fetch_order(m)
+    # device-side list of unmatched reads (msc_fetch_nonmatch) == complement of the matched read ids
+    n_reads = len(reads[1]) - 1 if isinstance(reads, tuple) else len(reads)
+    want_nm = np.setdiff1d(np.arange(n_reads, dtype=np.uint32), np.unique(m["read_id"]).astype(np.uint32))
+    assert np.array_equal(nm, want_nm)
     return m, st, keys, cands
 
 
@@ -71,6 +76,8 @@ def check_against_oracle(tmp_path, raw_reads, names, genes, cfgd, gene_names=Non
     res = b"".join(ln + b"\n" for ln in formats.results_lines(m, seqs, counts, rnames, targets, gnames, glens))
     assert res == helpers.read_bytes(out["results"])
     assert formats.nonmatch_fastq(m, seqs, counts, rnames) == helpers.read_bytes(out["nonmatch"])
+    nm_ids = np.setdiff1d(np.arange(len(seqs)), np.unique(m["read_id"]))
+    assert formats.nonmatch_fastq_from_ids(nm_ids, seqs, counts, rnames) == helpers.read_bytes(out["nonmatch"])
     return m, st
 
 
