@@ -118,7 +118,7 @@ struct msc_ctx {
   // matches
   uint64_t n_match_pre = 0, n_match = 0;
   bool have_confirm = false, have_combine = false;
-  DevBuf match_pre, best, rcount, rstart, rfill, match_out, long_list;
+  DevBuf match_pre, best, rcount, rstart, rfill, match_out, long_list, mid_list;
   // confirm kernel mode 2 (MaxMatches overflow groups diverted to the host)
   struct {
     const uint8_t* slot_over = nullptr;
@@ -575,6 +575,7 @@ int enqueue_combine(msc_ctx* ctx) {
   CK(ctx->rfill.reserve((U + 1) * sizeof(uint32_t)));
   CK(ctx->match_out.reserve((mcap + 1) * sizeof(uint4)));
   CK(ctx->long_list.reserve((U + 1) * sizeof(uint32_t)));
+  CK(ctx->mid_list.reserve((U + 1) * sizeof(uint32_t)));
   CK(cudaEventRecord(ctx->ev[EV_COMB0], ctx->stream));
   if (!ctx->pro.combine) {
     Filler f;
@@ -597,11 +598,12 @@ int enqueue_combine(msc_ctx* ctx) {
   if (U) {
     // deterministic (gene, pos) order inside every read group; match_pre is dead and serves as scratch
     segment_sort_short_kernel<<<grid_for(U, 256), 256, 0, ctx->stream>>>(
-        ctx->match_out.as<uint4>(), ctx->rstart.as<uint32_t>(), U, ctx->long_list.as<uint32_t>(), ctx->ctr(C_NLONG));
+        ctx->match_out.as<uint4>(), ctx->rstart.as<uint32_t>(), U, ctx->long_list.as<uint32_t>(), ctx->ctr(C_NLONG),
+        ctx->mid_list.as<uint32_t>(), ctx->ctr(C_PAD1));
     LAUNCH_CHECK();
     segment_rank_sort_kernel<<<g, kRankThreads, 0, ctx->stream>>>(ctx->match_out.as<uint4>(), ctx->match_pre.as<uint4>(),
                                                          ctx->rstart.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
-                                                         ctx->ctr(C_NLONG));
+                                                         ctx->ctr(C_NLONG), ctx->mid_list.as<uint32_t>(), ctx->ctr(C_PAD1));
     LAUNCH_CHECK();
   }
   CK(cudaEventRecord(ctx->ev[EV_COMB1], ctx->stream));
@@ -843,7 +845,7 @@ void msc_destroy(msc_ctx* ctx) {
                     &ctx->items,       &ctx->dup_slot,  &ctx->tg_ascii,  &ctx->tg_off,    &ctx->tg_words,
                     &ctx->tg_x,        &ctx->xsum,      &ctx->blk2gene,  &ctx->prep_perm, &ctx->prep_gstart, &ctx->nm_flag, &ctx->nm_pos, &ctx->nm_list, &ctx->cand,     &ctx->cinfo,     &ctx->sizes,     &ctx->pstart,
                     &ctx->block_first, &ctx->match_pre, &ctx->best,     &ctx->rcount,    &ctx->rstart,    &ctx->rfill,
-                    &ctx->match_out,   &ctx->long_list, &ctx->counters,  &ctx->tile_sums, &ctx->scan_state, &ctx->nmiss};
+                    &ctx->match_out,   &ctx->long_list, &ctx->mid_list, &ctx->counters,  &ctx->tile_sums, &ctx->scan_state, &ctx->nmiss};
   for (DevBuf* b : bufs) b->release();
   ctx->prep.release_all();
   if (ctx->ev_prep0) cudaEventDestroy(ctx->ev_prep0);

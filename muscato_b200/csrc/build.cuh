@@ -158,11 +158,21 @@ __global__ void __launch_bounds__(256) build_alloc_kernel(const uint32_t* __rest
                                                           uint32_t* __restrict__ tab_fill,
                                                           uint32_t* __restrict__ tab_start,
                                                           unsigned long long* __restrict__ n_dup) {
+  // the reservations of a block are summed in shared memory: ONE bump of the global counter per
+  // block (same-address global atomics serialise)
+  __shared__ uint32_t s_total;
+  __shared__ unsigned long long s_base;
+  if (threadIdx.x == 0) s_total = 0u;
+  __syncthreads();
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_items) return;
-  const uint32_t d = __ldg(dup_slot + idx);
-  if (d && atomicAdd(tab_fill + (d - 1), 1u) == 0u)
-    tab_start[d - 1] = (uint32_t)atomicAdd(n_dup, (unsigned long long)__ldg(tab_cnt + (d - 1)));
+  const uint32_t d = idx < n_items ? __ldg(dup_slot + idx) : 0u;
+  const bool first = d && atomicAdd(tab_fill + (d - 1), 1u) == 0u;
+  uint32_t local = 0;
+  if (first) local = atomicAdd(&s_total, __ldg(tab_cnt + (d - 1)));
+  __syncthreads();
+  if (threadIdx.x == 0 && s_total) s_base = atomicAdd(n_dup, (unsigned long long)s_total);
+  __syncthreads();
+  if (first) tab_start[d - 1] = (uint32_t)(s_base + local);
 }
 
 // Pass B2: scatter the further members into their slot's CSR range.  A CSR entry is 16 bytes:

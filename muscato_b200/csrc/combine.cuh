@@ -43,14 +43,17 @@ __device__ __forceinline__ bool match_less(const uint4& a, const uint4& b) {
 __global__ void __launch_bounds__(256) segment_sort_short_kernel(uint4* __restrict__ m,
                                                                  const uint32_t* __restrict__ rstart, uint64_t n_reads,
                                                                  uint32_t* __restrict__ long_list,
-                                                                 unsigned long long* __restrict__ n_long) {
+                                                                 unsigned long long* __restrict__ n_long,
+                                                                 uint32_t* __restrict__ mid_list,
+                                                                 unsigned long long* __restrict__ n_mid) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   const uint32_t lo = rstart[r], hi = rstart[r + 1];
   const uint32_t n = hi - lo;
   if (n <= 1) return;
-  if (n > kShortSegment) {
-    long_list[atomicAdd(n_long, 1ull)] = (uint32_t)r;
+  if (n > kShortSegment) {  // queued: one warp per group up to 32 members, one block per larger group
+    if (n <= 32u) mid_list[atomicAdd(n_mid, 1ull)] = (uint32_t)r;
+    else long_list[atomicAdd(n_long, 1ull)] = (uint32_t)r;
     return;
   }
   uint4 v[kShortSegment];
@@ -83,19 +86,19 @@ constexpr int kRankSmem = 2048;
 
 __global__ void __launch_bounds__(kRankThreads) segment_rank_sort_kernel(
     uint4* __restrict__ m, uint4* __restrict__ scratch, const uint32_t* __restrict__ rstart,
-    const uint32_t* __restrict__ long_list, const unsigned long long* __restrict__ n_long) {
+    const uint32_t* __restrict__ long_list, const unsigned long long* __restrict__ n_long,
+    const uint32_t* __restrict__ mid_list, const unsigned long long* __restrict__ n_mid) {
   __shared__ uint64_t keys[kRankSmem];
   __shared__ uint2 rest[kRankSmem];
-  const uint64_t nl = *n_long;
+  const uint64_t nl = *n_long, nm = *n_mid;
   // pass 1: groups of up to 32 members, one WARP per group: every lane holds one member and
   // counts the members that precede it with 32 shuffles (no shared memory, no block barrier)
   {
     const unsigned lane = threadIdx.x & 31u;
     const uint64_t gw = ((uint64_t)blockIdx.x * kRankThreads + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * kRankThreads) >> 5;
-    for (uint64_t s = gw; s < nl; s += nw) {
-      const uint32_t r = long_list[s];
+    for (uint64_t s = gw; s < nm; s += nw) {
+      const uint32_t r = mid_list[s];
       const uint32_t lo = rstart[r], n = rstart[r + 1] - lo;
-      if (n > 32u) continue;
       uint4 a = make_uint4(0u, 0u, 0u, 0u);
       if (lane < n) a = m[lo + lane];
       const uint64_t k = lane < n ? (((uint64_t)a.y << 32) | (uint64_t)a.z) : ~0ull;
@@ -109,7 +112,6 @@ __global__ void __launch_bounds__(kRankThreads) segment_rank_sort_kernel(
   for (uint64_t s = blockIdx.x; s < nl; s += gridDim.x) {
     const uint32_t r = long_list[s];
     const uint32_t lo = rstart[r], hi = rstart[r + 1], n = hi - lo;
-    if (n <= 32u) continue;  // block-uniform
     if (n <= (uint32_t)kRankSmem) {
       // bitonic sort of (gene, pos) keys in shared memory (padded to a power of two with +inf keys)
       uint32_t np2 = 2;
