@@ -198,6 +198,11 @@ int msc_rebuild_and_run(msc_ctx* ctx, int what);
 enum { MSC_STAGE_SCREEN = 1, MSC_STAGE_CONFIRM = 2, MSC_STAGE_COMBINE = 4 };
 int msc_run_stages(msc_ctx* ctx, int rebuild_what, int stages);
 
+/* Per-stage timers (ms_pack_reads .. ms_combine) cost one event record between kernels per stage
+ * boundary (~2.5 us each on a B200); on = 0 leaves them out -- ms_scan / ms_scan_kernel are always
+ * measured.  Default: on (MSC_STAGE_EVENTS=0 in the environment turns them off at msc_create). */
+int msc_set_stage_timing(msc_ctx* ctx, int on);
+
 int msc_get_stats(const msc_ctx* ctx, msc_stats* out);
 void msc_reset_stats(msc_ctx* ctx);
 void msc_free(void* p);

@@ -94,6 +94,7 @@ _SIGS = [
     ("msc_run", C.c_int, [C.c_void_p]),
     ("msc_rebuild_and_run", C.c_int, [C.c_void_p, C.c_int]),
     ("msc_run_stages", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("msc_set_stage_timing", C.c_int, [C.c_void_p, C.c_int]),
     ("msc_get_stats", C.c_int, [C.c_void_p, C.POINTER(msc_stats)]),
     ("msc_reset_stats", None, [C.c_void_p]),
     ("msc_free", None, [C.c_void_p]),

@@ -142,6 +142,9 @@ struct msc_ctx {
   unsigned long long scan_arrivals = 0;  // arrivals the scan kernel's grid barrier has seen so far (never reset)
   unsigned long long* h_counters = nullptr;  // pinned mirror
   // MSC_TRACE=1: an event after every launch, per-launch device times printed at each sync
+  // stage boundary events other than the scan kernel's pair: MSC_STAGE_EVENTS=0 leaves them out
+  // (every record is one more stream operation between two kernels)
+  bool stage_events = true;
   bool trace = false;
   std::vector<std::pair<const char*, cudaEvent_t>> trace_ev;
   size_t trace_used = 0;
@@ -332,7 +335,7 @@ float elapsed(msc_ctx* ctx, int a, int b) {
 int enqueue_build_reads(msc_ctx* ctx) {
   const uint64_t U = ctx->n_reads;
   const int S = ctx->win.S;
-  CK(cudaEventRecord(ctx->ev[EV_PACKR0], ctx->stream));
+  if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_PACKR0], ctx->stream));
   if (ctx->trace) ctx->trace_mark("start build_reads");
   if (!ctx->pro.reads) {
     Filler f;
@@ -349,7 +352,7 @@ int enqueue_build_reads(msc_ctx* ctx) {
     LAUNCH_CHECK();
   }
   CK(cudaEventRecord(ctx->ev_rd_free, ctx->stream));
-  CK(cudaEventRecord(ctx->ev[EV_PACKR1], ctx->stream));
+  if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_PACKR1], ctx->stream));
 
   const uint64_t n_items = U * (uint64_t)ctx->win.nwin;
   if (U) {
@@ -382,7 +385,7 @@ int enqueue_build_reads(msc_ctx* ctx) {
         ctx->rmeta.as<uint2>(), (uint32_t)ctx->win.nwin, ctx->items.as<uint4>());
     LAUNCH_CHECK();
   }
-  CK(cudaEventRecord(ctx->ev[EV_BUILD1], ctx->stream));
+  if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_BUILD1], ctx->stream));
   ctx->have_cand = ctx->have_confirm = ctx->have_combine = false;
   ctx->pend_reads = true;
   return MSC_OK;
@@ -397,12 +400,14 @@ void account_build_reads(msc_ctx* ctx) {
   ctx->st.n_key_groups = ctx->n_groups;
   ctx->st.table_slots = 1ull << ctx->lg_slots;
   ctx->st.bloom_bytes = (1ull << ctx->lg_bloom) * sizeof(uint64_t);
-  ctx->st.ms_pack_reads += elapsed(ctx, EV_PACKR0, EV_PACKR1);
-  ctx->st.ms_build += elapsed(ctx, EV_PACKR1, EV_BUILD1);
+  if (ctx->stage_events) {
+    ctx->st.ms_pack_reads += elapsed(ctx, EV_PACKR0, EV_PACKR1);
+    ctx->st.ms_build += elapsed(ctx, EV_PACKR1, EV_BUILD1);
+  }
 }
 
 int enqueue_pack_targets(msc_ctx* ctx) {
-  CK(cudaEventRecord(ctx->ev[EV_PACKT0], ctx->stream));
+  if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_PACKT0], ctx->stream));
   if (!ctx->pro.targets) {
     Filler f;
     add_targets_fills(ctx, f);
@@ -414,14 +419,14 @@ int enqueue_pack_targets(msc_ctx* ctx) {
       ctx->tg_x.as<uint64_t>(), ctx->xsum.as<uint32_t>(), ctx->ctr(C_TGX));
   LAUNCH_CHECK();
   CK(cudaEventRecord(ctx->ev_tg_free, ctx->stream));
-  CK(cudaEventRecord(ctx->ev[EV_PACKT1], ctx->stream));
+  if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_PACKT1], ctx->stream));
   ctx->have_cand = ctx->have_confirm = ctx->have_combine = false;
   ctx->pend_targets = true;
   return MSC_OK;
 }
 
 void account_pack_targets(msc_ctx* ctx) {
-  ctx->st.ms_pack_targets += elapsed(ctx, EV_PACKT0, EV_PACKT1);
+  if (ctx->stage_events) ctx->st.ms_pack_targets += elapsed(ctx, EV_PACKT0, EV_PACKT1);
   ctx->st.n_targets = ctx->n_targets;
   ctx->st.target_bases = ctx->n_bases;
 }
@@ -505,7 +510,7 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
                                                            ctx->ctr(C_NPAIRS), ctx->block_cap(),
                                                            ctx->block_first.as<uint32_t>());
   LAUNCH_CHECK();
-  CK(cudaEventRecord(ctx->ev[EV_EXPAND1], ctx->stream));
+  if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_EXPAND1], ctx->stream));
 
   if (!ctx->pro.pairs) {
     Filler f;
@@ -564,7 +569,7 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
         ctx->ctr(C_NOVER));
     LAUNCH_CHECK();
   }
-  CK(cudaEventRecord(ctx->ev[EV_CONFIRM1], ctx->stream));
+  if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_CONFIRM1], ctx->stream));
   return MSC_OK;
 }
 
@@ -576,7 +581,7 @@ int enqueue_combine(msc_ctx* ctx) {
   CK(ctx->match_out.reserve((mcap + 1) * sizeof(uint4)));
   CK(ctx->long_list.reserve((U + 1) * sizeof(uint32_t)));
   CK(ctx->mid_list.reserve((U + 1) * sizeof(uint32_t)));
-  CK(cudaEventRecord(ctx->ev[EV_COMB0], ctx->stream));
+  if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_COMB0], ctx->stream));
   if (!ctx->pro.combine) {
     Filler f;
     add_combine_fills(ctx, f);
@@ -606,7 +611,7 @@ int enqueue_combine(msc_ctx* ctx) {
                                                          ctx->ctr(C_NLONG), ctx->mid_list.as<uint32_t>(), ctx->ctr(C_PAD1));
     LAUNCH_CHECK();
   }
-  CK(cudaEventRecord(ctx->ev[EV_COMB1], ctx->stream));
+  if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_COMB1], ctx->stream));
   return MSC_OK;
 }
 
@@ -657,8 +662,10 @@ int mark_expand_start(msc_ctx* ctx);
 
 int finish_confirm(msc_ctx* ctx) {
   RC(finish_pairs(ctx, ctx->match_pre, &ctx->n_match_pre));
-  ctx->st.ms_expand += elapsed(ctx, EV_SCAN1, EV_EXPAND1);
-  ctx->st.ms_confirm += elapsed(ctx, EV_EXPAND1, EV_CONFIRM1);
+  if (ctx->stage_events) {
+    ctx->st.ms_expand += elapsed(ctx, EV_SCAN1, EV_EXPAND1);
+    ctx->st.ms_confirm += elapsed(ctx, EV_EXPAND1, EV_CONFIRM1);
+  }
   ctx->st.n_pairs = ctx->n_pairs;
   ctx->st.n_pass = ctx->h_counters[C_NPASS];
   ctx->st.n_matches_pre = ctx->n_match_pre;
@@ -682,7 +689,7 @@ int finish_confirm(msc_ctx* ctx) {
 int finish_combine(msc_ctx* ctx) {
   ctx->n_match = ctx->h_counters[C_NOUT];
   ctx->st.n_matches = ctx->n_match;
-  ctx->st.ms_combine += elapsed(ctx, EV_COMB0, EV_COMB1);
+  if (ctx->stage_events) ctx->st.ms_combine += elapsed(ctx, EV_COMB0, EV_COMB1);
   ctx->have_combine = true;
   return MSC_OK;
 }
@@ -796,6 +803,7 @@ msc_ctx* msc_create(const msc_config* config, char* errbuf, uint64_t errlen) {
   ctx->device = c.device;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->trace = getenv("MSC_TRACE") && atoi(getenv("MSC_TRACE")) > 0;
+  if (const char* e = getenv("MSC_STAGE_EVENTS")) ctx->stage_events = atoi(e) != 0;
   ctx->win.nwin = c.n_windows;
   ctx->win.W = c.window_width;
   ctx->win.MRL = c.max_read_length;
@@ -1343,6 +1351,14 @@ int msc_fetch_matches(msc_ctx* ctx, msc_match** out, uint64_t* n) {
     return rc;
   }
   *out = h;
+  return MSC_OK;
+}
+
+int msc_set_stage_timing(msc_ctx* ctx, int on) {
+  if (!ctx) return MSC_ERR_STATE;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->pend_reads || ctx->pend_targets) RC(sync_counters(ctx));  // book builds enqueued under the old setting
+  ctx->stage_events = on != 0;
   return MSC_OK;
 }
 

@@ -217,6 +217,10 @@ class HotPath:
         finally:
             self._lib.msc_free(out)
 
+    def set_stage_timing(self, on: bool):
+        """Per-stage timers on/off (one event record per stage boundary); the scan kernel is always timed."""
+        self._check(self._lib.msc_set_stage_timing(self._ctx, 1 if on else 0))
+
     def stats(self) -> dict:
         st = _capi.msc_stats()
         self._check(self._lib.msc_get_stats(self._ctx, C.byref(st)))
