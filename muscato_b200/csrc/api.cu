@@ -32,6 +32,25 @@ using namespace msc;
 
 namespace {
 
+// Kernel launch with the programmatic-stream-serialization attribute (PDL): the kernel may be
+// launched while its predecessor in the stream is still running; every kernel starts with
+// pdl_enter() (common.cuh), which waits for the predecessor's completion before touching memory.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                     Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1u : 0u;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
@@ -145,6 +164,7 @@ struct msc_ctx {
   // stage boundary events other than the scan kernel's pair: MSC_STAGE_EVENTS=0 leaves them out
   // (every record is one more stream operation between two kernels)
   bool stage_events = true;
+  bool pdl = true;  // MSC_PDL=0: plain stream-ordered launches
   bool trace = false;
   std::vector<std::pair<const char*, cudaEvent_t>> trace_ev;
   size_t trace_used = 0;
@@ -228,7 +248,7 @@ int enqueue_exclusive_scan(msc_ctx* ctx, const uint32_t* in, const unsigned long
   const unsigned grid = (unsigned)std::min(ctx->sm_count, kScanThreads);
   if (ctx->tile_sums.cap == 0) CK(ctx->tile_sums.reserve((size_t)kScanThreads * sizeof(uint64_t)));
   ctx->scan_arrivals += grid;
-  scan_resident_kernel<OutT><<<grid, kScanThreads, 0, ctx->stream>>>(in, n_ptr, n_host, out, write_end ? 1 : 0, total,
+  launch_k(ctx->pdl, scan_resident_kernel<OutT>, grid, kScanThreads, 0, ctx->stream, in, n_ptr, n_host, out, write_end ? 1 : 0, total,
                                                                      ctx->tile_sums.as<uint64_t>(),
                                                                      ctx->scan_state.as<unsigned long long>(),
                                                                      ctx->scan_arrivals);
@@ -281,7 +301,7 @@ void add_combine_fills(msc_ctx* ctx, Filler& f) {
 
 int enqueue_fill(msc_ctx* ctx, const Filler& f) {
   if (f.job.n == 0) return MSC_OK;
-  fill_buffers_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, ctx->stream>>>(f.job);
+  launch_k(ctx->pdl, fill_buffers_kernel, (unsigned)ctx->sm_count * 8, 256, 0, ctx->stream, f.job);
   LAUNCH_CHECK();
   return MSC_OK;
 }
@@ -346,7 +366,7 @@ int enqueue_build_reads(msc_ctx* ctx) {
   if (U) {
     const int rpb = std::max(1, 256 / S);  // whole reads per block
     const size_t smem = (size_t)rpb * (size_t)ctx->win.MRL + 64;
-    pack_reads_kernel<<<grid_for(U, rpb), 256, smem, ctx->stream>>>(
+    launch_k(ctx->pdl, pack_reads_kernel, grid_for(U, rpb), 256, smem, ctx->stream, 
         ctx->rd_ascii.as<uint8_t>(), ctx->rd_offs.as<uint64_t>(), U, S, rpb, ctx->rd_words.as<uint64_t>(),
         ctx->rd_x.as<uint64_t>(), ctx->len_flags.as<uint32_t>());
     LAUNCH_CHECK();
@@ -372,15 +392,15 @@ int enqueue_build_reads(msc_ctx* ctx) {
     a.dup_slot = ctx->dup_slot.as<uint32_t>();
     a.bloom = ctx->bloom.as<unsigned long long>();
     a.geom = ctx->geom;
-    build_keys_insert_kernel<<<grid_for(U, 256), 256, 0, ctx->stream>>>(ctx->win, a);
+    launch_k(ctx->pdl, build_keys_insert_kernel, grid_for(U, 256), 256, 0, ctx->stream, ctx->win, a);
     LAUNCH_CHECK();
   }
   if (U) {
-    build_alloc_kernel<<<grid_for(n_items, 256), 256, 0, ctx->stream>>>(
+    launch_k(ctx->pdl, build_alloc_kernel, grid_for(n_items, 256), 256, 0, ctx->stream, 
         ctx->dup_slot.as<uint32_t>(), n_items, ctx->tab_cnt.as<uint32_t>(), ctx->tab_fill.as<uint32_t>(),
         ctx->tab_start.as<uint32_t>(), ctx->ctr(C_NDUP));
     LAUNCH_CHECK();
-    build_fill_kernel<<<grid_for(n_items, 256), 256, 0, ctx->stream>>>(
+    launch_k(ctx->pdl, build_fill_kernel, grid_for(n_items, 256), 256, 0, ctx->stream, 
         ctx->dup_slot.as<uint32_t>(), n_items, ctx->tab_start.as<uint32_t>(), ctx->tab_fill.as<uint32_t>(),
         ctx->rmeta.as<uint2>(), (uint32_t)ctx->win.nwin, ctx->items.as<uint4>());
     LAUNCH_CHECK();
@@ -414,7 +434,7 @@ int enqueue_pack_targets(msc_ctx* ctx) {
     RC(enqueue_fill(ctx, f));
   }
   ctx->pro.targets = false;
-  pack_targets_kernel<<<grid_for(ctx->n_words_alloc, 256), 256, 0, ctx->stream>>>(
+  launch_k(ctx->pdl, pack_targets_kernel, grid_for(ctx->n_words_alloc, 256), 256, 0, ctx->stream, 
       ctx->tg_ascii.as<uint8_t>(), ctx->n_bases, ctx->tg_words.as<uint64_t>(), ctx->n_words_alloc,
       ctx->tg_x.as<uint64_t>(), ctx->xsum.as<uint32_t>(), ctx->ctr(C_TGX));
   LAUNCH_CHECK();
@@ -481,7 +501,7 @@ int enqueue_scan(msc_ctx* ctx) {
     a.n_bloom_pass = ctx->ctr(C_BLOOMPASS);
     a.W = ctx->win.W;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ctx->n_tiles, (uint64_t)ctx->scan_grid));
-    scan_fn<<<grid, kScanBlock, 0, ctx->stream>>>(a);
+    launch_k(ctx->pdl, scan_fn, grid, kScanBlock, 0, ctx->stream, a);
     LAUNCH_CHECK();
   }
   CK(cudaEventRecord(ctx->ev[EV_SCAN1], ctx->stream));
@@ -497,7 +517,7 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   if (ctx->block_first.cap == 0) CK(ctx->block_first.reserve(((size_t)(1u << 19) + 2) * sizeof(uint32_t)));
   if (outbuf.cap == 0) CK(outbuf.reserve((size_t)(1u << 20) * sizeof(uint4)));
   const unsigned pgrid = (unsigned)ctx->sm_count * 8;
-  cand_prepare_kernel<<<pgrid, 256, 0, ctx->stream>>>(ctx->cand.as<uint2>(), ctx->ctr(C_NCAND), ccap,
+  launch_k(ctx->pdl, cand_prepare_kernel, pgrid, 256, 0, ctx->stream, ctx->cand.as<uint2>(), ctx->ctr(C_NCAND), ccap,
                                                       ctx->tab_cnt.as<uint32_t>(), ctx->tab_item0.as<uint32_t>(),
                                                       ctx->tab_start.as<uint32_t>(), ctx->tg_off.as<uint32_t>(),
                                                       ctx->blk2gene.as<uint32_t>(), ctx->win.W, ctx->rmeta.as<uint2>(),
@@ -506,7 +526,7 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   LAUNCH_CHECK();
   RC(enqueue_exclusive_scan<uint64_t>(ctx, ctx->sizes.as<uint32_t>(), ctx->ctr(C_NCAND), ccap, ctx->pstart.as<uint64_t>(),
                                       true, ctx->ctr(C_NPAIRS)));
-  pair_block_starts_kernel<<<pgrid, 256, 0, ctx->stream>>>(ctx->pstart.as<uint64_t>(), ctx->ctr(C_NCAND), ccap,
+  launch_k(ctx->pdl, pair_block_starts_kernel, pgrid, 256, 0, ctx->stream, ctx->pstart.as<uint64_t>(), ctx->ctr(C_NCAND), ccap,
                                                            ctx->ctr(C_NPAIRS), ctx->block_cap(),
                                                            ctx->block_first.as<uint32_t>());
   LAUNCH_CHECK();
@@ -556,15 +576,15 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
     ctx->confirm_grid = ctx->sm_count * std::max(1, per_sm);
   }
   const unsigned cgrid = (unsigned)ctx->confirm_grid;
-  if (mode == 0) confirm_pairs_kernel<0><<<cgrid, 256, 0, ctx->stream>>>(ctx->win, a);
-  else if (mode == 1) confirm_pairs_kernel<1><<<cgrid, 256, 0, ctx->stream>>>(ctx->win, a);
-  else confirm_pairs_kernel<2><<<cgrid, 256, 0, ctx->stream>>>(ctx->win, a);
+  if (mode == 0) launch_k(ctx->pdl, confirm_pairs_kernel<0>, cgrid, 256, 0, ctx->stream, ctx->win, a);
+  else if (mode == 1) launch_k(ctx->pdl, confirm_pairs_kernel<1>, cgrid, 256, 0, ctx->stream, ctx->win, a);
+  else launch_k(ctx->pdl, confirm_pairs_kernel<2>, cgrid, 256, 0, ctx->stream, ctx->win, a);
   LAUNCH_CHECK();
   if (mode == 0) {
     // MaxMatches pre-check (cmd/muscato_confirm/main.go:233-242, :424-448): truncation can only
     // happen in a key group with more than MaxMatches passing pairs.
     const uint64_t slots = 1ull << ctx->lg_slots;
-    overflow_count_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, ctx->stream>>>(
+    launch_k(ctx->pdl, overflow_count_kernel, (unsigned)ctx->sm_count * 8, 256, 0, ctx->stream, 
         ctx->pass_cnt.as<uint32_t>(), slots, (unsigned long long)ctx->cfg.max_matches, ctx->ctr(C_NPASS),
         ctx->ctr(C_NOVER));
     LAUNCH_CHECK();
@@ -589,24 +609,24 @@ int enqueue_combine(msc_ctx* ctx) {
   }
   ctx->pro.combine = false;
   const unsigned g = (unsigned)ctx->sm_count * 8;
-  combine_count_kernel<<<g, 256, 0, ctx->stream>>>(ctx->match_pre.as<uint4>(), ctx->ctr(C_NMATCH), mcap,
+  launch_k(ctx->pdl, combine_count_kernel, g, 256, 0, ctx->stream, ctx->match_pre.as<uint4>(), ctx->ctr(C_NMATCH), mcap,
                                                    ctx->best.as<uint32_t>(), (uint32_t)ctx->cfg.mmtol,
                                                    ctx->rcount.as<uint32_t>());
   LAUNCH_CHECK();
   RC(enqueue_exclusive_scan<uint32_t>(ctx, ctx->rcount.as<uint32_t>(), nullptr, U, ctx->rstart.as<uint32_t>(), true,
                                       ctx->ctr(C_NOUT)));
-  combine_scatter_kernel<<<g, 256, 0, ctx->stream>>>(ctx->match_pre.as<uint4>(), ctx->ctr(C_NMATCH), mcap,
+  launch_k(ctx->pdl, combine_scatter_kernel, g, 256, 0, ctx->stream, ctx->match_pre.as<uint4>(), ctx->ctr(C_NMATCH), mcap,
                                                      ctx->best.as<uint32_t>(), (uint32_t)ctx->cfg.mmtol,
                                                      ctx->rstart.as<uint32_t>(), ctx->rfill.as<uint32_t>(),
                                                      ctx->match_out.as<uint4>());
   LAUNCH_CHECK();
   if (U) {
     // deterministic (gene, pos) order inside every read group; match_pre is dead and serves as scratch
-    segment_sort_short_kernel<<<grid_for(U, 256), 256, 0, ctx->stream>>>(
+    launch_k(ctx->pdl, segment_sort_short_kernel, grid_for(U, 256), 256, 0, ctx->stream, 
         ctx->match_out.as<uint4>(), ctx->rstart.as<uint32_t>(), U, ctx->long_list.as<uint32_t>(), ctx->ctr(C_NLONG),
         ctx->mid_list.as<uint32_t>(), ctx->ctr(C_PAD1));
     LAUNCH_CHECK();
-    segment_rank_sort_kernel<<<g, kRankThreads, 0, ctx->stream>>>(ctx->match_out.as<uint4>(), ctx->match_pre.as<uint4>(),
+    launch_k(ctx->pdl, segment_rank_sort_kernel, g, kRankThreads, 0, ctx->stream, ctx->match_out.as<uint4>(), ctx->match_pre.as<uint4>(),
                                                          ctx->rstart.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
                                                          ctx->ctr(C_NLONG), ctx->mid_list.as<uint32_t>(), ctx->ctr(C_PAD1));
     LAUNCH_CHECK();
@@ -804,6 +824,7 @@ msc_ctx* msc_create(const msc_config* config, char* errbuf, uint64_t errlen) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->trace = getenv("MSC_TRACE") && atoi(getenv("MSC_TRACE")) > 0;
   if (const char* e = getenv("MSC_STAGE_EVENTS")) ctx->stage_events = atoi(e) != 0;
+  if (const char* e = getenv("MSC_PDL")) ctx->pdl = atoi(e) != 0;
   ctx->win.nwin = c.n_windows;
   ctx->win.W = c.window_width;
   ctx->win.MRL = c.max_read_length;
@@ -993,7 +1014,7 @@ int msc_set_reads_device(msc_ctx* ctx, const uint8_t* d_ascii, const uint64_t* d
     RC(enqueue_fill(ctx, f));
   }
   if (n_reads) {
-    validate_read_offsets_kernel<<<grid_for(n_reads, 256), 256, 0, ctx->stream>>>(
+    launch_k(ctx->pdl, validate_read_offsets_kernel, grid_for(n_reads, 256), 256, 0, ctx->stream, 
         ctx->rd_offs.as<uint64_t>(), n_reads, total_bytes, (uint64_t)ctx->win.MRL, ctx->ctr(C_PAD1));
     LAUNCH_CHECK();
   }
@@ -1080,29 +1101,29 @@ int msc_prep_reads(msc_ctx* ctx, const uint8_t* raw_ascii, const uint64_t* raw_o
   uint32_t* cur = idx_a.as<uint32_t>();
   uint32_t* nxt = idx_b.as<uint32_t>();
   if (n) {
-    prep_encode_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(d_raw.as<uint8_t>(), d_offs.as<uint64_t>(), n, MRL,
+    launch_k(ctx->pdl, prep_encode_kernel, grid_for(n, 256), 256, 0, ctx->stream, d_raw.as<uint8_t>(), d_offs.as<uint64_t>(), n, MRL,
                                                                   (int)min_read_length, n_planes, planes.as<uint8_t>(),
                                                                   keep.as<uint32_t>(), ctx->ctr(C_PREP_KEPT));
     LAUNCH_CHECK();
-    iota_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(cur, n);
+    launch_k(ctx->pdl, iota_kernel, grid_for(n, 256), 256, 0, ctx->stream, cur, n);
     LAUNCH_CHECK();
     // stable LSD radix sort of the read indices, one byte plane (two symbols) per pass
     for (int b = n_planes - 1; b >= 0; b--) {
       const uint8_t* plane = planes.as<uint8_t>() + (size_t)b * n;
-      radix_hist_kernel<<<n_chunks, kRadixThreads, 0, ctx->stream>>>(cur, plane, n, n_chunks, hist.as<uint32_t>());
+      launch_k(ctx->pdl, radix_hist_kernel, n_chunks, kRadixThreads, 0, ctx->stream, cur, plane, n, n_chunks, hist.as<uint32_t>());
       LAUNCH_CHECK();
       PRC(enqueue_exclusive_scan<uint32_t>(ctx, hist.as<uint32_t>(), nullptr, (uint64_t)256 * n_chunks, hoff.as<uint32_t>(),
                                            false, ctx->ctr(C_PAD3)));
-      radix_scatter_kernel<<<n_chunks, kRadixThreads, 0, ctx->stream>>>(cur, plane, n, n_chunks, hoff.as<uint32_t>(), nxt);
+      launch_k(ctx->pdl, radix_scatter_kernel, n_chunks, kRadixThreads, 0, ctx->stream, cur, plane, n, n_chunks, hoff.as<uint32_t>(), nxt);
       LAUNCH_CHECK();
       std::swap(cur, nxt);
     }
-    prep_heads_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(cur, planes.as<uint8_t>(), n, ctx->ctr(C_PREP_KEPT), n_planes,
+    launch_k(ctx->pdl, prep_heads_kernel, grid_for(n, 256), 256, 0, ctx->stream, cur, planes.as<uint8_t>(), n, ctx->ctr(C_PREP_KEPT), n_planes,
                                                                  head.as<uint32_t>());
     LAUNCH_CHECK();
     PRC(enqueue_exclusive_scan<uint32_t>(ctx, head.as<uint32_t>(), ctx->ctr(C_PREP_KEPT), n, head_scan.as<uint32_t>(), true,
                                          ctx->ctr(C_PREP_UNIQ)));
-    prep_groups_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(cur, head.as<uint32_t>(), head_scan.as<uint32_t>(),
+    launch_k(ctx->pdl, prep_groups_kernel, grid_for(n, 256), 256, 0, ctx->stream, cur, head.as<uint32_t>(), head_scan.as<uint32_t>(),
                                                                   ctx->ctr(C_PREP_KEPT), d_offs.as<uint64_t>(), MRL,
                                                                   ctx->ctr(C_PREP_UNIQ), ctx->prep_gstart.as<uint32_t>(),
                                                                   ulen.as<uint32_t>());
@@ -1119,7 +1140,7 @@ int msc_prep_reads(msc_ctx* ctx, const uint8_t* raw_ascii, const uint64_t* raw_o
   if (!n || !ctx->prep_kept) PCK(cudaMemsetAsync(ctx->prep_gstart.p, 0, 2 * sizeof(uint32_t), ctx->stream));
   PRC(reads_reserve(ctx, U, ctx->prep_bytes));
   if (U) {
-    prep_gather_kernel<<<grid_for(U * 32, 256), 256, 0, ctx->stream>>>(d_raw.as<uint8_t>(), d_offs.as<uint64_t>(), ctx->prep_perm.as<uint32_t>(),
+    launch_k(ctx->pdl, prep_gather_kernel, grid_for(U * 32, 256), 256, 0, ctx->stream, d_raw.as<uint8_t>(), d_offs.as<uint64_t>(), ctx->prep_perm.as<uint32_t>(),
                                                                      ctx->prep_gstart.as<uint32_t>(), uoffs.as<uint64_t>(),
                                                                      ctx->ctr(C_PREP_UNIQ), ctx->rd_ascii.as<uint8_t>());
     LAUNCH_CHECK();
@@ -1317,12 +1338,12 @@ int msc_fetch_nonmatch(msc_ctx* ctx, uint32_t* ids, uint64_t capacity, uint64_t*
   CK(ctx->nm_flag.reserve((U + 4) * sizeof(uint32_t)));
   CK(ctx->nm_pos.reserve((U + 4) * sizeof(uint32_t)));
   CK(ctx->nm_list.reserve((U + 4) * sizeof(uint32_t)));
-  nonmatch_flag_kernel<<<grid_for(U, 256), 256, 0, ctx->stream>>>(ctx->best.as<uint32_t>(), U, MSC_NO_MATCH,
+  launch_k(ctx->pdl, nonmatch_flag_kernel, grid_for(U, 256), 256, 0, ctx->stream, ctx->best.as<uint32_t>(), U, MSC_NO_MATCH,
                                                                    ctx->nm_flag.as<uint32_t>());
   LAUNCH_CHECK();
   RC(enqueue_exclusive_scan<uint32_t>(ctx, ctx->nm_flag.as<uint32_t>(), nullptr, U, ctx->nm_pos.as<uint32_t>(), true,
                                       ctx->ctr(C_PAD2)));
-  nonmatch_scatter_kernel<<<grid_for(U, 256), 256, 0, ctx->stream>>>(ctx->nm_flag.as<uint32_t>(), ctx->nm_pos.as<uint32_t>(), U,
+  launch_k(ctx->pdl, nonmatch_scatter_kernel, grid_for(U, 256), 256, 0, ctx->stream, ctx->nm_flag.as<uint32_t>(), ctx->nm_pos.as<uint32_t>(), U,
                                                                       ctx->nm_list.as<uint32_t>());
   LAUNCH_CHECK();
   RC(sync_counters(ctx));

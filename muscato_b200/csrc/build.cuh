@@ -72,6 +72,7 @@ constexpr int kInsertBatch = 2;  // table claims in flight per thread
 // build is bound by the round trip of those atomics, not by their number.
 // item = read * nwin + window.
 __global__ void __launch_bounds__(256, 6) build_keys_insert_kernel(const WinCfg cfg, const BuildArgs a) {
+  pdl_enter();
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t nk = 0;
   if (r < a.n_reads) {
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(256) build_alloc_kernel(const uint32_t* __rest
                                                           uint32_t* __restrict__ tab_fill,
                                                           uint32_t* __restrict__ tab_start,
                                                           unsigned long long* __restrict__ n_dup) {
+  pdl_enter();
   // the reservations of a block are summed in shared memory: ONE bump of the global counter per
   // block (same-address global atomics serialise)
   __shared__ uint32_t s_total;
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(256) build_fill_kernel(const uint32_t* __restr
                                                          uint32_t* __restrict__ tab_fill,
                                                          const uint2* __restrict__ rmeta, uint32_t nwin,
                                                          uint4* __restrict__ items) {
+  pdl_enter();
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_items) return;
   const uint32_t d = __ldg(dup_slot + idx);

@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(256) combine_count_kernel(const uint4* __restr
                                                             const unsigned long long* __restrict__ n_ptr, uint64_t cap,
                                                             const uint32_t* __restrict__ best, uint32_t mmtol,
                                                             uint32_t* __restrict__ rcount) {
+  pdl_enter();
   const uint64_t n = min((uint64_t)*n_ptr, cap);
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint4 v = m[i];
@@ -24,6 +25,7 @@ __global__ void __launch_bounds__(256) combine_scatter_kernel(const uint4* __res
                                                               const uint32_t* __restrict__ best, uint32_t mmtol,
                                                               const uint32_t* __restrict__ rstart,
                                                               uint32_t* __restrict__ rfill, uint4* __restrict__ out) {
+  pdl_enter();
   const uint64_t n = min((uint64_t)*n_ptr, cap);
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint4 v = m[i];
@@ -46,6 +48,7 @@ __global__ void __launch_bounds__(256) segment_sort_short_kernel(uint4* __restri
                                                                  unsigned long long* __restrict__ n_long,
                                                                  uint32_t* __restrict__ mid_list,
                                                                  unsigned long long* __restrict__ n_mid) {
+  pdl_enter();
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   const uint32_t lo = rstart[r], hi = rstart[r + 1];
@@ -88,6 +91,7 @@ __global__ void __launch_bounds__(kRankThreads) segment_rank_sort_kernel(
     uint4* __restrict__ m, uint4* __restrict__ scratch, const uint32_t* __restrict__ rstart,
     const uint32_t* __restrict__ long_list, const unsigned long long* __restrict__ n_long,
     const uint32_t* __restrict__ mid_list, const unsigned long long* __restrict__ n_mid) {
+  pdl_enter();
   __shared__ uint64_t keys[kRankSmem];
   __shared__ uint2 rest[kRankSmem];
   const uint64_t nl = *n_long, nm = *n_mid;
@@ -167,12 +171,14 @@ __global__ void __launch_bounds__(kRankThreads) segment_rank_sort_kernel(
 // reads_sorted order, which is the order of the non-match fastq.
 __global__ void __launch_bounds__(256) nonmatch_flag_kernel(const uint32_t* __restrict__ best, uint64_t n_reads,
                                                             uint32_t no_match, uint32_t* __restrict__ flag) {
+  pdl_enter();
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < n_reads) flag[r] = best[r] == no_match ? 1u : 0u;
 }
 __global__ void __launch_bounds__(256) nonmatch_scatter_kernel(const uint32_t* __restrict__ flag,
                                                                const uint32_t* __restrict__ pos, uint64_t n_reads,
                                                                uint32_t* __restrict__ list) {
+  pdl_enter();
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < n_reads && flag[r]) list[pos[r]] = (uint32_t)r;
 }
@@ -181,6 +187,7 @@ __global__ void __launch_bounds__(256) nonmatch_scatter_kernel(const uint32_t* _
 __global__ void __launch_bounds__(256) overflow_flag_kernel(const uint32_t* __restrict__ pass_cnt, uint64_t n_slots,
                                                             unsigned long long max_matches,
                                                             uint8_t* __restrict__ slot_over) {
+  pdl_enter();
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_slots) slot_over[i] = (unsigned long long)pass_cnt[i] > max_matches ? 1 : 0;
 }
@@ -188,6 +195,7 @@ __global__ void __launch_bounds__(256) overflow_flag_kernel(const uint32_t* __re
 // best[read] = min nx over a match list (used after the host merged truncated groups back in).
 __global__ void __launch_bounds__(256) best_from_matches_kernel(const uint4* __restrict__ m, uint64_t n,
                                                                 uint32_t* __restrict__ best) {
+  pdl_enter();
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) atomicMin(best + m[i].x, m[i].w);
 }
@@ -199,6 +207,7 @@ __global__ void __launch_bounds__(256) overflow_count_kernel(const uint32_t* __r
                                                              unsigned long long max_matches,
                                                              const unsigned long long* __restrict__ n_pass,
                                                              unsigned long long* __restrict__ n_over) {
+  pdl_enter();
   if (*n_pass <= max_matches) return;  // no group can exceed MaxMatches (the usual case: nothing to read)
   uint32_t over = 0;  // n_slots is a power of two >= 1024: 16-byte loads
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots / 4; i += (uint64_t)gridDim.x * blockDim.x) {

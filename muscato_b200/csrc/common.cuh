@@ -162,6 +162,16 @@ __device__ __forceinline__ int64_t table_find(const uint64_t* __restrict__ tab_f
   }
 }
 
+// Programmatic dependent launch (PDL): every kernel of the pipeline starts with pdl_enter().  The
+// launch_dependents half lets the NEXT kernel of the stream be launched (its CTAs scheduled as
+// resources free up) while this grid is still running; the wait half blocks until the PREVIOUS
+// grid has completed and its memory is visible -- so data dependencies are exactly those of a plain
+// in-order stream, only the launch latency between two kernels is overlapped.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // One 256-bit read-only global load (sm_100: LDG.E.256) of a 32-byte aligned record.
 __device__ __forceinline__ void ldg256(const void* p, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d) {
   asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));

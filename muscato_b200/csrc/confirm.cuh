@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256) cand_prepare_kernel(const uint2* __restri
                                                            const uint32_t* __restrict__ blk2gene, int W,
                                                            const uint2* __restrict__ rmeta, uint64_t nwin_magic,
                                                            uint4* __restrict__ cinfo, uint32_t* __restrict__ sizes) {
+  pdl_enter();
   const uint64_t n_cand = min((uint64_t)*n_cand_ptr, cand_cap);
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint2 cd = cand[i];
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(256) pair_block_starts_kernel(const uint64_t* 
                                                                 uint64_t cand_cap,
                                                                 const unsigned long long* __restrict__ n_pairs_ptr,
                                                                 uint64_t block_cap, uint32_t* __restrict__ block_first) {
+  pdl_enter();
   const uint64_t n_cand = min((uint64_t)*n_cand_ptr, cand_cap);
   const uint64_t n_pairs = *n_pairs_ptr;
   if (n_pairs == 0) return;
@@ -345,6 +347,7 @@ constexpr int kOutStage = 128;  // per-warp output staging (records); flushed wh
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(256, MSC_CONFIRM_CTAS) confirm_pairs_kernel(const WinCfg cfg, const ConfirmArgs a) {
+  pdl_enter();
   __shared__ uint4 s_out[8][kOutStage];
   const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
   uint4* my_out = s_out[wid];

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t* __restri
                                                          int stride, int reads_per_block,
                                                          uint64_t* __restrict__ words, uint64_t* __restrict__ xplane,
                                                          uint32_t* __restrict__ len_flags) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t sm[];
   const uint64_t r0 = (uint64_t)blockIdx.x * (uint64_t)reads_per_block;
   const uint64_t r1 = min(r0 + (uint64_t)reads_per_block, n_reads);
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t* __restri
 __global__ void __launch_bounds__(256) validate_read_offsets_kernel(const uint64_t* __restrict__ offs, uint64_t n_reads,
                                                                     uint64_t total, uint64_t max_len,
                                                                     unsigned long long* __restrict__ bad) {
+  pdl_enter();
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_reads) return;
   const uint64_t a = offs[i], b = offs[i + 1];
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(256) pack_targets_kernel(const uint8_t* __rest
                                                            uint64_t* __restrict__ xplane,
                                                            uint32_t* __restrict__ xsum,
                                                            unsigned long long* __restrict__ any_x) {
+  pdl_enter();
   const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= n_words_alloc) return;
   const uint64_t b0 = w * 32;

@@ -47,6 +47,7 @@ struct FillJob {
 };
 
 __global__ void __launch_bounds__(256) fill_buffers_kernel(const FillJob job) {
+  pdl_enter();
   for (int j = 0; j < job.n; j++) {
     uint4* p = reinterpret_cast<uint4*>(job.ptr[j]);
     const unsigned long long n16 = job.bytes[j] >> 4;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_resident_kernel(const uint3
                                                                      unsigned long long* __restrict__ total_out,
                                                                      uint64_t* block_sums, unsigned long long* barrier,
                                                                      unsigned long long barrier_target) {
+  pdl_enter();
   __shared__ uint64_t warp_sums[kScanThreads / 32];
   __shared__ uint64_t s_total, s_off;
   const uint64_t n = scan_count(n_ptr, n_host);

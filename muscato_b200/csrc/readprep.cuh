@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256) prep_encode_kernel(const uint8_t* __restr
                                                           int min_len, int n_planes, uint8_t* __restrict__ planes,
                                                           uint32_t* __restrict__ keep,
                                                           unsigned long long* __restrict__ n_kept) {
+  pdl_enter();
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t k = 0;
   if (i < n) {
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(256) prep_encode_kernel(const uint8_t* __restr
 }
 
 __global__ void __launch_bounds__(256) iota_kernel(uint32_t* __restrict__ idx, uint64_t n) {
+  pdl_enter();
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) idx[i] = (uint32_t)i;
 }
@@ -75,6 +77,7 @@ __global__ void __launch_bounds__(256) iota_kernel(uint32_t* __restrict__ idx, u
 __global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(const uint32_t* __restrict__ idx,
                                                                    const uint8_t* __restrict__ plane, uint64_t n,
                                                                    uint32_t n_chunks, uint32_t* __restrict__ hist) {
+  pdl_enter();
   __shared__ uint32_t sh[256];
   sh[threadIdx.x] = 0;
   __syncthreads();
@@ -96,6 +99,7 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(const uint
                                                                       uint32_t n_chunks,
                                                                       const uint32_t* __restrict__ offsets,
                                                                       uint32_t* __restrict__ idx_out) {
+  pdl_enter();
   __shared__ uint32_t base[256];     // running output position of every digit for this chunk
   __shared__ uint32_t wh[8][256];    // per-warp digit counts of the current sub-tile -> exclusive positions
   const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
@@ -139,6 +143,7 @@ __global__ void __launch_bounds__(256) prep_heads_kernel(const uint32_t* __restr
                                                          const uint8_t* __restrict__ planes, uint64_t n,
                                                          const unsigned long long* __restrict__ n_kept_ptr,
                                                          int n_planes, uint32_t* __restrict__ head) {
+  pdl_enter();
   const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t n_kept = *n_kept_ptr;
   if (j >= n_kept) return;
@@ -161,6 +166,7 @@ __global__ void __launch_bounds__(256) prep_groups_kernel(const uint32_t* __rest
                                                           const unsigned long long* __restrict__ n_unique_ptr,
                                                           uint32_t* __restrict__ group_start,
                                                           uint32_t* __restrict__ ulen) {
+  pdl_enter();
   const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t n_kept = *n_kept_ptr;
   if (j == 0) group_start[*n_unique_ptr] = (uint32_t)n_kept;  // sentinel: end of the last group
@@ -182,6 +188,7 @@ __global__ void __launch_bounds__(256) prep_gather_kernel(const uint8_t* __restr
                                                           const uint64_t* __restrict__ uoffs,
                                                           const unsigned long long* __restrict__ n_unique_ptr,
                                                           uint8_t* __restrict__ out_ascii) {
+  pdl_enter();
   // one warp per unique read
   const uint64_t u = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = threadIdx.x & 31u;

@@ -72,6 +72,7 @@ __device__ __forceinline__ uint64_t window_at(uint64_t lo, uint64_t hi, unsigned
 // K32: W <= 16, the key arithmetic of phase 1 is 32 bit.  WN: number of competing m-mers.
 template <bool K32, int WN>
 __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel(const ScanArgs a) {
+  pdl_enter();
   __shared__ alignas(128) uint64_t tiles[kScanWarps][2][kWarpSmemWords];
   __shared__ alignas(8) uint64_t bars[kScanWarps][2];
   __shared__ uint16_t queue[kScanWarps][1024];
