@@ -156,50 +156,57 @@ Reads parse_reads_sorted(const std::string& text) {
   return r;
 }
 
-// prepReads = muscato_prep_reads | sort | muscato_uniqify (cmd/muscato/main.go:152-221).
-Reads prep_reads(const std::string& fastq, int min_len, int max_len) {
+// prepReads = muscato_prep_reads | sort | muscato_uniqify (cmd/muscato/main.go:152-221) with the
+// sort and the collapse of equal sequences done on the GPU (msc_prep_reads).  The host parses the
+// fastq records (utils/fastq.go:35-61), hands the raw sequences over, and joins counts and names
+// from the grouping the library returns: inside a group the `seq\tname` lines are in bytewise
+// name order, names longer than 1000 bytes are cut to 995 + "..." before sorting
+// (cmd/muscato_prep_reads/main.go:76-79), the name column is the text before its first tab and
+// the joined names are cut to 996 + "..." (cmd/muscato_uniqify/main.go:89-111).
+Reads prep_reads_device(msc_ctx* ctx, const std::string& fastq, int min_len, int max_len) {
   Lines L;
   L.text = fastq;
   L.split();
-  std::vector<std::string> recs;
-  for (size_t i = 0; i + 3 < L.ln.size() + 0 && i + 4 <= L.ln.size(); i += 4) {
-    std::string name(L.text, L.ln[i].first, L.ln[i].second);
-    std::string seq(L.text, L.ln[i + 1].first, L.ln[i + 1].second);
-    if ((int)seq.size() < min_len) continue;  // cmd/muscato_prep_reads/main.go:59-62
+  std::vector<std::string> names;
+  std::string raw;
+  std::vector<uint64_t> offs(1, 0);
+  for (size_t i = 0; i + 4 <= L.ln.size(); i += 4) {
+    names.emplace_back(L.text, L.ln[i].first, L.ln[i].second);
+    raw.append(L.text, L.ln[i + 1].first, L.ln[i + 1].second);
+    offs.push_back(raw.size());
+  }
+  const uint64_t n_raw = names.size();
+  uint64_t kept = 0, uniq = 0;
+  if (msc_prep_reads(ctx, reinterpret_cast<const uint8_t*>(raw.data()), offs.data(), n_raw, min_len, &kept, &uniq) != MSC_OK)
+    throw std::runtime_error(std::string("msc_prep_reads: ") + msc_last_error(ctx));
+  std::vector<uint32_t> perm(kept + 1), gs(uniq + 1);
+  if (msc_fetch_read_groups(ctx, perm.data(), gs.data()) != MSC_OK)
+    throw std::runtime_error(std::string("msc_fetch_read_groups: ") + msc_last_error(ctx));
+  Reads r;
+  std::vector<std::string> nm;
+  for (uint64_t u = 0; u < uniq; u++) {
+    nm.clear();
+    for (uint32_t j = gs[u]; j < gs[u + 1]; j++) {
+      std::string n = names[perm[j]];
+      if (n.size() > 1000) n = n.substr(0, 995) + "...";
+      nm.push_back(n);
+    }
+    std::sort(nm.begin(), nm.end());
+    std::string na;
+    for (size_t i = 0; i < nm.size(); i++) {
+      if (i) na += ';';
+      const size_t t = nm[i].find('\t');
+      na += t == std::string::npos ? nm[i] : nm[i].substr(0, t);  // bytes.Split(line, "\t")[1]
+    }
+    if (na.size() > 1000) na = na.substr(0, 996) + "...";
+    const uint32_t rep = perm[gs[u]];
+    std::string seq(raw, offs[rep], std::min<uint64_t>(offs[rep + 1] - offs[rep], (uint64_t)max_len));  // :67-69
     for (auto& ch : seq)
       if (ch != 'A' && ch != 'T' && ch != 'C' && ch != 'G') ch = 'X';  // subx :33-44
-    if ((int)seq.size() > max_len) seq.resize(max_len);                 // :67-69
-    if (name.size() > 1000) name = name.substr(0, 995) + "...";         // :76-79
-    recs.push_back(seq + "\t" + name);
-  }
-  std::sort(recs.begin(), recs.end());  // LC_ALL=C sort of whole lines
-  Reads r;
-  std::string cur;
-  std::vector<std::string> names;
-  bool have = false;
-  auto flush = [&]() {  // printrow, cmd/muscato_uniqify/main.go:89-111
-    std::string na;
-    for (size_t i = 0; i < names.size(); i++) { if (i) na += ';'; na += names[i]; }
-    if (na.size() > 1000) na = na.substr(0, 996) + "...";
-    r.seq.push_back(cur);
-    r.count.push_back(std::to_string(names.size()));
+    r.seq.push_back(seq);
+    r.count.push_back(std::to_string(nm.size()));
     r.names.push_back(na);
-  };
-  for (auto& rec : recs) {
-    const size_t t = rec.find('\t');
-    const std::string s = rec.substr(0, t);
-    std::string nm = rec.substr(t + 1);
-    const size_t t2 = nm.find('\t');
-    if (t2 != std::string::npos) nm.resize(t2);  // bytes.Split(line, "\t")[1]
-    if (!have || s != cur) {
-      if (have) flush();
-      cur = s;
-      names.clear();
-      have = true;
-    }
-    names.push_back(nm);
   }
-  if (have) flush();
   return r;
 }
 
@@ -289,16 +296,6 @@ int main(int argc, char** argv) {
     }
     const Cfg cfg = read_cfg(argv[1]);
 
-    Reads reads;
-    const std::string rs_path = cfg.TempDir + "/reads_sorted.txt.sz";
-    if (from_fastq) {
-      reads = prep_reads(szio::read_all(cfg.ReadFileName), cfg.MinReadLength, cfg.MaxReadLength);
-      std::string txt;
-      for (size_t i = 0; i < reads.seq.size(); i++) txt += reads.seq[i] + "\t" + reads.count[i] + "\t" + reads.names[i] + "\n";
-      szio::write_file(rs_path, txt, true);
-    } else {
-      reads = parse_reads_sorted(szio::read_text(rs_path));
-    }
     const std::vector<std::string> targets = parse_targets(szio::read_text(cfg.GeneFileName));
 
     msc_config mc;
@@ -325,11 +322,31 @@ int main(int argc, char** argv) {
         throw std::runtime_error(m);
       }
     };
-    {
+
+    Reads reads;
+    const std::string rs_path = cfg.TempDir + "/reads_sorted.txt.sz";
+    if (from_fastq) {
+      // prepReads with the sort / uniqify on the device; the unique reads are installed as the
+      // read set by msc_prep_reads itself
+      try {
+        reads = prep_reads_device(ctx, szio::read_all(cfg.ReadFileName), cfg.MinReadLength, cfg.MaxReadLength);
+      } catch (...) {
+        msc_destroy(ctx);
+        throw;
+      }
+      std::string txt;
+      for (size_t i = 0; i < reads.seq.size(); i++) txt += reads.seq[i] + "\t" + reads.count[i] + "\t" + reads.names[i] + "\n";
+      szio::write_file(rs_path, txt, true);
+    } else {
+      reads = parse_reads_sorted(szio::read_text(rs_path));
       std::string all;
       std::vector<uint64_t> offs;
       concat(reads.seq, all, offs);
       check(msc_set_reads(ctx, reinterpret_cast<const uint8_t*>(all.data()), offs.data(), reads.seq.size()), "msc_set_reads");
+    }
+    {
+      std::string all;
+      std::vector<uint64_t> offs;
       concat(targets, all, offs);
       check(msc_set_targets(ctx, reinterpret_cast<const uint8_t*>(all.data()), offs.data(), targets.size()), "msc_set_targets");
     }
