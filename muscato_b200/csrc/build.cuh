@@ -62,16 +62,22 @@ struct BuildArgs {
 // the number of distinct fingerprints is n_keys - n_dup: no per-warp counter atomics in the insert
 // kernel -- ~10^6 same-address atomics cost more than the inserts themselves.)
 
-constexpr int kInsertBatch = 2;  // table claims in flight per thread
+#ifndef MSC_INSERT_BATCH
+#define MSC_INSERT_BATCH 1
+#endif
+#ifndef MSC_INSERT_CTAS
+#define MSC_INSERT_CTAS 8
+#endif
+constexpr int kInsertBatch = MSC_INSERT_BATCH;  // home buckets in flight per thread
 
 // Pass A: one thread per read.  Which windows are valid (length rule + entropy rule), the
 // fingerprint of each valid window key, its Bloom bits, and the claim of its table slot: the
 // first item of a key group lives in the slot itself (most groups have exactly one member);
 // further members are flagged in dup_slot and scattered into the slot's CSR range by pass B.
-// The atomicCAS of up to kInsertBatch windows are issued before any of them is resolved -- the
-// build is bound by the round trip of those atomics, not by their number.
+// The home buckets (32 bytes, one 256-bit load each) of up to kInsertBatch windows are fetched
+// before any claim is made; a claim is then one atomicCAS on the first slot seen free.
 // item = read * nwin + window.
-__global__ void __launch_bounds__(256, 6) build_keys_insert_kernel(const WinCfg cfg, const BuildArgs a) {
+__global__ void __launch_bounds__(256, MSC_INSERT_CTAS) build_keys_insert_kernel(const WinCfg cfg, const BuildArgs a) {
   pdl_enter();
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t nk = 0;
@@ -82,17 +88,17 @@ __global__ void __launch_bounds__(256, 6) build_keys_insert_kernel(const WinCfg 
     const uint64_t* row = a.rd_words + r * (uint64_t)cfg.S;
     const uint64_t* xrow = a.rd_x + r * (uint64_t)cfg.S;
     const uint64_t kmask = low_bases_mask(cfg.W);
-    const uint64_t smask = (1ull << a.lg_slots) - 1ull;
+    const uint64_t bmask = (1ull << (a.lg_slots - 2)) - 1ull;
     uint32_t vm = 0;
     for (int k0 = 0; k0 < cfg.nwin; k0 += kInsertBatch) {
-      uint64_t fp[kInsertBatch], sl[kInsertBatch];
-      unsigned long long cur[kInsertBatch];
+      uint64_t fp[kInsertBatch], bk[kInsertBatch];
+      uint64_t q[kInsertBatch][4];
 #pragma unroll
       for (int u = 0; u < kInsertBatch; u++) {
         const int k = k0 + u;
         fp[u] = 0;
-        sl[u] = 0;
-        cur[u] = 0;
+        bk[u] = 0;
+        q[u][0] = q[u][1] = q[u][2] = q[u][3] = 0;
         if (k < cfg.nwin) {
           const int q1 = cfg.windows[k], q2 = q1 + cfg.W;
           if (L >= q2) {  // cmd/muscato_window_reads/main.go:109-112, cmd/muscato_screen/main.go:177-179
@@ -106,8 +112,8 @@ __global__ void __launch_bounds__(256, 6) build_keys_insert_kernel(const WinCfg 
               uint32_t mlo, mhi;
               bloom_locate(key, xm, fp[u], cfg.W, a.geom, widx, mlo, mhi);
               atomicOr(a.bloom + widx, (unsigned long long)mlo | ((unsigned long long)mhi << 32));
-              sl[u] = table_home(fp[u], a.lg_slots);
-              cur[u] = atomicCAS(reinterpret_cast<unsigned long long*>(a.tab_fp + sl[u]), 0ull, (unsigned long long)fp[u]);
+              bk[u] = table_home_bucket(fp[u], a.lg_slots);
+              ldcg256(a.tab_fp + (bk[u] << 2), q[u][0], q[u][1], q[u][2], q[u][3]);  // the home bucket as it stands
             }
           }
         }
@@ -119,15 +125,35 @@ __global__ void __launch_bounds__(256, 6) build_keys_insert_kernel(const WinCfg 
         const uint64_t item = r * (uint64_t)cfg.nwin + (uint64_t)k;
         uint32_t dup = 0;
         if (fp[u]) {
-          while (cur[u] != 0ull && cur[u] != fp[u]) {  // linear probing
-            sl[u] = (sl[u] + 1) & smask;
-            cur[u] = atomicCAS(reinterpret_cast<unsigned long long*>(a.tab_fp + sl[u]), 0ull, (unsigned long long)fp[u]);
+          // first slot of the probe sequence that holds fp (further member) or that this thread
+          // claims with a CAS (first member); a slot seen free may have been taken meanwhile --
+          // the CAS returns what is there now
+          int64_t slot = -1;
+          bool first = false;
+          while (slot < 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              if (slot >= 0) break;
+              uint64_t v = q[u][i];
+              if (v == 0ull)
+                v = atomicCAS(reinterpret_cast<unsigned long long*>(a.tab_fp + (bk[u] << 2) + i), 0ull, (unsigned long long)fp[u]);
+              if (v == 0ull) {
+                slot = (int64_t)((bk[u] << 2) + i);
+                first = true;
+              } else if (v == fp[u]) {
+                slot = (int64_t)((bk[u] << 2) + i);
+              }
+            }
+            if (slot < 0) {  // bucket full of other keys: next bucket
+              bk[u] = (bk[u] + 1) & bmask;
+              ldcg256(a.tab_fp + (bk[u] << 2), q[u][0], q[u][1], q[u][2], q[u][3]);
+            }
           }
-          if (cur[u] == 0ull) {
-            a.tab_item0[sl[u]] = (uint32_t)item;
+          if (first) {
+            a.tab_item0[slot] = (uint32_t)item;
           } else {
-            atomicAdd(a.tab_cnt + sl[u], 1u);
-            dup = (uint32_t)sl[u] + 1u;
+            atomicAdd(a.tab_cnt + slot, 1u);
+            dup = (uint32_t)slot + 1u;
           }
         }
         a.dup_slot[item] = dup;

@@ -31,7 +31,7 @@ __device__ __forceinline__ uint64_t extract32(const uint64_t* __restrict__ w, ui
 // ---------------------------------------------------------------------------
 // Window-key fingerprint.  A W<=32 window is 2W bits (key) plus its X mask (xm, same
 // spacing).  An X-free window's fingerprint is the key itself (+1, so that it is never 0): exact
-// and free; the table's home slot comes from one multiplicative hash (table_home).  Windows
+// and free; the table's home bucket comes from one multiplicative hash (table_home_bucket).  Windows
 // containing X mix the mask in.  fp only has to be free of false negatives: the confirm kernel
 // re-checks the window bases exactly (cmd/muscato_confirm/main.go:382-393 requires byte
 // equality), so the rare collisions (an X window with an X-free one, the all-G 32-mer with the
@@ -146,19 +146,47 @@ __host__ __device__ __forceinline__ void bloom_locate(uint64_t key, uint64_t xm,
     mhi = bloom_mask_hi(fp);
   }
 }
-__host__ __device__ __forceinline__ uint64_t table_home(uint64_t fp, int lg_slots) {
-  return (fp * 0x9E3779B97F4A7C15ull) >> (64 - lg_slots);
+// ---------------------------------------------------------------------------
+// Key table: open addressing over BUCKETS of four 64-bit fingerprints (32 bytes = one sector, read
+// with one 256-bit load).  A key lives in the first free slot of the first bucket of its probe
+// sequence that is not full (home bucket from one multiplicative hash, then linear); there are no
+// deletions, so a bucket with a free slot ends every look-up.  At the table's load factor (<= 0.5,
+// two keys per bucket on average) ~95 % of the look-ups and inserts touch exactly one sector.
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t table_home_bucket(uint64_t fp, int lg_slots) {
+  return (fp * 0x9E3779B97F4A7C15ull) >> (66 - lg_slots);  // lg_buckets = lg_slots - 2
 }
 
-// Open-addressing lookup (linear probing).  Returns slot or -1.
+// One 256-bit read-only global load (sm_100: LDG.E.256) of a 32-byte aligned record.
+__device__ __forceinline__ void ldg256(const void* p, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d) {
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+// The same through L2 only (.cg): for records that other SMs are updating with atomics.
+__device__ __forceinline__ void ldcg256(const void* p, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d) {
+  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+}
+
+// Position of fp in a bucket's four fingerprints: 0..3 = found, 4 = not here but the bucket has a
+// free slot (the key is not in the table), 5 = bucket full, go on.
+__device__ __forceinline__ int bucket_probe(uint64_t fp, uint64_t q0, uint64_t q1, uint64_t q2, uint64_t q3) {
+  if (q0 == fp) return 0;
+  if (q1 == fp) return 1;
+  if (q2 == fp) return 2;
+  if (q3 == fp) return 3;
+  return (q0 == 0ull) | (q1 == 0ull) | (q2 == 0ull) | (q3 == 0ull) ? 4 : 5;
+}
+
+// Look-up.  Returns slot (= 4 * bucket + position) or -1.
 __device__ __forceinline__ int64_t table_find(const uint64_t* __restrict__ tab_fp, int lg_slots, uint64_t fp) {
-  const uint64_t mask = (1ull << lg_slots) - 1ull;
-  uint64_t s = table_home(fp, lg_slots);
+  const uint64_t bmask = (1ull << (lg_slots - 2)) - 1ull;
+  uint64_t b = table_home_bucket(fp, lg_slots);
   while (true) {
-    const uint64_t cur = __ldg(tab_fp + s);
-    if (cur == fp) return (int64_t)s;
-    if (cur == 0) return -1;
-    s = (s + 1) & mask;
+    uint64_t q0, q1, q2, q3;
+    ldg256(tab_fp + (b << 2), q0, q1, q2, q3);
+    const int r = bucket_probe(fp, q0, q1, q2, q3);
+    if (r < 4) return (int64_t)((b << 2) + (uint64_t)r);
+    if (r == 4) return -1;
+    b = (b + 1) & bmask;
   }
 }
 
@@ -170,11 +198,6 @@ __device__ __forceinline__ int64_t table_find(const uint64_t* __restrict__ tab_f
 __device__ __forceinline__ void pdl_enter() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-
-// One 256-bit read-only global load (sm_100: LDG.E.256) of a 32-byte aligned record.
-__device__ __forceinline__ void ldg256(const void* p, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d) {
-  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
 
 // ---------------------------------------------------------------------------

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
   uint32_t phases = 0;
   int buf = 0;
   uint32_t n_pass = 0;
-  uint16_t* q = queue[warp];
+  uint16_t* q16 = queue[warp];
   uint2* st = stage[warp];
   uint32_t n_st = 0;  // staged candidates of this warp (warp-uniform)
   // One global atomic per flush instead of one per drain round: same-address atomics serialise.
@@ -211,44 +211,47 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
       while (m) {
         const uint32_t j = __ffs(m) - 1;
         m &= m - 1;
-        q[at++] = (uint16_t)((lane << 5) | j);
+        q16[at++] = (uint16_t)((lane << 5) | j);
       }
       __syncwarp();
       const uint64_t wbase = w0 * 32ull;  // first position of this warp tile
-      // kDrain table look-ups in flight per lane: the first probe of each is issued before any
-      // is resolved (the look-ups are independent; a single one costs an L2 / HBM round trip).
-      constexpr int kDrain = 4;
+      // kDrain table look-ups in flight per lane: the home bucket (four fingerprints, one 256-bit
+      // load) of each is fetched before any is resolved -- the look-ups are independent and a
+      // single one costs an L2 / HBM round trip.
+      constexpr int kDrain = 2;
+      const uint64_t bmask = (1ull << (a.lg_slots - 2)) - 1ull;
       for (uint32_t base = 0; base < total; base += 32 * kDrain) {
-        uint64_t fp[kDrain], cur[kDrain], sl[kDrain];
+        uint64_t fp[kDrain], bk[kDrain], q[kDrain][4];
         uint32_t e[kDrain];
-        const uint64_t smask = (1ull << a.lg_slots) - 1ull;
 #pragma unroll
         for (int u = 0; u < kDrain; u++) {
           const uint32_t idx = base + 32 * u + lane;
-          e[u] = idx < total ? q[idx] : 0xffffffffu;
+          e[u] = idx < total ? q16[idx] : 0xffffffffu;
           fp[u] = 0;
-          cur[u] = 0;
-          sl[u] = 0;
+          bk[u] = 0;
+          q[u][0] = q[u][1] = q[u][2] = q[u][3] = 0;
           if (e[u] != 0xffffffffu) {
             const unsigned src = e[u] >> 5, j = e[u] & 31u;
             uint64_t xm = 0;
             if ((xwords_all >> src) & 1u) xm = window_at(__ldg(a.tg_x + w0 + src), __ldg(a.tg_x + w0 + src + 1), j, kmask);
             fp[u] = key_fp(window_at(tile[src], tile[src + 1], j, kmask), xm);
-            sl[u] = table_home(fp[u], a.lg_slots);
-            cur[u] = __ldg(a.tab_fp + sl[u]);
+            bk[u] = table_home_bucket(fp[u], a.lg_slots);
+            ldg256(a.tab_fp + (bk[u] << 2), q[u][0], q[u][1], q[u][2], q[u][3]);
           }
         }
 #pragma unroll
         for (int u = 0; u < kDrain; u++) {
           if (base + 32 * u >= total) break;  // warp-uniform
-          while (cur[u] != fp[u] && cur[u] != 0ull) {  // linear probing (fp == 0 never enters: cur == 0)
-            sl[u] = (sl[u] + 1) & smask;
-            cur[u] = __ldg(a.tab_fp + sl[u]);
+          int r = fp[u] ? bucket_probe(fp[u], q[u][0], q[u][1], q[u][2], q[u][3]) : 4;
+          while (r == 5) {  // home bucket full of other keys (rare): walk on
+            bk[u] = (bk[u] + 1) & bmask;
+            ldg256(a.tab_fp + (bk[u] << 2), q[u][0], q[u][1], q[u][2], q[u][3]);
+            r = bucket_probe(fp[u], q[u][0], q[u][1], q[u][2], q[u][3]);
           }
-          const bool hit = cur[u] != 0ull;  // inactive lanes have cur == fp == 0
+          const bool hit = r < 4;
           const unsigned found = __ballot_sync(0xffffffffu, hit);
           if (found) {
-            if (hit) st[n_st + __popc(found & ((1u << lane) - 1u))] = make_uint2((uint32_t)sl[u], (uint32_t)(wbase + e[u]));
+            if (hit) st[n_st + __popc(found & ((1u << lane) - 1u))] = make_uint2((uint32_t)((bk[u] << 2) + r), (uint32_t)(wbase + e[u]));
             n_st += __popc(found);
             __syncwarp();
             if (n_st > kStageCap - 32) flush_stage();
