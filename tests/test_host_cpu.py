@@ -173,3 +173,43 @@ def test_cpp_executable_fails_loudly_without_gpu(tmp_path):
     r = subprocess.run([build.EXE_PATH, str(tmp_path / "config.json"), "--from-fastq"], capture_output=True, text=True)
     assert r.returncode != 0 and "CUDA" in r.stderr
     assert not os.path.exists(tmp_path / "result.txt")            # nothing is produced by a fallback
+
+
+def test_host_half_of_device_prep_reads():
+    """formats.uniqify_from_groups (the host half of msc_prep_reads) fed with the grouping a
+    bytewise sort produces must reproduce prepReads (prep_reads | sort | uniqify) exactly."""
+    import numpy as np
+    from muscato_b200 import formats
+    rng = np.random.default_rng(5)
+    recs = []
+    pool = []
+    for i in range(400):
+        if pool and rng.random() < 0.4:
+            s = pool[int(rng.integers(len(pool)))]
+            if rng.random() < 0.3:
+                s = s[: max(1, len(s) // 2)]
+        else:
+            s = helpers.random_dna(rng, int(rng.integers(5, 40)), b"ACGTN")
+        pool.append(s)
+        recs.append((b"@n%d\tx y" % int(rng.integers(50)), s))
+    fq = b"".join(n + b"\n" + s + b"\n+\n" + b"!" * len(s) + b"\n" for n, s in recs)
+    min_len, max_len = 8, 30
+    want = formats.prep_reads_uniqify(fq, min_len, max_len)
+    names, raw = formats.parse_fastq(fq)
+    # what the device returns: kept reads sorted by (X-substituted, truncated) sequence, group starts
+    def key(s):
+        return bytes(c if c in b"ATCG" else 0x58 for c in s[:max_len])
+    kept = [i for i, s in enumerate(raw) if len(s) >= min_len]
+    perm = sorted(kept, key=lambda i: key(raw[i]))
+    gs = [0]
+    for j in range(1, len(perm)):
+        if key(raw[perm[j]]) != key(raw[perm[j - 1]]):
+            gs.append(j)
+    gs.append(len(perm))
+    got = formats.uniqify_from_groups(names, raw, np.array(perm, dtype=np.uint32), np.array(gs, dtype=np.uint32), max_len)
+    assert got == want
+    # non-match fastq from ids == from matches
+    m = np.zeros(3, dtype=[("read_id", "u4"), ("gene_id", "u4"), ("pos", "u4"), ("nx", "u4")])
+    m["read_id"] = [0, 2, 2]
+    ids = np.setdiff1d(np.arange(len(want[0])), np.unique(m["read_id"]))
+    assert formats.nonmatch_fastq_from_ids(ids, *want) == formats.nonmatch_fastq(m, *want)
