@@ -90,17 +90,43 @@ __global__ void __launch_bounds__(kScanThreads) scan_resident_kernel(const uint3
   const uint64_t per = (((n + G - 1) / G) + 3) & ~3ull;  // slice length, multiple of 4
   const uint64_t lo = min(n, b * per), hi = min(n, lo + per);
 
+  // Small slices (up to 16 elements per thread, i.e. n <= ~1.2 M on 148 SMs): every thread keeps
+  // its 16 contiguous elements in registers across the grid barrier -- the input is read once.
+  constexpr int kRegItems = 16;
+  const bool in_regs = per <= (uint64_t)kScanThreads * kRegItems;
+  uint32_t rv[kRegItems];
+  uint64_t ex_in_block = 0;
+
   // phase 1: slice sum
   uint64_t s = 0;
-  for (uint64_t i = lo + (uint64_t)threadIdx.x * 4; i < hi; i += kScanTile) {
-    if (i + 4 <= hi) {
-      const uint4 v = *reinterpret_cast<const uint4*>(in + i);
+  if (in_regs) {
+    const uint64_t i0 = lo + (uint64_t)threadIdx.x * kRegItems;
+#pragma unroll
+    for (int q = 0; q < kRegItems; q += 4) {
+      const uint64_t i = i0 + q;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (i + 4 <= hi) {
+        v = *reinterpret_cast<const uint4*>(in + i);
+      } else if (i < hi) {
+        v.x = in[i];
+        if (i + 1 < hi) v.y = in[i + 1];
+        if (i + 2 < hi) v.z = in[i + 2];
+      }
+      rv[q] = v.x; rv[q + 1] = v.y; rv[q + 2] = v.z; rv[q + 3] = v.w;
       s += (uint64_t)v.x + v.y + v.z + v.w;
-    } else {
-      for (uint64_t j = i; j < hi; j++) s += in[j];
     }
+    ex_in_block = block_exclusive_scan_u64(s, &s_total, warp_sums);
+  } else {
+    for (uint64_t i = lo + (uint64_t)threadIdx.x * 4; i < hi; i += kScanTile) {
+      if (i + 4 <= hi) {
+        const uint4 v = *reinterpret_cast<const uint4*>(in + i);
+        s += (uint64_t)v.x + v.y + v.z + v.w;
+      } else {
+        for (uint64_t j = i; j < hi; j++) s += in[j];
+      }
+    }
+    (void)block_exclusive_scan_u64(s, &s_total, warp_sums);
   }
-  (void)block_exclusive_scan_u64(s, &s_total, warp_sums);
   if (threadIdx.x == 0) {
     *reinterpret_cast<volatile uint64_t*>(block_sums + b) = s_total;
     __threadfence();
@@ -122,11 +148,19 @@ __global__ void __launch_bounds__(kScanThreads) scan_resident_kernel(const uint3
     }
   }
   uint64_t run0 = s_off;
-  const uint64_t grand = s_total;
-  (void)grand;
   __syncthreads();
 
   // phase 3: scan of the slice
+  if (in_regs) {
+    const uint64_t i0 = lo + (uint64_t)threadIdx.x * kRegItems;
+    uint64_t run = run0 + ex_in_block;
+#pragma unroll
+    for (int q = 0; q < kRegItems; q++) {
+      if (i0 + q < hi) out[i0 + q] = (OutT)run;
+      run += rv[q];
+    }
+    return;
+  }
   for (uint64_t base = lo; base < hi; base += kScanTile) {
     const uint64_t i = base + (uint64_t)threadIdx.x * 4;
     uint32_t v[4] = {0u, 0u, 0u, 0u};
