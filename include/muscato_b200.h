@@ -20,7 +20,7 @@ extern "C" {
 #endif
 
 #define MSC_MAX_WINDOWS 32
-#define MSC_MAX_WINDOW_WIDTH 32
+#define MSC_MAX_WINDOW_WIDTH 50   /* wider windows are undefined in the reference (100 - q2 < W at target position 0) */
 #define MSC_MAX_READ_LENGTH 1024
 
 enum {

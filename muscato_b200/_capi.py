@@ -12,7 +12,7 @@ import os
 from .build import LIB_PATH
 
 MSC_MAX_WINDOWS = 32
-MSC_MAX_WINDOW_WIDTH = 32
+MSC_MAX_WINDOW_WIDTH = 50
 MSC_MAX_READ_LENGTH = 1024
 
 MSC_OK, MSC_ERR_CONFIG, MSC_ERR_INPUT, MSC_ERR_CUDA, MSC_ERR_STATE, MSC_ERR_NOMEM, MSC_ERR_IO = range(7)

@@ -452,24 +452,27 @@ void account_pack_targets(msc_ctx* ctx) {
 }
 
 // ---- enqueue: scan ---------------------------------------------------------------------------
-template <bool K32>
+template <int KW>
 void (*pick_scan_wn(int wn))(const ScanArgs) {
   switch (wn) {
-    case 1: return scan_targets_kernel<K32, 1>;
-    case 2: return scan_targets_kernel<K32, 2>;
-    case 3: return scan_targets_kernel<K32, 3>;
-    case 4: return scan_targets_kernel<K32, 4>;
-    case 5: return scan_targets_kernel<K32, 5>;
-    case 6: return scan_targets_kernel<K32, 6>;
-    case 7: return scan_targets_kernel<K32, 7>;
-    default: return scan_targets_kernel<K32, 8>;
+    case 1: return scan_targets_kernel<KW, 1>;
+    case 2: return scan_targets_kernel<KW, 2>;
+    case 3: return scan_targets_kernel<KW, 3>;
+    case 4: return scan_targets_kernel<KW, 4>;
+    case 5: return scan_targets_kernel<KW, 5>;
+    case 6: return scan_targets_kernel<KW, 6>;
+    case 7: return scan_targets_kernel<KW, 7>;
+    default: return scan_targets_kernel<KW, 8>;
   }
 }
-void (*pick_scan_kernel(bool k32, int wn))(const ScanArgs) { return k32 ? pick_scan_wn<true>(wn) : pick_scan_wn<false>(wn); }
+// W <= 16: 32-bit keys; W <= 32: one 64-bit key word; wider: two key words
+void (*pick_scan_kernel(int W, int wn))(const ScanArgs) {
+  return W <= 16 ? pick_scan_wn<0>(wn) : W <= 32 ? pick_scan_wn<1>(wn) : pick_scan_wn<2>(wn);
+}
 
 int enqueue_scan(msc_ctx* ctx) {
   if (ctx->cand.cap == 0) CK(ctx->cand.reserve(std::max<uint64_t>(1u << 20, ctx->n_bases / 16) * sizeof(uint2)));
-  void (*scan_fn)(const ScanArgs) = pick_scan_kernel(ctx->win.W <= 16, ctx->geom.wn);
+  void (*scan_fn)(const ScanArgs) = pick_scan_kernel(ctx->win.W, ctx->geom.wn);
   if (ctx->scan_grid == 0 || ctx->scan_fn_sized != (const void*)scan_fn) {
     int blocks_per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_fn, kScanBlock, 0));
@@ -797,7 +800,8 @@ msc_ctx* msc_create(const msc_config* config, char* errbuf, uint64_t errlen) {
   // checkArgs (cmd/muscato/main.go:851-858, :871-874): Windows, WindowWidth, MaxReadLength are mandatory.
   if (c.n_windows < 1 || c.n_windows > MSC_MAX_WINDOWS) return fail("Windows: need 1..32 window offsets");
   if (c.window_width < 1 || c.window_width > MSC_MAX_WINDOW_WIDTH)
-    return fail("WindowWidth must be in 1..32 (wider windows are not supported by this build)");
+    return fail("WindowWidth must be in 1..50 (beyond that the reference itself is undefined: 100 - q2 < WindowWidth at "
+                "target position 0, cmd/muscato_screen/main.go:305-313)");
   if (c.max_read_length < 1 || c.max_read_length > MSC_MAX_READ_LENGTH)
     return fail("MaxReadLength must be in 1..1024");
   for (int k = 0; k < c.n_windows; k++)

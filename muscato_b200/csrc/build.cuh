@@ -37,6 +37,23 @@ __device__ __forceinline__ int dinuc_count(uint64_t key, uint64_t xm, int W) {
   return __popc(seen);
 }
 
+// The same for a wide window (32 < W <= 64) held in two words.
+__device__ __forceinline__ int dinuc_count_wide(uint64_t k0, uint64_t k1, uint64_t x0, uint64_t x1, int W) {
+  auto sym = [&](int i) -> uint32_t {
+    const uint64_t k = i < 32 ? k0 : k1, x = i < 32 ? x0 : x1;
+    const int s = 2 * (i & 31);
+    return ((x >> s) & 1ull) ? 4u : (uint32_t)((k >> s) & 3ull);
+  };
+  uint32_t seen = 0;
+  uint32_t prev = sym(0);
+  for (int i = 1; i < W; i++) {
+    const uint32_t cur = sym(i);
+    seen |= 1u << (5u * prev + cur);
+    prev = cur;
+  }
+  return __popc(seen);
+}
+
 struct BuildArgs {
   // reads
   const uint64_t* rd_words;
@@ -87,7 +104,9 @@ __global__ void __launch_bounds__(256, MSC_INSERT_CTAS) build_keys_insert_kernel
     const bool hasx = lf >> 31;
     const uint64_t* row = a.rd_words + r * (uint64_t)cfg.S;
     const uint64_t* xrow = a.rd_x + r * (uint64_t)cfg.S;
-    const uint64_t kmask = low_bases_mask(cfg.W);
+    const bool wide = cfg.W > 32;
+    const uint64_t kmask = low_bases_mask(min(cfg.W, 32));
+    const uint64_t kmask1 = wide ? low_bases_mask(cfg.W - 32) : 0ull;
     const uint64_t bmask = (1ull << (a.lg_slots - 2)) - 1ull;
     uint32_t vm = 0;
     for (int k0 = 0; k0 < cfg.nwin; k0 += kInsertBatch) {
@@ -103,14 +122,22 @@ __global__ void __launch_bounds__(256, MSC_INSERT_CTAS) build_keys_insert_kernel
           const int q1 = cfg.windows[k], q2 = q1 + cfg.W;
           if (L >= q2) {  // cmd/muscato_window_reads/main.go:109-112, cmd/muscato_screen/main.go:177-179
             const uint64_t key = extract32(row, (uint64_t)q1) & kmask;
-            const uint64_t xm = hasx ? (extract32(xrow, (uint64_t)q1) & kmask) : 0ull;
-            if (cfg.min_dinuc <= 0 || dinuc_count(key, xm, cfg.W) >= cfg.min_dinuc) {  // :183-185 / :116-118
-              fp[u] = key_fp(key, xm);
+            const uint64_t xm0 = hasx ? (extract32(xrow, (uint64_t)q1) & kmask) : 0ull;
+            uint64_t key1 = 0, xm1 = 0;
+            if (wide) {  // bases 32..W-1 of the window
+              key1 = extract32(row, (uint64_t)q1 + 32) & kmask1;
+              xm1 = hasx ? (extract32(xrow, (uint64_t)q1 + 32) & kmask1) : 0ull;
+            }
+            const uint64_t xm = xm0 | xm1;
+            const int nd = cfg.min_dinuc <= 0 ? 0
+                           : wide ? dinuc_count_wide(key, key1, xm0, xm1, cfg.W) : dinuc_count(key, xm0, cfg.W);
+            if (cfg.min_dinuc <= 0 || nd >= cfg.min_dinuc) {  // :183-185 / :116-118
+              fp[u] = wide ? key_fp_wide(key, key1, xm0, xm1) : key_fp(key, xm0);
               vm |= 1u << k;
               nk++;
               uint64_t widx;
               uint32_t mlo, mhi;
-              bloom_locate(key, xm, fp[u], cfg.W, a.geom, widx, mlo, mhi);
+              bloom_locate(key, xm, fp[u], cfg.W, a.geom, widx, mlo, mhi, key1);
               atomicOr(a.bloom + widx, (unsigned long long)mlo | ((unsigned long long)mhi << 32));
               bk[u] = table_home_bucket(fp[u], a.lg_slots);
               ldcg256(a.tab_fp + (bk[u] << 2), q[u][0], q[u][1], q[u][2], q[u][3]);  // the home bucket as it stands

@@ -51,6 +51,20 @@ __host__ __device__ __forceinline__ uint64_t key_fp(uint64_t key, uint64_t xm) {
   return z ? z : 1ull;
 }
 
+// Wide windows (32 < W <= 64): the window is two words (bases 0..31 and 32..W-1, each with its X
+// mask); the fingerprint is a hash of all four, so it is never exact and the confirm kernel
+// always re-checks the window bases.
+__host__ __device__ __forceinline__ uint64_t key_fp_wide(uint64_t k0, uint64_t k1, uint64_t xm0, uint64_t xm1) {
+  uint64_t z = fmix64(k0 + 0x9E3779B97F4A7C15ull) ^ (fmix64(k1 ^ 0xD6E8FEB86659FD93ull) * 0xC2B2AE3D27D4EB4Full);
+  if (xm0 | xm1) z ^= fmix64(xm0 * 0xD6E8FEB86659FD93ull + xm1 * 0x9E3779B97F4A7C15ull + 1ull);
+  z = fmix64(z);
+  return z ? z : 1ull;
+}
+// What a wide key contributes to the 32-bit Bloom hash besides its first 16 bases.
+__host__ __device__ __forceinline__ uint32_t wide_khi(uint64_t k0, uint64_t k1) {
+  return (uint32_t)(k0 >> 32) ^ ((uint32_t)k1 * 0x9E3779B1u) ^ ((uint32_t)(k1 >> 32) * 0xC2B2AE35u);
+}
+
 // ---------------------------------------------------------------------------
 // Blocked Bloom front: one 64-bit word per key (a single 8-byte load per probed target
 // position), 2 bits in each 32-bit half.
@@ -130,13 +144,15 @@ __host__ __device__ __forceinline__ uint32_t bloom_sector_rt(uint32_t prex, int 
 }
 
 // Word index and the two 32-bit half masks of a key (build side and the scan's X path; the
-// scan's main path inlines the same arithmetic with WN as a template parameter).
+// scan's main path inlines the same arithmetic with WN as a template parameter).  key1 = bases
+// 32.. of a wide window (0 for W <= 32); xm = OR of the X masks of all its words.
 __host__ __device__ __forceinline__ void bloom_locate(uint64_t key, uint64_t xm, uint64_t fp, int W,
                                                       const BloomGeom& g, uint64_t& widx, uint32_t& mlo,
-                                                      uint32_t& mhi) {
+                                                      uint32_t& mhi, uint64_t key1 = 0ull) {
   if (xm == 0) {
     const uint32_t prex = (uint32_t)key ^ g.xr;
-    const uint32_t h = W <= 16 ? bloom_hash32<true>(prex, 0u) : bloom_hash32<false>(prex, (uint32_t)(key >> 32));
+    const uint32_t h = W <= 16 ? bloom_hash32<true>(prex, 0u)
+                               : bloom_hash32<false>(prex, W <= 32 ? (uint32_t)(key >> 32) : wide_khi(key, key1));
     const uint32_t sec = bloom_sector_rt(prex, g.wn, g.m, g.lg_words);
     widx = ((uint64_t)sec << 2) | (uint64_t)(h >> 30);
     bloom_masks32(h, mlo, mhi);

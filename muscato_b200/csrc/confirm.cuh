@@ -140,13 +140,43 @@ __device__ __forceinline__ uint64_t funnel64(uint64_t t0, uint64_t t1, unsigned 
   return (t0 >> sh) | ((t1 << 1) << (63u - sh));
 }
 
+// Exact equality of a read window with the target window that lies on it (bases and X masks),
+// in chunks of 32 bases (one chunk for W <= 32): the byte comparison of the merge join
+// (cmd/muscato_confirm/main.go:382-393).  rq / tq = first base of the window in the read row /
+// in the target stream.
+__device__ __forceinline__ bool window_match(const uint64_t* __restrict__ row, const uint64_t* __restrict__ xrow, bool rx,
+                                             const uint64_t* __restrict__ tg_words, const uint64_t* __restrict__ tg_x,
+                                             bool tx, uint64_t rq, uint64_t tq, int W) {
+  for (int off = 0; off < W; off += 32) {
+    const uint64_t mk = low_bases_mask(min(32, W - off));
+    if ((extract32(row, rq + off) & mk) != (extract32(tg_words, tq + off) & mk)) return false;
+    if (rx | tx) {
+      const uint64_t rxm = rx ? (extract32(xrow, rq + off) & mk) : 0ull;
+      const uint64_t txm = tx ? (extract32(tg_x, tq + off) & mk) : 0ull;
+      if (rxm != txm) return false;
+    }
+  }
+  return true;
+}
+
+// Fingerprint of window [rq, rq + W) of a read, as the table stores it (build_keys_insert_kernel).
+__device__ __forceinline__ uint64_t read_window_fp(const uint64_t* __restrict__ row, const uint64_t* __restrict__ xrow,
+                                                   bool rx, uint64_t rq, int W) {
+  const uint64_t mk = low_bases_mask(min(W, 32));
+  const uint64_t k0 = extract32(row, rq) & mk, x0 = rx ? (extract32(xrow, rq) & mk) : 0ull;
+  if (W <= 32) return key_fp(k0, x0);
+  const uint64_t mk1 = low_bases_mask(W - 32);
+  return key_fp_wide(k0, extract32(row, rq + 32) & mk1, x0, rx ? (extract32(xrow, rq + 32) & mk1) : 0ull);
+}
+
 // One (candidate, read) pair; c = index of its candidate.  MODE is a compile-time copy of
 // ConfirmArgs::mode so that the hot mode-0 kernel carries none of the tap / overflow code.
 // Returns true when the pair yields an output record (`rec`): a match (read, gene, pos, nx) in
 // modes 0/2, an exact-key candidate (gene, p, read, window) in mode 1.  n_pass counts pairs
 // that passed through their window (before cross-window de-duplication).
 //
-// Fast path (no X in the read or in the target range, W < 32): the table's fingerprints are
+// Fast path (no X in the read or in the target range, W < 32; wide windows, W > 32, always take the
+// re-check): the table's fingerprints are
 // exact there (common.cuh), so the window that produced the pair matches by construction and
 // the pair only needs the fit rule and the full-read mismatch count -- target words are loaded
 // once each (nwords + 1 loads) and funnel-shifted against the read's row.
@@ -203,21 +233,13 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
 
   const bool tx = targets_have_x && tg_range_has_x(a.xsum, gstart >> 5, ((gstart + (uint64_t)L) >> 5) + 1);
   const bool anyx = rx | tx;
-  const uint64_t kmask = low_bases_mask(W);
   const uint64_t* xrow = a.rd_x + (uint64_t)r * cfg.S;
 
   // Exact key equality for the window that produced this pair (merge join on the k-mer bytes,
   // cmd/muscato_confirm/main.go:382-393).  Fingerprints of X-free W<32 windows are exact, so only
-  // pairs that involve X (or W == 32) can be fingerprint collisions.
-  if (MODE == 1 || anyx || W == 32) {
-    const uint64_t rk = extract32(row, (uint64_t)q1) & kmask;
-    const uint64_t tk = extract32(a.tg_words, gpos) & kmask;
-    if (rk != tk) return false;
-    if (anyx) {
-      const uint64_t rxm = rx ? (extract32(xrow, (uint64_t)q1) & kmask) : 0ull;
-      const uint64_t txm = tx ? (extract32(a.tg_x, gpos) & kmask) : 0ull;
-      if (rxm != txm) return false;
-    }
+  // pairs that involve X (or W >= 32) can be fingerprint collisions.
+  if (MODE == 1 || anyx || W >= 32) {
+    if (!window_match(row, xrow, rx, a.tg_words, a.tg_x, tx, (uint64_t)q1, gpos, W)) return false;
     if (MODE == 1) {
       rec = make_uint4(cj.z, (uint32_t)p, r, (uint32_t)k);
       return true;
@@ -310,17 +332,10 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
     vm &= vm - 1;
     const int q1b = cfg.windows[k2];
     if (pos + q1b == 0 && (int64_t)L > lim0) continue;
-    const uint64_t rk = extract32(row, (uint64_t)q1b) & kmask;
-    const uint64_t tk = extract32(a.tg_words, gstart + (uint64_t)q1b) & kmask;
-    if (rk != tk) continue;
-    if (anyx) {
-      const uint64_t rxm = rx ? (extract32(xrow, (uint64_t)q1b) & kmask) : 0ull;
-      const uint64_t txm = tx ? (extract32(a.tg_x, gstart + (uint64_t)q1b) & kmask) : 0ull;
-      if (rxm != txm) continue;
-    }
+    if (!window_match(row, xrow, rx, a.tg_words, a.tg_x, tx, (uint64_t)q1b, gstart + (uint64_t)q1b, W)) continue;
     if (MODE == 2) {
       // a window whose key group is subject to truncation does not "own" the pair
-      const int64_t s2 = table_find(a.tab_fp, a.lg_slots, key_fp(rk, rx ? (extract32(xrow, (uint64_t)q1b) & kmask) : 0ull));
+      const int64_t s2 = table_find(a.tab_fp, a.lg_slots, read_window_fp(row, xrow, rx, (uint64_t)q1b, W));
       if (s2 >= 0 && a.slot_over[s2]) continue;
     }
     return false;  // an earlier window owns this pair

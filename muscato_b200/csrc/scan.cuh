@@ -69,8 +69,9 @@ __device__ __forceinline__ uint64_t window_at(uint64_t lo, uint64_t hi, unsigned
 //   phase 2  the warp compacts its passes into a shared-memory queue and drains it 32 at a time:
 //            lane i re-derives the key of queued position i with two shuffles, looks it up in the
 //            exact table, and the warp appends the found (slot, position) pairs with ONE atomic.
-// K32: W <= 16, the key arithmetic of phase 1 is 32 bit.  WN: number of competing m-mers.
-template <bool K32, int WN>
+// KW: 0 = W <= 16 (the key arithmetic of phase 1 is 32 bit), 1 = W <= 32, 2 = wide window
+// (32 < W <= 64, two key words).  WN: number of competing m-mers.
+template <int KW, int WN>
 __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel(const ScanArgs a) {
   pdl_enter();
   __shared__ alignas(128) uint64_t tiles[kScanWarps][2][kWarpSmemWords];
@@ -91,7 +92,10 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
   }
   __syncwarp();
 
-  const uint64_t kmask = low_bases_mask(a.W);
+  constexpr bool K32 = KW == 0;
+  constexpr bool WIDE = KW == 2;
+  const uint64_t kmask = low_bases_mask(min(a.W, 32));
+  const uint64_t kmask1 = WIDE ? low_bases_mask(a.W - 32) : 0ull;  // bases 32..W-1 of a wide window
   const uint32_t xr = a.geom.xr;
   const int gm = a.geom.m;
   const int lg_words = a.geom.lg_words;
@@ -142,7 +146,9 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
       const uint64_t w = w0 + (uint64_t)lane;
       const uint32_t xs0 = __ldg(a.xsum + (w >> 5));
       const uint32_t xs1 = __ldg(a.xsum + ((w + 1) >> 5));
-      xwords = __ballot_sync(0xffffffffu, ((xs0 >> (unsigned)(w & 31u)) | (xs1 >> (unsigned)((w + 1) & 31u))) & 1u);
+      uint32_t anyx = (xs0 >> (unsigned)(w & 31u)) | (xs1 >> (unsigned)((w + 1) & 31u));
+      if (WIDE) anyx |= __ldg(a.xsum + ((w + 2) >> 5)) >> (unsigned)((w + 2) & 31u);  // a wide window reaches word w + 2
+      xwords = __ballot_sync(0xffffffffu, anyx & 1u);
     }
     if (tile_words < 32) xwords &= (1u << tile_words) - 1u;
     const unsigned xwords_all = xwords;
@@ -163,7 +169,8 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
           } else {
             const uint64_t key = window_at(tile[wi], tile[wi + 1], lane, kmask);
             prex = (uint32_t)key ^ xr;
-            h[i] = bloom_hash32<false>(prex, (uint32_t)(key >> 32));
+            if (WIDE) h[i] = bloom_hash32<false>(prex, wide_khi(key, window_at(tile[wi + 1], tile[wi + 2], lane, kmask1)));
+            else h[i] = bloom_hash32<false>(prex, (uint32_t)(key >> 32));
           }
           const uint32_t sec = bloom_sector_of(bloom_min_mmer<WN>(prex, a.mul), gm, lg_words);
           bw[i] = __ldg(a.bloom + __funnelshift_l(h[i], sec, 2));  // (sec << 2) | (h >> 30)
@@ -182,10 +189,17 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
         const int wi = __ffs(xwords) - 1;
         xwords &= xwords - 1;
         const uint64_t xl = __ldg(a.tg_x + w0 + wi), xh = __ldg(a.tg_x + w0 + wi + 1);
-        const uint64_t key = window_at(tile[wi], tile[wi + 1], lane, kmask), xm = window_at(xl, xh, lane, kmask);
+        const uint64_t key = window_at(tile[wi], tile[wi + 1], lane, kmask), xm0 = window_at(xl, xh, lane, kmask);
+        uint64_t key1 = 0, xm1 = 0;
+        if (WIDE) {
+          key1 = window_at(tile[wi + 1], tile[wi + 2], lane, kmask1);
+          xm1 = window_at(xh, __ldg(a.tg_x + w0 + wi + 2), lane, kmask1);
+        }
+        const uint64_t xm = xm0 | xm1;
         uint64_t widx;
         uint32_t mlo, mhi;
-        bloom_locate(key, xm, xm ? key_fp(key, xm) : 0ull, a.W, a.geom, widx, mlo, mhi);
+        bloom_locate(key, xm, xm ? (WIDE ? key_fp_wide(key, key1, xm0, xm1) : key_fp(key, xm0)) : 0ull, a.W, a.geom, widx,
+                     mlo, mhi, key1);
         const uint2 bwx = __ldg(a.bloom + widx);
         const unsigned b = __ballot_sync(0xffffffffu, ((bwx.x & mlo) == mlo) & ((bwx.y & mhi) == mhi));
         if ((int)lane == wi) mask = b;
@@ -232,9 +246,16 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
           q[u][0] = q[u][1] = q[u][2] = q[u][3] = 0;
           if (e[u] != 0xffffffffu) {
             const unsigned src = e[u] >> 5, j = e[u] & 31u;
-            uint64_t xm = 0;
-            if ((xwords_all >> src) & 1u) xm = window_at(__ldg(a.tg_x + w0 + src), __ldg(a.tg_x + w0 + src + 1), j, kmask);
-            fp[u] = key_fp(window_at(tile[src], tile[src + 1], j, kmask), xm);
+            uint64_t xm = 0, xm1 = 0;
+            const bool hasx = (xwords_all >> src) & 1u;
+            if (hasx) xm = window_at(__ldg(a.tg_x + w0 + src), __ldg(a.tg_x + w0 + src + 1), j, kmask);
+            if (WIDE) {
+              if (hasx) xm1 = window_at(__ldg(a.tg_x + w0 + src + 1), __ldg(a.tg_x + w0 + src + 2), j, kmask1);
+              fp[u] = key_fp_wide(window_at(tile[src], tile[src + 1], j, kmask), window_at(tile[src + 1], tile[src + 2], j, kmask1),
+                                  xm, xm1);
+            } else {
+              fp[u] = key_fp(window_at(tile[src], tile[src + 1], j, kmask), xm);
+            }
             bk[u] = table_home_bucket(fp[u], a.lg_slots);
             ldg256(a.tab_fp + (bk[u] << 2), q[u][0], q[u][1], q[u][2], q[u][3]);
           }

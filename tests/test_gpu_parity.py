@@ -151,6 +151,11 @@ CASES = [
     ("w32_long", 32, [0, 40, 100], 200, 0.96, 4, 3, [200, 150, 133], 700, 0.02, 0.0),
     ("w20_unsorted_windows", 20, [30, 0, 10, 10], 150, 0.98, 0, 0, [150, 64, 45], 500, 0.01, 0.0),
     ("w7_lowcomplex", 7, [0, 7, 3], 64, 0.9, 0, 5, [64, 32, 21], 150, 0.03, 0.0),
+    # wide windows (two key words, hashed fingerprints, window re-checked in confirm)
+    ("w33_wide", 33, [0, 20, 50], 120, 0.95, 4, 2, [120, 90, 60], 400, 0.015, 0.0),
+    ("w40_wide_x", 40, [0, 45], 100, 0.94, 3, 1, [100, 88, 50], 350, 0.01, 0.01),
+    ("w50_wide_max", 50, [0, 25, 60], 150, 0.96, 0, 1, [150, 111, 64, 50], 500, 0.01, 0.0),
+    ("w36_wide_lowcomplex", 36, [0, 10], 80, 0.9, 2, 3, [80, 46, 40], 200, 0.02, 0.0),
 ]
 
 
@@ -158,7 +163,7 @@ CASES = [
 def test_random_cases_vs_oracle(case, tmp_path, oracle_bin):
     name, W, wins, mrl, pm, mind, mmtol, rlens, glen, sub, xr = case
     rng = np.random.default_rng(zlib.crc32(name.encode()))
-    alphabet = b"AC" if "lowcomplex" in name else b"ACGT"
+    alphabet = b"AC" if name == "w7_lowcomplex" else b"ACG" if "lowcomplex" in name else b"ACGT"
     n_genes = 30
     glens = [glen] * (n_genes - 4) + [W - 1, W, W + 3, max(W + 1, 20)]  # targets shorter than / equal to W
     reads, genes = _planted_case(rng, n_genes, glens, 300, rlens, sub, alphabet=alphabet, x_rate=xr)
@@ -250,7 +255,7 @@ def test_input_validation_errors():
         with pytest.raises(MuscatoError):
             hp.screen()                      # nothing set
     with pytest.raises(MuscatoError):
-        _engine(Config(Windows=[0], WindowWidth=40, MaxReadLength=100).apply_defaults())
+        _engine(Config(Windows=[0], WindowWidth=51, MaxReadLength=100).apply_defaults())
 
 
 @pytest.mark.parametrize("case", ["00", "03", "04"])
