@@ -84,6 +84,7 @@ enum Counter {
   C_NKEYS = 0, C_NGROUPS, C_NDUP, C_SCRATCH, C_NCAND, C_BLOOMPASS, C_NMATCH, C_NPASS, C_NOVER, C_NOUT, C_NPAIRS,
   C_PAD0, C_NLONG, C_PAD1, C_TGX,  // C_NLONG, C_TGX at even indices; C_TGX = "some target word has X"
   C_PAD2, C_PREP_KEPT, C_PREP_UNIQ, C_PREP_BYTES, C_PAD3,  // C_PREP_KEPT at an even index (16)
+  C_PREP_TIE, C_PAD4,                                      // C_PREP_TIE (20): longest unsorted run of prep_tiefix_kernel
   C_COUNT = 24  // groups that are cleared together start at even indices (16-byte aligned)
 };
 
@@ -149,9 +150,9 @@ struct msc_ctx {
   bool have_prep = false;
   DevBuf prep_perm, prep_gstart, nm_flag, nm_pos, nm_list;
   struct PrepTmp {  // scratch of msc_prep_reads, kept between calls
-    DevBuf d_raw, d_offs, planes, idx_a, idx_b, keep, hist, hoff, head, head_scan, ulen, uoffs;
+    DevBuf d_raw, d_offs, planes, key64, idx_a, idx_b, keep, hist, hoff, head, head_scan, ulen, uoffs;
     void release_all() {
-      DevBuf* t[] = {&d_raw, &d_offs, &planes, &idx_a, &idx_b, &keep, &hist, &hoff, &head, &head_scan, &ulen, &uoffs};
+      DevBuf* t[] = {&d_raw, &d_offs, &planes, &key64, &idx_a, &idx_b, &keep, &hist, &hoff, &head, &head_scan, &ulen, &uoffs};
       for (DevBuf* b : t) b->release();
     }
   } prep;
@@ -1082,6 +1083,7 @@ int msc_prep_reads(msc_ctx* ctx, const uint8_t* raw_ascii, const uint64_t* raw_o
   PCK(d_raw.reserve(total + 64));
   PCK(d_offs.reserve((n + 1) * sizeof(uint64_t)));
   PCK(planes.reserve((size_t)n_planes * std::max<uint64_t>(n, 1)));
+  PCK(ctx->prep.key64.reserve((n + 1) * sizeof(uint64_t)));
   PCK(idx_a.reserve((n + 1) * sizeof(uint32_t)));
   PCK(idx_b.reserve((n + 1) * sizeof(uint32_t)));
   PCK(keep.reserve((n + 1) * sizeof(uint32_t)));
@@ -1100,6 +1102,7 @@ int msc_prep_reads(msc_ctx* ctx, const uint8_t* raw_ascii, const uint64_t* raw_o
   {
     Filler f;
     f.add(ctx->ctr(C_PREP_KEPT), 4 * sizeof(unsigned long long));  // C_PREP_KEPT, C_PREP_UNIQ, C_PREP_BYTES, C_PAD3
+    f.add(ctx->ctr(C_PREP_TIE), 2 * sizeof(unsigned long long));   // C_PREP_TIE, C_PAD4
     PRC(enqueue_fill(ctx, f));
   }
   uint32_t* cur = idx_a.as<uint32_t>();
@@ -1107,22 +1110,43 @@ int msc_prep_reads(msc_ctx* ctx, const uint8_t* raw_ascii, const uint64_t* raw_o
   if (n) {
     launch_k(ctx->pdl, prep_encode_kernel, grid_for(n, 256), 256, 0, ctx->stream, d_raw.as<uint8_t>(), d_offs.as<uint64_t>(), n, MRL,
                                                                   (int)min_read_length, n_planes, planes.as<uint8_t>(),
-                                                                  keep.as<uint32_t>(), ctx->ctr(C_PREP_KEPT));
+                                                                  ctx->prep.key64.as<uint64_t>(), keep.as<uint32_t>(), ctx->ctr(C_PREP_KEPT));
     LAUNCH_CHECK();
-    launch_k(ctx->pdl, iota_kernel, grid_for(n, 256), 256, 0, ctx->stream, cur, n);
-    LAUNCH_CHECK();
-    // stable LSD radix sort of the read indices, one byte plane (two symbols) per pass
-    for (int b = n_planes - 1; b >= 0; b--) {
-      const uint8_t* plane = planes.as<uint8_t>() + (size_t)b * n;
-      launch_k(ctx->pdl, radix_hist_kernel, n_chunks, kRadixThreads, 0, ctx->stream, cur, plane, n, n_chunks, hist.as<uint32_t>());
+    // Stable LSD radix sort of the read indices, one byte plane (two symbols) per pass.  Fast
+    // path: sort on the first kPrePlanes planes (16 bases) only and let prep_tiefix_kernel order
+    // the short runs of equal prefix by the rest of the key; a run longer than kMaxTieRun (a
+    // sequence present in very many copies, or adversarial input) makes the call fall back to
+    // passes over all planes.
+    constexpr int kPrePlanes = 8;
+    auto radix_passes = [&](int first_plane_excl_hi) -> int {  // planes first_plane_excl_hi-1 .. 0
+      for (int b = first_plane_excl_hi - 1; b >= 0; b--) {
+        const uint8_t* plane = planes.as<uint8_t>() + (size_t)b * n;
+        launch_k(ctx->pdl, radix_hist_kernel, n_chunks, kRadixThreads, 0, ctx->stream, cur, plane, n, n_chunks, hist.as<uint32_t>());
+        LAUNCH_CHECK();
+        RC(enqueue_exclusive_scan<uint32_t>(ctx, hist.as<uint32_t>(), nullptr, (uint64_t)256 * n_chunks, hoff.as<uint32_t>(),
+                                            false, ctx->ctr(C_PAD3)));
+        launch_k(ctx->pdl, radix_scatter_kernel, n_chunks, kRadixThreads, 0, ctx->stream, cur, plane, n, n_chunks, hoff.as<uint32_t>(), nxt);
+        LAUNCH_CHECK();
+        std::swap(cur, nxt);
+      }
+      return MSC_OK;
+    };
+    bool full_sort = n_planes <= kPrePlanes || (getenv("MSC_PREP_FULL_SORT") && atoi(getenv("MSC_PREP_FULL_SORT")) > 0);
+    for (int attempt = 0; attempt < 2; attempt++) {
+      launch_k(ctx->pdl, iota_kernel, grid_for(n, 256), 256, 0, ctx->stream, cur, n);
       LAUNCH_CHECK();
-      PRC(enqueue_exclusive_scan<uint32_t>(ctx, hist.as<uint32_t>(), nullptr, (uint64_t)256 * n_chunks, hoff.as<uint32_t>(),
-                                           false, ctx->ctr(C_PAD3)));
-      launch_k(ctx->pdl, radix_scatter_kernel, n_chunks, kRadixThreads, 0, ctx->stream, cur, plane, n, n_chunks, hoff.as<uint32_t>(), nxt);
+      PRC(radix_passes(full_sort ? n_planes : kPrePlanes));
+      if (full_sort) break;
+      launch_k(ctx->pdl, prep_tiefix_kernel, grid_for(n, 256), 256, 0, ctx->stream, cur, planes.as<uint8_t>(),
+               ctx->prep.key64.as<uint64_t>(), n,
+               ctx->ctr(C_PREP_KEPT), kPrePlanes, n_planes, ctx->ctr(C_PREP_TIE));
       LAUNCH_CHECK();
-      std::swap(cur, nxt);
+      PRC(sync_counters(ctx));  // C_PREP_TIE = longest run that was left unsorted (0: none)
+      if (ctx->h_counters[C_PREP_TIE] == 0) break;
+      full_sort = true;
     }
-    launch_k(ctx->pdl, prep_heads_kernel, grid_for(n, 256), 256, 0, ctx->stream, cur, planes.as<uint8_t>(), n, ctx->ctr(C_PREP_KEPT), n_planes,
+    launch_k(ctx->pdl, prep_heads_kernel, grid_for(n, 256), 256, 0, ctx->stream, cur, planes.as<uint8_t>(),
+             ctx->prep.key64.as<uint64_t>(), n, ctx->ctr(C_PREP_KEPT), n_planes,
                                                                  head.as<uint32_t>());
     LAUNCH_CHECK();
     PRC(enqueue_exclusive_scan<uint32_t>(ctx, head.as<uint32_t>(), ctx->ctr(C_PREP_KEPT), n, head_scan.as<uint32_t>(), true,

@@ -33,7 +33,7 @@ __device__ __forceinline__ uint32_t prep_symbol(uint32_t c) {  // bytewise rank 
 __global__ void __launch_bounds__(256) prep_encode_kernel(const uint8_t* __restrict__ ascii,
                                                           const uint64_t* __restrict__ offs, uint64_t n, int max_len,
                                                           int min_len, int n_planes, uint8_t* __restrict__ planes,
-                                                          uint32_t* __restrict__ keep,
+                                                          uint64_t* __restrict__ key64, uint32_t* __restrict__ keep,
                                                           unsigned long long* __restrict__ n_kept) {
   pdl_enter();
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256) prep_encode_kernel(const uint8_t* __restr
     const int Lraw = (int)(offs[i + 1] - o);
     const bool kept = Lraw >= min_len;  // cmd/muscato_prep_reads/main.go:59-62 (tested before truncation)
     const int L = min(Lraw, max_len);
+    uint64_t k64 = 0;  // planes 0..7 (the first 16 symbols), most significant first: the tie test's prefix
     for (int b = 0; b < n_planes; b++) {
       uint32_t v = 0xFFu;
       if (kept) {
@@ -52,7 +53,10 @@ __global__ void __launch_bounds__(256) prep_encode_kernel(const uint8_t* __restr
         v = (hi << 4) | lo;
       }
       planes[(uint64_t)b * n + i] = (uint8_t)v;
+      if (b < 8) k64 |= (uint64_t)v << (56 - 8 * b);
     }
+    // (planes beyond n_planes stay 0 in k64: equal for all reads)
+    key64[i] = k64;
     keep[i] = kept ? 1u : 0u;
     k = kept ? 1u : 0u;
   }
@@ -138,9 +142,57 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(const uint
   }
 }
 
+// Tie fix after a sort on the first `n_pre` planes only: runs of equal prefix (almost always
+// duplicates or a handful of reads that share their first 2 * n_pre bases) are put in full-key
+// order by the thread that owns the run's first position (insertion sort, keys compared plane by
+// plane from n_pre on).  Runs longer than kMaxTieRun are left alone and reported through
+// `too_long`; the caller then falls back to a sort over all planes.
+constexpr int kMaxTieRun = 64;
+
+__device__ __forceinline__ bool prep_prefix_equal(const uint64_t* __restrict__ key64, uint32_t a, uint32_t b) {
+  return key64[a] == key64[b];  // the first 8 planes (n_pre == 8), packed by prep_encode_kernel
+}
+__device__ __forceinline__ bool prep_suffix_less(const uint8_t* __restrict__ planes, uint64_t n, int n_pre, int n_planes,
+                                                 uint32_t a, uint32_t b) {
+  for (int p = n_pre; p < n_planes; p++) {
+    const uint8_t ka = planes[(uint64_t)p * n + a], kb = planes[(uint64_t)p * n + b];
+    if (ka != kb) return ka < kb;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(256) prep_tiefix_kernel(uint32_t* __restrict__ idx, const uint8_t* __restrict__ planes,
+                                                          const uint64_t* __restrict__ key64, uint64_t n,
+                                                          const unsigned long long* __restrict__ n_kept_ptr,
+                                                          int n_pre, int n_planes,
+                                                          unsigned long long* __restrict__ too_long) {
+  pdl_enter();
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t n_kept = *n_kept_ptr;
+  if (j >= n_kept) return;
+  if (j > 0 && prep_prefix_equal(key64, idx[j], idx[j - 1])) return;  // not the first of its run
+  uint64_t len = 1;
+  while (j + len < n_kept && len <= (uint64_t)kMaxTieRun && prep_prefix_equal(key64, idx[j + len], idx[j])) len++;
+  if (len == 1) return;
+  if (len > (uint64_t)kMaxTieRun) {
+    atomicMax(too_long, (unsigned long long)len);
+    return;
+  }
+  for (uint64_t a = 1; a < len; a++) {  // stable insertion sort on the key suffix
+    const uint32_t v = idx[j + a];
+    uint64_t b = a;
+    while (b > 0 && prep_suffix_less(planes, n, n_pre, n_planes, v, idx[j + b - 1])) {
+      idx[j + b] = idx[j + b - 1];
+      b--;
+    }
+    idx[j + b] = v;
+  }
+}
+
 // head[j] = 1 when sorted position j starts a new sequence (compared over all key planes).
 __global__ void __launch_bounds__(256) prep_heads_kernel(const uint32_t* __restrict__ idx,
-                                                         const uint8_t* __restrict__ planes, uint64_t n,
+                                                         const uint8_t* __restrict__ planes,
+                                                         const uint64_t* __restrict__ key64, uint64_t n,
                                                          const unsigned long long* __restrict__ n_kept_ptr,
                                                          int n_planes, uint32_t* __restrict__ head) {
   pdl_enter();
@@ -150,9 +202,9 @@ __global__ void __launch_bounds__(256) prep_heads_kernel(const uint32_t* __restr
   uint32_t h = 1;
   if (j > 0) {
     const uint32_t a = idx[j], b = idx[j - 1];
-    h = 0;
-    for (int p = 0; p < n_planes; p++)
-      if (planes[(uint64_t)p * n + a] != planes[(uint64_t)p * n + b]) { h = 1; break; }
+    h = key64[a] != key64[b] ? 1u : 0u;  // planes 0..7 in one compare
+    for (int p = 8; p < n_planes && !h; p++)
+      if (planes[(uint64_t)p * n + a] != planes[(uint64_t)p * n + b]) h = 1;
   }
   head[j] = h;
 }

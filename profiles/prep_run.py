@@ -42,4 +42,5 @@ ok = bool(len(u) == uniq and np.array_equal(rep.view(np.dtype((np.void, L))).rav
 print(json.dumps({"n_raw": n, "n_kept": kept, "n_unique": uniq, "equals_numpy_unique": ok,
                   "msc_prep_reads_ms": round(1e3 * min(ts), 3), "device_sort_collapse_ms": round(st["ms_prep"], 3),
                   "device_pack_build_ms": round(st["ms_pack_reads"] + st["ms_build"], 3), "numpy_unique_s": round(np_s, 2),
-                  "note": "wall time of the call: H2D of the raw reads, encode, %d radix passes, collapse, gather, pack + key table" % ((L + 1) // 2)}))
+                  "note": "msc_prep_reads_ms = wall time of the call from pageable host memory (H2D of the raw reads included); "
+                          "device_sort_collapse_ms = encode + 8 radix passes on the first 16 bases + tie fix + collapse + gather"}))

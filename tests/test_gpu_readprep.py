@@ -106,6 +106,24 @@ def test_device_prep_equals_host_mirror_and_oracle(seed, n, min_l, max_l, mrl, m
         assert formats.load_reads_sorted(out["reads_sorted"]) == want
 
 
+@pytest.mark.parametrize("n_same,n_prefix", [(0, 40), (150, 30), (70, 0)])
+def test_device_prep_shared_prefixes_and_heavy_duplicates(n_same, n_prefix):
+    """Runs of equal 16-base prefix: short runs are ordered by the tie-fix kernel, a sequence present
+    in more than 64 copies makes msc_prep_reads fall back to the sort over all planes."""
+    rng = np.random.default_rng(100 + n_same + n_prefix)
+    pre = helpers.random_dna(rng, 20, b"ACGT")
+    recs = [(b"@a%d" % i, helpers.random_dna(rng, 60, b"ACGT")) for i in range(500)]
+    recs += [(b"@p%d" % i, pre + helpers.random_dna(rng, int(rng.integers(0, 45)), b"ACGT")) for i in range(n_prefix)]
+    same = pre + helpers.random_dna(rng, 40, b"ACGT")
+    recs += [(b"@s%d" % (i % 7), same) for i in range(n_same)]
+    order = rng.permutation(len(recs))
+    fq = b"".join(recs[i][0] + b"\n" + recs[i][1] + b"\n+\n" + b"!" * len(recs[i][1]) + b"\n" for i in order)
+    cfg = Config(Windows=[0], WindowWidth=12, MaxReadLength=64, MinReadLength=0).apply_defaults()
+    want = formats.prep_reads_uniqify(fq, cfg.MinReadLength, cfg.MaxReadLength)
+    with HotPath(cfg, device=0, keep_ascii=True) as hp:
+        assert device_prep(hp, fq, cfg) == want
+
+
 def test_device_prep_empty_and_all_skipped():
     cfg = Config(Windows=[0], WindowWidth=4, MaxReadLength=20, MinReadLength=10).apply_defaults()
     with HotPath(cfg, device=0, keep_ascii=True) as hp:
