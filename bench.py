@@ -273,15 +273,32 @@ def run_ours(args, rank, local_rank, world):
             dist.all_reduce(best, op=dist.ReduceOp.MIN)
             torch.cuda.synchronize()
 
+    ext_stream = torch.cuda.ExternalStream(hp.stream(), device=dev) if world > 1 else None
+
     def step_resident():
         if world == 1:
             # device pack of reads + key table + Bloom, device pack of targets, scan, expansion,
             # confirm, combine: one enqueue, one synchronisation
             hp.rebuild_and_run(3)
             return
-        hp.run_stages(3, 1 | 2)   # rebuild + screen + confirm, one sync
-        exchange_best()           # NCCL MIN all-reduce of the per-read best mismatch count
-        hp.run_stages(0, 4)       # combine
+        # Stream-ordered: rebuild + screen + confirm are only enqueued (MSC_STAGE_DEFER = 8), the NCCL
+        # MIN all-reduce of the per-read best mismatch count is ordered behind them on the library's
+        # own stream, combine follows; ONE host synchronisation per step, as on a single GPU.  The
+        # first step takes the synchronising path: it sizes the output buffers, after which the
+        # deferred path cannot ask for a repeat on the same input.
+        if not defer_ok[0]:
+            hp.run_stages(3, 1 | 2)   # rebuild + screen + confirm, one sync
+            exchange_best()           # NCCL MIN all-reduce of the per-read best mismatch count
+            hp.run_stages(0, 4)       # combine
+            defer_ok[0] = True
+            return
+        hp.run_stages(3, 1 | 2 | 8)
+        best = torch.as_tensor(hp.best_device(), device=dev)
+        with torch.cuda.stream(ext_stream):
+            dist.all_reduce(best, op=dist.ReduceOp.MIN)
+        hp.run_stages(0, 4)           # raises on MSC_ERR_AGAIN (cannot happen after the sizing step)
+
+    defer_ok = [False]
 
     if world > 1:
         d_rd_a = torch.empty(rd_a.numel(), dtype=torch.uint8, device=dev)
@@ -302,6 +319,12 @@ def run_ours(args, rank, local_rank, world):
         hp.set_targets_ptr(tg_a.data_ptr(), tg_o.data_ptr(), n_tg)
         if world == 1:
             hp.run()
+        elif defer_ok[0]:
+            hp.run_stages(0, 1 | 2 | 8)   # stream-ordered, see step_resident
+            best = torch.as_tensor(hp.best_device(), device=dev)
+            with torch.cuda.stream(ext_stream):
+                dist.all_reduce(best, op=dist.ReduceOp.MIN)
+            hp.run_stages(0, 4)
         else:
             hp.run_stages(0, 1 | 2)
             exchange_best()

@@ -30,7 +30,8 @@ enum {
   MSC_ERR_CUDA = 3,     /* CUDA runtime failure (message in msc_last_error) */
   MSC_ERR_STATE = 4,    /* call order violated (e.g. screen before set_reads) */
   MSC_ERR_NOMEM = 5,
-  MSC_ERR_IO = 6
+  MSC_ERR_IO = 6,
+  MSC_ERR_AGAIN = 7     /* a deferred run has to be repeated (see MSC_STAGE_DEFER) */
 };
 
 enum { MSC_MATCH_FIRST = 0, MSC_MATCH_BEST = 1 };
@@ -195,8 +196,17 @@ int msc_rebuild_and_run(msc_ctx* ctx, int what);
 /* General form: optional rebuild (what = 0..3) followed by any prefix-consistent subset of the
  * stages, one synchronisation.  A multi-GPU host runs SCREEN|CONFIRM, all-reduces
  * msc_best_device over the ranks, then runs COMBINE. */
-enum { MSC_STAGE_SCREEN = 1, MSC_STAGE_CONFIRM = 2, MSC_STAGE_COMBINE = 4 };
+enum { MSC_STAGE_SCREEN = 1, MSC_STAGE_CONFIRM = 2, MSC_STAGE_COMBINE = 4, MSC_STAGE_DEFER = 8 };
 int msc_run_stages(msc_ctx* ctx, int rebuild_what, int stages);
+
+/* Stream-ordered multi-GPU step (no host round trip between the stages): with
+ * SCREEN | CONFIRM | DEFER the stages are only ENQUEUED on msc_stream(ctx); the host orders its
+ * NCCL MIN all-reduce of msc_best_device(ctx) after them on the same stream (or a stream that
+ * waits on it) and then calls msc_run_stages(ctx, 0, MSC_STAGE_COMBINE), which enqueues the combine,
+ * synchronises ONCE and completes all three stages.  If a bounded output buffer turned out too
+ * small (it has been grown) or a key group exceeds MaxMatches, that call returns MSC_ERR_AGAIN and
+ * the caller repeats the sequence (in the MaxMatches case without MSC_STAGE_DEFER). */
+void* msc_stream(msc_ctx* ctx);   /* the cudaStream_t every kernel of the context runs on */
 
 /* Per-stage timers (ms_pack_reads .. ms_combine) cost one event record between kernels per stage
  * boundary (~2.5 us each on a B200); on = 0 leaves them out -- ms_scan / ms_scan_kernel are always

@@ -15,10 +15,10 @@ MSC_MAX_WINDOWS = 32
 MSC_MAX_WINDOW_WIDTH = 50
 MSC_MAX_READ_LENGTH = 1024
 
-MSC_OK, MSC_ERR_CONFIG, MSC_ERR_INPUT, MSC_ERR_CUDA, MSC_ERR_STATE, MSC_ERR_NOMEM, MSC_ERR_IO = range(7)
+MSC_OK, MSC_ERR_CONFIG, MSC_ERR_INPUT, MSC_ERR_CUDA, MSC_ERR_STATE, MSC_ERR_NOMEM, MSC_ERR_IO, MSC_ERR_AGAIN = range(8)
 MSC_MATCH_FIRST, MSC_MATCH_BEST = 0, 1
 MSC_NO_MATCH = 0x7F7F7F7F
-MSC_STAGE_SCREEN, MSC_STAGE_CONFIRM, MSC_STAGE_COMBINE = 1, 2, 4
+MSC_STAGE_SCREEN, MSC_STAGE_CONFIRM, MSC_STAGE_COMBINE, MSC_STAGE_DEFER = 1, 2, 4, 8
 
 
 class msc_config(C.Structure):
@@ -86,6 +86,7 @@ _SIGS = [
     ("msc_screen", C.c_int, [C.c_void_p]),
     ("msc_confirm", C.c_int, [C.c_void_p]),
     ("msc_best_device", C.c_void_p, [C.c_void_p]),
+    ("msc_stream", C.c_void_p, [C.c_void_p]),
     ("msc_combine", C.c_int, [C.c_void_p]),
     ("msc_matches_device", C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),
     ("msc_fetch_matches", C.c_int, [C.c_void_p, C.POINTER(C.POINTER(msc_match)), C.POINTER(C.c_uint64)]),

@@ -138,6 +138,9 @@ struct msc_ctx {
   // matches
   uint64_t n_match_pre = 0, n_match = 0;
   bool have_confirm = false, have_combine = false;
+  // MSC_STAGE_DEFER: screen + confirm were enqueued without a host synchronisation; they are
+  // completed (counters read, buffers checked) by the next call that synchronises
+  bool deferred = false;
   DevBuf match_pre, best, rcount, rstart, rfill, match_out, long_list, mid_list;
   // confirm kernel mode 2 (MaxMatches overflow groups diverted to the host)
   struct {
@@ -727,7 +730,31 @@ int mark_expand_start(msc_ctx* ctx) {
 
 // [rebuild +] screen [+ confirm + combine] with a single synchronisation; repeated from the
 // scan when a buffer had to grow.
-int run_pipeline(msc_ctx* ctx, int rebuild_what, bool do_scan, bool do_confirm, bool do_combine) {
+int run_pipeline(msc_ctx* ctx, int rebuild_what, bool do_scan, bool do_confirm, bool do_combine, bool defer = false) {
+  if (ctx->deferred) {
+    // a deferred screen + confirm is in flight: the only continuation is combine (+ its completion)
+    if (!do_combine || do_scan || do_confirm || rebuild_what || defer) {
+      ctx->deferred = false;  // drop the pending run: the context goes back to "inputs set"
+      RC(sync_counters(ctx));
+      ctx->have_cand = ctx->have_confirm = ctx->have_combine = false;
+      return ctx->fail(MSC_ERR_STATE, "a deferred screen/confirm was pending: only the combine stage may follow it (dropped)");
+    }
+    ctx->deferred = false;
+    RC(enqueue_combine(ctx));
+    RC(sync_counters(ctx));
+    int rc = finish_scan(ctx);
+    if (rc == MSC_OK) rc = finish_confirm(ctx);
+    if (rc == MSC_OK) rc = finish_combine(ctx);
+    if (rc == NEED_RETRY || rc == NEED_RECOMBINE) {
+      // a buffer was grown, or MaxMatches truncation had to rewrite the matches: what was exchanged
+      // between the stages is stale -- the caller repeats the sequence (without MSC_STAGE_DEFER when
+      // groups overflow MaxMatches)
+      ctx->have_cand = ctx->have_confirm = ctx->have_combine = false;
+      return ctx->fail(MSC_ERR_AGAIN, "deferred run must be repeated (%s)",
+                       rc == NEED_RETRY ? "an output buffer was grown" : "MaxMatches truncation applies: run without MSC_STAGE_DEFER");
+    }
+    return rc;
+  }
   // Fused run: all zero-fills of the stages below in one prologue launch.
   if ((int)((rebuild_what & 1) != 0) + (int)((rebuild_what & 2) != 0) + (int)do_scan + (int)do_confirm + (int)do_combine > 1) {
     Filler f;
@@ -755,6 +782,10 @@ int run_pipeline(msc_ctx* ctx, int rebuild_what, bool do_scan, bool do_confirm, 
       RC(enqueue_pairs(ctx, 0, ctx->match_pre));
     }
     if (do_combine) RC(enqueue_combine(ctx));
+    if (defer) {  // no host synchronisation: completed by the combine call that follows
+      ctx->deferred = true;
+      return MSC_OK;
+    }
     RC(sync_counters(ctx));
     int rc = MSC_OK;
     if (do_scan) rc = finish_scan(ctx);
@@ -1298,7 +1329,9 @@ int msc_confirm(msc_ctx* ctx) {
   return run_pipeline(ctx, 0, false, true, false);
 }
 
-void* msc_best_device(msc_ctx* ctx) { return (ctx && ctx->have_confirm) ? ctx->best.p : nullptr; }
+void* msc_best_device(msc_ctx* ctx) { return (ctx && (ctx->have_confirm || ctx->deferred)) ? ctx->best.p : nullptr; }
+
+void* msc_stream(msc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 void* msc_matches_device(msc_ctx* ctx, uint64_t* n) {
   if (!ctx || !ctx->have_combine) return nullptr;
@@ -1326,12 +1359,15 @@ int msc_run_stages(msc_ctx* ctx, int rebuild_what, int stages) {
   if (!ctx->have_reads || !ctx->have_targets) return ctx->fail(MSC_ERR_STATE, "msc_run_stages: set reads and targets first");
   if ((rebuild_what & 3) && !ctx->cfg.keep_ascii) return ctx->fail(MSC_ERR_STATE, "rebuild needs keep_ascii=1");
   const bool scan = stages & MSC_STAGE_SCREEN, conf = stages & MSC_STAGE_CONFIRM, comb = stages & MSC_STAGE_COMBINE;
+  const bool defer = stages & MSC_STAGE_DEFER;
+  if (defer && (!scan || !conf || comb))
+    return ctx->fail(MSC_ERR_STATE, "MSC_STAGE_DEFER goes with SCREEN | CONFIRM (combine follows in its own call)");
   if (conf && !scan && (!ctx->have_cand || (rebuild_what & 3)))
     return ctx->fail(MSC_ERR_STATE, "msc_run_stages: confirm needs candidates (run the screen stage)");
-  if (comb && !conf && (!ctx->have_confirm || scan || (rebuild_what & 3)))
+  if (comb && !conf && !ctx->deferred && (!ctx->have_confirm || scan || (rebuild_what & 3)))
     return ctx->fail(MSC_ERR_STATE, "msc_run_stages: combine needs confirmed pairs");
   CK(cudaSetDevice(ctx->device));
-  return run_pipeline(ctx, rebuild_what & 3, scan, conf, comb);
+  return run_pipeline(ctx, rebuild_what & 3, scan, conf, comb, defer);
 }
 
 int msc_rebuild_and_run(msc_ctx* ctx, int what) {

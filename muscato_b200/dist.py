@@ -37,6 +37,32 @@ def allreduce_best(best, group=None):
     return best
 
 
+def sharded_step(hp, rebuild_what: int = 0, group=None, deferred: bool = True):
+    """One hot-path step over this rank's target shard: screen + confirm, MIN all-reduce of the
+    per-read best array, combine.  deferred=True is the stream-ordered form (MSC_STAGE_DEFER): the
+    stages are only enqueued on the context's stream, the all-reduce is ordered behind them on that
+    stream and the combine call synchronises once.  Use deferred=False for the first step on new
+    inputs (it sizes the bounded output buffers, so that a deferred step cannot ask for a repeat)."""
+    import torch
+    import torch.distributed as dist
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    if not multi:
+        hp.run_stages(rebuild_what, 1 | 2 | 4)
+        return
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if deferred:
+        hp.run_stages(rebuild_what, 1 | 2 | 8)
+        best = torch.as_tensor(hp.best_device(), device=dev)
+        with torch.cuda.stream(torch.cuda.ExternalStream(hp.stream(), device=dev)):
+            dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
+    else:
+        hp.run_stages(rebuild_what, 1 | 2)
+        best = torch.as_tensor(hp.best_device(), device=dev)
+        dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
+        torch.cuda.synchronize()
+    hp.run_stages(0, 4)
+
+
 def gather_matches(local, gene_offset: int, dst: int = 0, group=None):
     """local: int32 tensor [n, 4] = (read, gene, pos, nx) with shard-local gene ids.
     Returns on rank `dst` the concatenation over ranks with global gene ids (else None)."""

@@ -157,6 +157,10 @@ class HotPath:
     def rebuild_and_run(self, what: int = 3):
         self._check(self._lib.msc_rebuild_and_run(self._ctx, what))
 
+    def stream(self) -> int:
+        """The cudaStream_t (as an integer) every kernel of this context runs on."""
+        return int(self._lib.msc_stream(self._ctx) or 0)
+
     def best_device(self) -> _DevArray:
         ptr = self._lib.msc_best_device(self._ctx)
         if not ptr:

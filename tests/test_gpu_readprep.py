@@ -134,3 +134,28 @@ def test_device_prep_empty_and_all_skipped():
         hp.set_targets([b"ACGTACGTACGTACGTACGTACGT"])
         hp.run()
         assert len(hp.fetch()) == 0
+
+
+def test_deferred_stages_equal_fused_run():
+    """MSC_STAGE_DEFER (stream-ordered multi-GPU step): screen + confirm enqueued without a host
+    synchronisation, combine completes all three -- same matches as msc_run; a pending deferred
+    run only accepts the combine stage."""
+    from muscato_b200.engine import MuscatoError
+    rng = np.random.default_rng(3)
+    genes = [helpers.random_dna(rng, 300, b"ACGT") for _ in range(20)]
+    reads = sorted({g[i:i + 60] for g in genes for i in range(0, 240, 7)})
+    cfg = Config(Windows=[0, 20], WindowWidth=12, MaxReadLength=60, PMatch=0.95, MinDinuc=0, MMTol=1).apply_defaults()
+    with HotPath(cfg, device=0, keep_ascii=True) as hp:
+        hp.set_reads(reads)
+        hp.set_targets(genes)
+        hp.run()
+        want = hp.fetch()
+        for _ in range(2):
+            hp.run_stages(3, 1 | 2 | 8)
+            assert hp.best_device() is not None
+            with pytest.raises(MuscatoError):
+                hp.run_stages(0, 1)          # only combine may follow
+            hp.run_stages(3, 1 | 2 | 8)      # the failed call cleared nothing it should not: start over
+            hp.run_stages(0, 4)
+            got = hp.fetch()
+            assert np.array_equal(got, want)
