@@ -282,7 +282,7 @@ void add_reads_fills(msc_ctx* ctx, Filler& f) {
   f.add(ctx->tab_fp.p, slots * sizeof(uint64_t));
   f.add(ctx->tab_cnt.p, slots * sizeof(uint32_t));
   f.add(ctx->tab_fill.p, slots * sizeof(uint32_t));
-  f.add(ctx->bloom.p, (1ull << ctx->lg_bloom) * sizeof(uint64_t));  // window_keys_kernel sets the bits
+  f.add(ctx->bloom.p, (1ull << ctx->lg_bloom) * sizeof(uint64_t));  // build_keys_insert_kernel sets the bits
 }
 void add_targets_fills(msc_ctx* ctx, Filler& f) {
   f.add(ctx->tg_x.p, ctx->n_words_alloc * sizeof(uint64_t));

@@ -77,7 +77,7 @@ __host__ __device__ __forceinline__ uint32_t wide_khi(uint64_t k0, uint64_t k1) 
 // and a warp that probes 32 consecutive positions touches ~32*2/(wn+1) sectors instead of 32.
 // The word inside the sector and the bit positions come from a cheap 32-bit hash of the whole
 // key.  Keys whose window contains X (xm != 0) are addressed by their fingerprint instead (no
-// locality; rare).  The filter only has to be free of false negatives: build (window_keys_kernel)
+// locality; rare).  The filter only has to be free of false negatives: build (build_keys_insert_kernel)
 // and scan use the same functions below.
 // ---------------------------------------------------------------------------
 struct BloomGeom {
