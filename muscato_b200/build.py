@@ -61,7 +61,7 @@ def build_host_exe() -> str:
     """The stage-compatible C++ executable (host text I/O above the C ABI), linked against the library."""
     os.makedirs(os.path.dirname(EXE_PATH), exist_ok=True)
     cxx = shutil.which("g++") or "g++"
-    cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-o", EXE_PATH,
+    cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-pthread", "-o", EXE_PATH,
            os.path.join(CSRC, "host", "muscato_b200_hotpath.cc"),
            "-L" + HERE, "-lmuscato_b200", "-Wl,-rpath,$ORIGIN/.."]
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -286,6 +286,13 @@ int main(int argc, char** argv) {
       szio::write_file(argv[3], szio::read_all(argv[2]), true);
       return 0;
     }
+    if (!strcmp(argv[1], "--sz-cat")) {  // decode a .sz file to stdout (no GPU involved): muscato_b200_hotpath --sz-cat FILE [threads]
+      if (argc < 3) throw std::runtime_error("--sz-cat needs a file");
+      const std::string raw = szio::read_all(argv[2]);
+      const std::string txt = szio::is_framed(raw) ? szio::decompress(raw, argc > 3 ? (unsigned)atoi(argv[3]) : 0u) : raw;
+      fwrite(txt.data(), 1, txt.size(), stdout);
+      return 0;
+    }
     int device = 0;
     bool from_fastq = false, epilogue = true;
     for (int a = 2; a < argc; a++) {

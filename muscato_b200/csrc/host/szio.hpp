@@ -6,11 +6,13 @@
 // accepts.  Container format only: the content is newline-delimited text.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace szio {
@@ -29,7 +31,26 @@ inline const uint32_t* crc_table() {
   return tab;
 }
 
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("sse4.2"))) inline uint32_t crc32c_hw(const uint8_t* p, size_t n) {
+  uint64_t c = 0xFFFFFFFFu;
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint64_t v;
+    memcpy(&v, p + i, 8);
+    c = __builtin_ia32_crc32di(c, v);
+  }
+  uint32_t c32 = (uint32_t)c;
+  for (; i < n; i++) c32 = __builtin_ia32_crc32qi(c32, p[i]);
+  return c32 ^ 0xFFFFFFFFu;
+}
+#endif
+
 inline uint32_t crc32c(const uint8_t* p, size_t n) {
+#if defined(__x86_64__) && defined(__GNUC__)
+  static const bool hw = __builtin_cpu_supports("sse4.2");
+  if (hw) return crc32c_hw(p, n);  // the CRC32 instruction computes exactly CRC-32C
+#endif
   const uint32_t* tab = crc_table();
   uint32_t c = 0xFFFFFFFFu;
   for (size_t i = 0; i < n; i++) c = tab[(c ^ p[i]) & 0xFF] ^ (c >> 8);
@@ -112,12 +133,69 @@ inline bool is_framed(const std::string& raw) {
   return raw.size() >= 10 && memcmp(raw.data(), "\xff\x06\x00\x00sNaPpY", 10) == 0;
 }
 
-inline std::string decompress(const std::string& raw) {
-  std::string out;
-  const uint8_t* p = reinterpret_cast<const uint8_t*>(raw.data());
-  size_t i = 0, n = raw.size();
-  bool magic = false;
+// Raw Snappy block decoded into a buffer of exactly `ulen` bytes (the length its header states).
+inline void snappy_block_decode_to(const uint8_t* b, size_t n, uint8_t* dst, size_t ulen) {
+  size_t i = 0;
+  while (i < n && (b[i] & 0x80)) i++;  // skip the varint length (validated by the caller)
+  i++;
+  size_t o = 0;
   while (i < n) {
+    const uint8_t tag = b[i++];
+    const int kind = tag & 3;
+    if (kind == 0) {
+      size_t len = tag >> 2;
+      if (len >= 60) {
+        const int nb = (int)len - 59;
+        if (i + nb > n) throw std::runtime_error("snappy: truncated literal length");
+        len = 0;
+        for (int k = 0; k < nb; k++) len |= (size_t)b[i + k] << (8 * k);
+        i += nb;
+      }
+      len += 1;
+      if (i + len > n || o + len > ulen) throw std::runtime_error("snappy: truncated literal");
+      memcpy(dst + o, b + i, len);
+      o += len;
+      i += len;
+      continue;
+    }
+    size_t len, off;
+    if (kind == 1) {
+      if (i + 1 > n) throw std::runtime_error("snappy: truncated copy");
+      len = 4 + ((tag >> 2) & 7);
+      off = ((size_t)(tag >> 5) << 8) | b[i];
+      i += 1;
+    } else if (kind == 2) {
+      if (i + 2 > n) throw std::runtime_error("snappy: truncated copy");
+      len = 1 + (tag >> 2);
+      off = b[i] | ((size_t)b[i + 1] << 8);
+      i += 2;
+    } else {
+      if (i + 4 > n) throw std::runtime_error("snappy: truncated copy");
+      len = 1 + (tag >> 2);
+      off = b[i] | ((size_t)b[i + 1] << 8) | ((size_t)b[i + 2] << 16) | ((size_t)b[i + 3] << 24);
+      i += 4;
+    }
+    if (off == 0 || off > o || o + len > ulen) throw std::runtime_error("snappy: bad copy");
+    if (off >= len) memcpy(dst + o, dst + o - off, len);
+    else for (size_t k = 0; k < len; k++) dst[o + k] = dst[o - off + k];  // overlapping run: byte by byte
+    o += len;
+  }
+  if (o != ulen) throw std::runtime_error("snappy: length mismatch");
+}
+
+// Un-frame a ".sz" stream.  threads = 0: all host threads.
+inline std::string decompress(const std::string& raw, unsigned threads = 0) {
+  struct Chunk {
+    uint8_t type;
+    const uint8_t* body;  // after the 4 CRC bytes
+    size_t len, off, ulen;
+    uint32_t want;
+  };
+  std::vector<Chunk> chunks;
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(raw.data());
+  size_t i = 0, n = raw.size(), total = 0;
+  bool magic = false;
+  while (i < n) {  // pass 1: index the chunks and their uncompressed lengths
     if (i + 4 > n) throw std::runtime_error("sz: truncated chunk header");
     const uint8_t type = p[i];
     const size_t len = p[i + 1] | ((size_t)p[i + 2] << 8) | ((size_t)p[i + 3] << 16);
@@ -132,16 +210,64 @@ inline std::string decompress(const std::string& raw) {
     if (!magic) throw std::runtime_error("sz: missing stream identifier");
     if (type == 0x00 || type == 0x01) {
       if (len < 4) throw std::runtime_error("sz: short chunk");
-      const uint32_t want = body[0] | ((uint32_t)body[1] << 8) | ((uint32_t)body[2] << 16) | ((uint32_t)body[3] << 24);
-      const size_t before = out.size();
-      if (type == 0x00) snappy_block_decode(body + 4, len - 4, out);
-      else out.append(reinterpret_cast<const char*>(body + 4), len - 4);
-      if (masked_crc(reinterpret_cast<const uint8_t*>(out.data()) + before, out.size() - before) != want)
-        throw std::runtime_error("sz: CRC mismatch");
+      Chunk c;
+      c.type = type;
+      c.body = body + 4;
+      c.len = len - 4;
+      c.want = body[0] | ((uint32_t)body[1] << 8) | ((uint32_t)body[2] << 16) | ((uint32_t)body[3] << 24);
+      c.off = total;
+      c.ulen = c.len;
+      if (type == 0x00) {
+        uint64_t ulen = 0;
+        int shift = 0;
+        size_t k = 0;
+        while (true) {
+          if (k >= c.len || shift > 35) throw std::runtime_error("snappy: truncated length");
+          const uint8_t b = c.body[k++];
+          ulen |= (uint64_t)(b & 0x7F) << shift;
+          if (b < 0x80) break;
+          shift += 7;
+        }
+        c.ulen = (size_t)ulen;
+      }
+      total += c.ulen;
+      chunks.push_back(c);
     } else if (type >= 0x02 && type <= 0x7F) {
       throw std::runtime_error("sz: reserved unskippable chunk");
     }  // 0x80..0xfe: skippable / padding
   }
+  std::string out(total, '\0');
+  uint8_t* o = reinterpret_cast<uint8_t*>(&out[0]);
+  // pass 2: decode + checksum, chunks dealt to the threads through one atomic counter
+  std::atomic<size_t> next{0};
+  std::atomic<bool> failed{false};
+  std::string err;
+  auto work = [&]() {
+    try {
+      while (!failed.load(std::memory_order_relaxed)) {
+        const size_t k = next.fetch_add(16);
+        if (k >= chunks.size()) break;
+        for (size_t c = k; c < std::min(chunks.size(), k + 16); c++) {
+          const Chunk& ch = chunks[c];
+          if (ch.type == 0x00) snappy_block_decode_to(ch.body, ch.len, o + ch.off, ch.ulen);
+          else memcpy(o + ch.off, ch.body, ch.len);
+          if (masked_crc(o + ch.off, ch.ulen) != ch.want) throw std::runtime_error("sz: CRC mismatch");
+        }
+      }
+    } catch (const std::exception& e) {
+      if (!failed.exchange(true)) err = e.what();
+    }
+  };
+  unsigned nt = threads ? threads : std::max(1u, std::thread::hardware_concurrency());
+  nt = (unsigned)std::min<size_t>(nt, (chunks.size() + 63) / 64 + 1);  // small files: no thread start-up cost
+  if (nt <= 1) {
+    work();
+  } else {
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; t++) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
+  }
+  if (failed.load()) throw std::runtime_error(err);
   return out;
 }
 
