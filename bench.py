@@ -253,6 +253,10 @@ def run_ours(args, rank, local_rank, world):
 
     cfg = Config(**CFG).apply_defaults()
     hp = HotPath(cfg, device=local_rank, keep_ascii=True)
+    if world > 1:
+        # sharded targets: the MaxMatches flag of SURVEY 8(e) rides in element [n_reads] of the best
+        # array through the all-reduce below (dist.resolve_shard_overflow is the rare path behind it)
+        hp.set_shards(world)
     hp.set_reads_ptr(rd_a.data_ptr(), rd_o.data_ptr(), n_reads)
     hp.set_targets_ptr(tg_a.data_ptr(), tg_o.data_ptr(), n_tg)
 
@@ -297,6 +301,8 @@ def run_ours(args, rank, local_rank, world):
         with torch.cuda.stream(ext_stream):
             dist.all_reduce(best, op=dist.ReduceOp.MIN)
         hp.run_stages(0, 4)           # raises on MSC_ERR_AGAIN (cannot happen after the sizing step)
+        if hp.shard_overflow():       # a key group with > MaxMatches / N passing pairs: not in this workload
+            raise RuntimeError("MaxMatches applies across shards: use dist.sharded_matches")
 
     defer_ok = [False]
 

@@ -208,6 +208,35 @@ int msc_run_stages(msc_ctx* ctx, int rebuild_what, int stages);
  * the caller repeats the sequence (in the MaxMatches case without MSC_STAGE_DEFER). */
 void* msc_stream(msc_ctx* ctx);   /* the cudaStream_t every kernel of the context runs on */
 
+/* MaxMatches with the targets sharded by gene range over several contexts / ranks.
+ * qinsert / "first" (cmd/muscato_confirm/main.go:233-242, :424-448) bound the result set of a
+ * (window, k-mer) group over ALL targets, in the order of the globally sorted smatch_<k> file
+ * (cmd/muscato/main.go:318-385), so a group whose passing pairs are spread over the shards cannot be
+ * truncated by any one of them.  msc_set_shards(ctx, n) (n > 1) switches a context to the sharded
+ * protocol:
+ *   - msc_confirm flags key groups with more than MaxMatches / n passing pairs (if no shard has
+ *     one, no group exceeds MaxMatches in total) and resolves nothing by itself; the flag is stored
+ *     in element [n_reads] of the msc_best_device array, i.e. the host all-reduces n_reads + 1
+ *     elements and every rank learns it with the exchange it performs anyway;
+ *   - after msc_combine, msc_shard_overflow(ctx) says whether any shard flagged a group.  If so
+ *     (rare path, host assisted): every rank calls msc_overflow_keys, the ranks exchange the key
+ *     fingerprints (they identify a k-mer independently of the rank), every rank calls
+ *     msc_divert_groups with the union -- which re-runs the pair kernel, keeps the undiverted
+ *     matches and their per-read minimum in the context and returns the diverted passing pairs as
+ *     records of msc_diverted_record_bytes(ctx) bytes (read, gene_base + gene, pos, nx, window, and
+ *     the candidate's left / right context bytes, which the reference's candidate order compares) --
+ *     one rank concatenates the records of all ranks and calls msc_replay_diverted, which replays
+ *     the reference's sequential truncation and returns the surviving matches (global gene ids).
+ *     The host folds their nx into the best array, all-reduces it again, calls msc_combine on every
+ *     rank and merges the survivors that meet the MMTol rule with the gathered matches.
+ * Outputs of msc_overflow_keys / msc_divert_groups / msc_replay_diverted are released with msc_free. */
+int msc_set_shards(msc_ctx* ctx, int32_t n_shards);
+int msc_shard_overflow(const msc_ctx* ctx);
+int msc_overflow_keys(msc_ctx* ctx, uint64_t** keys, uint64_t* n);
+uint32_t msc_diverted_record_bytes(const msc_ctx* ctx);
+int msc_divert_groups(msc_ctx* ctx, const uint64_t* keys, uint64_t n_keys, uint32_t gene_base, uint8_t** recs, uint64_t* n_recs);
+int msc_replay_diverted(msc_ctx* ctx, const uint8_t* recs, uint64_t n_recs, msc_match** out, uint64_t* n);
+
 /* Per-stage timers (ms_pack_reads .. ms_combine) cost one event record between kernels per stage
  * boundary (~2.5 us each on a B200); on = 0 leaves them out -- ms_scan / ms_scan_kernel are always
  * measured.  Default: on (MSC_STAGE_EVENTS=0 in the environment turns them off at msc_create). */

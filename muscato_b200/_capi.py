@@ -95,6 +95,14 @@ _SIGS = [
     ("msc_run", C.c_int, [C.c_void_p]),
     ("msc_rebuild_and_run", C.c_int, [C.c_void_p, C.c_int]),
     ("msc_run_stages", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("msc_set_shards", C.c_int, [C.c_void_p, C.c_int32]),
+    ("msc_shard_overflow", C.c_int, [C.c_void_p]),
+    ("msc_overflow_keys", C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]),
+    ("msc_diverted_record_bytes", C.c_uint32, [C.c_void_p]),
+    ("msc_divert_groups", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
+                                    C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_uint64)]),
+    ("msc_replay_diverted", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.POINTER(msc_match)),
+                                      C.POINTER(C.c_uint64)]),
     ("msc_set_stage_timing", C.c_int, [C.c_void_p, C.c_int]),
     ("msc_get_stats", C.c_int, [C.c_void_p, C.POINTER(msc_stats)]),
     ("msc_reset_stats", None, [C.c_void_p]),

@@ -84,7 +84,8 @@ enum Counter {
   C_NKEYS = 0, C_NGROUPS, C_NDUP, C_SCRATCH, C_NCAND, C_BLOOMPASS, C_NMATCH, C_NPASS, C_NOVER, C_NOUT, C_NPAIRS,
   C_PAD0, C_NLONG, C_PAD1, C_TGX,  // C_NLONG, C_TGX at even indices; C_TGX = "some target word has X"
   C_PAD2, C_PREP_KEPT, C_PREP_UNIQ, C_PREP_BYTES, C_PAD3,  // C_PREP_KEPT at an even index (16)
-  C_PREP_TIE, C_PAD4,                                      // C_PREP_TIE (20): longest unsorted run of prep_tiefix_kernel
+  C_PREP_TIE, C_SHARDOVER,                                 // C_PREP_TIE (20): longest unsorted run of prep_tiefix_kernel;
+                                                           // C_SHARDOVER: some target shard flagged a MaxMatches candidate group
   C_COUNT = 24  // groups that are cleared together start at even indices (16-byte aligned)
 };
 
@@ -142,6 +143,10 @@ struct msc_ctx {
   // completed (counters read, buffers checked) by the next call that synchronises
   bool deferred = false;
   DevBuf match_pre, best, rcount, rstart, rfill, match_out, long_list, mid_list;
+  // targets sharded over several contexts: MaxMatches is detected at MaxMatches / n_shards and
+  // resolved by the host protocol (msc_overflow_keys / msc_divert_groups / msc_replay_diverted)
+  int n_shards = 1;
+  bool shard_overflow = false;
   // confirm kernel mode 2 (MaxMatches overflow groups diverted to the host)
   struct {
     const uint8_t* slot_over = nullptr;
@@ -591,9 +596,11 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
     // MaxMatches pre-check (cmd/muscato_confirm/main.go:233-242, :424-448): truncation can only
     // happen in a key group with more than MaxMatches passing pairs.
     const uint64_t slots = 1ull << ctx->lg_slots;
+    const unsigned long long thr = ctx->n_shards > 1 ? (unsigned long long)ctx->cfg.max_matches / (unsigned long long)ctx->n_shards
+                                                     : (unsigned long long)ctx->cfg.max_matches;
     launch_k(ctx->pdl, overflow_count_kernel, (unsigned)ctx->sm_count * 8, 256, 0, ctx->stream, 
-        ctx->pass_cnt.as<uint32_t>(), slots, (unsigned long long)ctx->cfg.max_matches, ctx->ctr(C_NPASS),
-        ctx->ctr(C_NOVER));
+        ctx->pass_cnt.as<uint32_t>(), slots, thr, ctx->ctr(C_NPASS), ctx->ctr(C_NOVER),
+        ctx->n_shards > 1 ? ctx->best.as<uint32_t>() + ctx->n_reads : (uint32_t*)nullptr);
     LAUNCH_CHECK();
   }
   if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_CONFIRM1], ctx->stream));
@@ -616,6 +623,10 @@ int enqueue_combine(msc_ctx* ctx) {
   }
   ctx->pro.combine = false;
   const unsigned g = (unsigned)ctx->sm_count * 8;
+  if (ctx->n_shards > 1) {  // best[n_reads] after the MIN all-reduce: did ANY shard see a MaxMatches candidate group?
+    launch_k(ctx->pdl, shard_flag_kernel, 1, 32, 0, ctx->stream, ctx->best.as<uint32_t>() + ctx->n_reads, ctx->ctr(C_SHARDOVER));
+    LAUNCH_CHECK();
+  }
   launch_k(ctx->pdl, combine_count_kernel, g, 256, 0, ctx->stream, ctx->match_pre.as<uint4>(), ctx->ctr(C_NMATCH), mcap,
                                                    ctx->best.as<uint32_t>(), (uint32_t)ctx->cfg.mmtol,
                                                    ctx->rcount.as<uint32_t>());
@@ -697,7 +708,7 @@ int finish_confirm(msc_ctx* ctx) {
   ctx->st.n_pass = ctx->h_counters[C_NPASS];
   ctx->st.n_matches_pre = ctx->n_match_pre;
   ctx->st.n_overflow_groups = ctx->h_counters[C_NOVER];
-  if (ctx->st.n_overflow_groups) {
+  if (ctx->st.n_overflow_groups && ctx->n_shards <= 1) {
     // Some key group holds more passing pairs than MaxMatches: replay the reference's
     // order-dependent truncation for those groups (rare path, host assisted).
     const float ms_e = ctx->st.ms_expand, ms_c = ctx->st.ms_confirm;
@@ -718,6 +729,7 @@ int finish_combine(msc_ctx* ctx) {
   ctx->st.n_matches = ctx->n_match;
   if (ctx->stage_events) ctx->st.ms_combine += elapsed(ctx, EV_COMB0, EV_COMB1);
   ctx->have_combine = true;
+  ctx->shard_overflow = ctx->n_shards > 1 && ctx->h_counters[C_SHARDOVER] != 0;
   return MSC_OK;
 }
 
@@ -1372,6 +1384,60 @@ int msc_run_stages(msc_ctx* ctx, int rebuild_what, int stages) {
 
 int msc_rebuild_and_run(msc_ctx* ctx, int what) {
   return msc_run_stages(ctx, what, MSC_STAGE_SCREEN | MSC_STAGE_CONFIRM | MSC_STAGE_COMBINE);
+}
+
+int msc_set_shards(msc_ctx* ctx, int32_t n_shards) {
+  if (!ctx) return MSC_ERR_STATE;
+  if (n_shards < 1) return ctx->fail(MSC_ERR_CONFIG, "msc_set_shards: n_shards must be >= 1");
+  ctx->n_shards = n_shards;
+  ctx->shard_overflow = false;
+  return MSC_OK;
+}
+
+int msc_shard_overflow(const msc_ctx* ctx) { return ctx && ctx->shard_overflow ? 1 : 0; }
+
+int msc_overflow_keys(msc_ctx* ctx, uint64_t** keys, uint64_t* n) {
+  if (!ctx || !keys || !n) return MSC_ERR_STATE;
+  if (!ctx->have_confirm || ctx->deferred) return ctx->fail(MSC_ERR_STATE, "msc_overflow_keys: run msc_confirm first");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<uint64_t> fps;
+  RC(shard_overflow_keys(ctx, fps));
+  *n = fps.size();
+  *keys = (uint64_t*)malloc(std::max<size_t>(fps.size(), 1) * sizeof(uint64_t));
+  if (!*keys) return ctx->fail(MSC_ERR_NOMEM, "host allocation failed");
+  if (!fps.empty()) memcpy(*keys, fps.data(), fps.size() * sizeof(uint64_t));
+  return MSC_OK;
+}
+
+uint32_t msc_diverted_record_bytes(const msc_ctx* ctx) { return ctx ? div_rec_bytes(ctx) : 0; }
+
+int msc_divert_groups(msc_ctx* ctx, const uint64_t* keys, uint64_t n_keys, uint32_t gene_base, uint8_t** recs, uint64_t* n_recs) {
+  if (!ctx || !recs || !n_recs || (n_keys && !keys)) return MSC_ERR_STATE;
+  if (!ctx->have_cand || !ctx->have_confirm || ctx->deferred)
+    return ctx->fail(MSC_ERR_STATE, "msc_divert_groups: run msc_screen and msc_confirm first");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<uint8_t> buf;
+  uint64_t nr = 0;
+  RC(shard_divert(ctx, keys, n_keys, gene_base, buf, nr));
+  *n_recs = nr;
+  *recs = (uint8_t*)malloc(std::max<size_t>(buf.size(), 1));
+  if (!*recs) return ctx->fail(MSC_ERR_NOMEM, "host allocation failed");
+  if (!buf.empty()) memcpy(*recs, buf.data(), buf.size());
+  return MSC_OK;
+}
+
+int msc_replay_diverted(msc_ctx* ctx, const uint8_t* recs, uint64_t n_recs, msc_match** out, uint64_t* n) {
+  if (!ctx || !out || !n || (n_recs && !recs)) return MSC_ERR_STATE;
+  if (!ctx->have_reads) return ctx->fail(MSC_ERR_STATE, "msc_replay_diverted: no reads set");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::vector<uint4> surv;
+  RC(shard_replay(ctx, recs, n_recs, surv));
+  *n = surv.size();
+  *out = (msc_match*)malloc(std::max<size_t>(surv.size(), 1) * sizeof(msc_match));
+  if (!*out) return ctx->fail(MSC_ERR_NOMEM, "host allocation failed");
+  if (!surv.empty()) memcpy(*out, surv.data(), surv.size() * sizeof(msc_match));
+  return MSC_OK;
 }
 
 int msc_fetch_matches_into(msc_ctx* ctx, msc_match* dst, uint64_t capacity, uint64_t* n) {

@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(256) best_from_matches_kernel(const uint4* __r
 __global__ void __launch_bounds__(256) overflow_count_kernel(const uint32_t* __restrict__ pass_cnt, uint64_t n_slots,
                                                              unsigned long long max_matches,
                                                              const unsigned long long* __restrict__ n_pass,
-                                                             unsigned long long* __restrict__ n_over) {
+                                                             unsigned long long* __restrict__ n_over,
+                                                             uint32_t* __restrict__ shard_flag) {
   pdl_enter();
   if (*n_pass <= max_matches) return;  // no group can exceed MaxMatches (the usual case: nothing to read)
   uint32_t over = 0;  // n_slots is a power of two >= 1024: 16-byte loads
@@ -216,7 +217,18 @@ __global__ void __launch_bounds__(256) overflow_count_kernel(const uint32_t* __r
             ((unsigned long long)v.z > max_matches) + ((unsigned long long)v.w > max_matches);
   }
   over = __reduce_add_sync(0xffffffffu, over);
-  if ((threadIdx.x & 31u) == 0 && over) atomicAdd(n_over, (unsigned long long)over);
+  if ((threadIdx.x & 31u) == 0 && over) {
+    atomicAdd(n_over, (unsigned long long)over);
+    // sharded targets (max_matches = MaxMatches / n_shards): the flag sits behind the per-read best
+    // array and reaches every rank with the MIN all-reduce of that array
+    if (shard_flag) *shard_flag = 0u;
+  }
+}
+
+// After the all-reduce: copy the flag into the counter block the host reads anyway.
+__global__ void shard_flag_kernel(const uint32_t* __restrict__ flag, unsigned long long* __restrict__ out) {
+  pdl_enter();
+  if (threadIdx.x == 0) *out = *flag == 0u ? 1ull : 0ull;
 }
 
 }  // namespace msc

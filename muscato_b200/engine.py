@@ -51,6 +51,7 @@ class HotPath:
             raise MuscatoError(-1, err.value.decode(errors="replace"))
         self.n_reads = 0
         self.n_targets = 0
+        self.n_shards = 1
         self._keep = []
 
     # -- lifecycle -------------------------------------------------------------------
@@ -165,7 +166,60 @@ class HotPath:
         ptr = self._lib.msc_best_device(self._ctx)
         if not ptr:
             raise MuscatoError(_capi.MSC_ERR_STATE, "best array not available (run confirm first)")
-        return _DevArray(ptr, self.n_reads, "<i4")
+        # with sharded targets element [n_reads] carries the MaxMatches flag through the all-reduce
+        return _DevArray(ptr, self.n_reads + (1 if self.n_shards > 1 else 0), "<i4")
+
+    # -- MaxMatches across target shards (include/muscato_b200.h, msc_set_shards) --------------
+    def set_shards(self, n_shards: int):
+        self._check(self._lib.msc_set_shards(self._ctx, int(n_shards)))
+        self.n_shards = int(n_shards)
+
+    def shard_overflow(self) -> bool:
+        """After combine: did any shard flag a key group with more than MaxMatches / n_shards passing pairs?"""
+        return bool(self._lib.msc_shard_overflow(self._ctx))
+
+    def overflow_keys(self) -> np.ndarray:
+        out = C.POINTER(C.c_uint64)()
+        n = C.c_uint64(0)
+        self._check(self._lib.msc_overflow_keys(self._ctx, C.byref(out), C.byref(n)))
+        try:
+            return np.ctypeslib.as_array(out, shape=(n.value,)).copy() if n.value else np.zeros(0, dtype=np.uint64)
+        finally:
+            self._lib.msc_free(out)
+
+    def diverted_record_bytes(self) -> int:
+        return int(self._lib.msc_diverted_record_bytes(self._ctx))
+
+    def divert_groups(self, keys: np.ndarray, gene_base: int) -> np.ndarray:
+        """uint8 [n, record_bytes]: the passing pairs of the flagged key groups of this shard."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        out = C.POINTER(C.c_uint8)()
+        n = C.c_uint64(0)
+        self._check(self._lib.msc_divert_groups(self._ctx, keys.ctypes.data, len(keys), int(gene_base), C.byref(out),
+                                                C.byref(n)))
+        rb = self.diverted_record_bytes()
+        try:
+            if n.value == 0:
+                return np.zeros((0, rb), dtype=np.uint8)
+            return np.ctypeslib.as_array(out, shape=(n.value * rb,)).copy().reshape(-1, rb)
+        finally:
+            self._lib.msc_free(out)
+
+    def replay_diverted(self, recs: np.ndarray) -> np.ndarray:
+        """The reference's sequential MaxMatches truncation over the diverted pairs of ALL shards;
+        returns the survivors (global gene ids), de-duplicated, ordered by (read, gene, pos)."""
+        recs = np.ascontiguousarray(recs, dtype=np.uint8)
+        rb = self.diverted_record_bytes()
+        assert recs.size % rb == 0
+        out = C.POINTER(_capi.msc_match)()
+        n = C.c_uint64(0)
+        self._check(self._lib.msc_replay_diverted(self._ctx, recs.ctypes.data, recs.size // rb, C.byref(out), C.byref(n)))
+        try:
+            if n.value == 0:
+                return np.zeros(0, dtype=MATCH_DTYPE)
+            return np.frombuffer(C.string_at(out, n.value * C.sizeof(_capi.msc_match)), dtype=MATCH_DTYPE).copy()
+        finally:
+            self._lib.msc_free(out)
 
     def matches_device(self):
         """(holder, n): device view of the combined matches as int32[n*4] (read, gene, pos, nx)."""

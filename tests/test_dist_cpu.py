@@ -97,3 +97,40 @@ def test_two_rank_exchange_equals_global_combine(tmp_path, oracle_bin):
     got = np.load(out_path).astype(np.int64)
     got = got[np.lexsort((got[:, 3], got[:, 2], got[:, 1], got[:, 0]))]
     assert np.array_equal(got, want)
+
+
+def _ragged_worker(rank, world, port, out_path):
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    keys = torch.arange(3 * rank, dtype=torch.int64) + 100 * rank            # rank 0 contributes nothing
+    allk = mdist.allgather_concat(keys)
+    recs = torch.full((2 - rank, 5), rank + 1, dtype=torch.uint8)             # 2-D, ragged first dimension
+    allr = mdist.allgather_concat(recs)
+    best = torch.tensor([5, 9, 0x7F7F7F7F, 3 + rank], dtype=torch.int32)
+    mdist._allreduce_min(best)
+    if rank == 0:
+        np.savez(out_path, k=allk.numpy(), r=allr.numpy(), b=best.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ragged_allgather_of_keys_and_records(tmp_path):
+    """The exchanges of the cross-shard MaxMatches protocol (dist.resolve_shard_overflow): key
+    fingerprints and diverted-pair records differ in number per rank."""
+    out_path = str(tmp_path / "ragged.npz")
+    mp.spawn(_ragged_worker, args=(2, _free_port(), out_path), nprocs=2, join=True)
+    z = np.load(out_path)
+    assert z["k"].tolist() == [100, 101, 102]
+    assert z["r"].tolist() == [[1] * 5, [1] * 5, [2] * 5]
+    assert z["b"].tolist() == [5, 9, 0x7F7F7F7F, 3]
+
+
+def test_merge_survivors_applies_mmtol_and_sort_u():
+    md = np.dtype([("read_id", "<u4"), ("gene_id", "<u4"), ("pos", "<u4"), ("nx", "<u4")])
+    gathered = np.array([[2, 7, 10, 1], [0, 3, 5, 0], [2, 1, 4, 2]], dtype=np.int64)
+    surv = np.array([(2, 7, 10, 1), (2, 0, 9, 3), (1, 4, 4, 2), (0, 9, 9, 1)], dtype=md)
+    best_of = np.array([1, 1, 2, 0])             # global best of each survivor's read
+    got = mdist.merge_survivors(gathered, surv, best_of, mmtol=1)
+    # (2,7,10,1) is a duplicate of a gathered line; (2,0,9,3) fails nx <= best + MMTol; the rest joins
+    assert got.tolist() == [[0, 3, 5, 0], [0, 9, 9, 1], [1, 4, 4, 2], [2, 1, 4, 2], [2, 7, 10, 1]]
+    assert mdist.merge_survivors(gathered, None, None, 0).tolist() == [[0, 3, 5, 0], [2, 1, 4, 2], [2, 7, 10, 1]]
+    assert mdist.merge_survivors(np.zeros((0, 4)), None, None, 0).shape == (0, 4)
