@@ -307,21 +307,34 @@ def run_ours(args, rank, local_rank, world):
     defer_ok = [False]
 
     if world > 1:
-        d_rd_a = torch.empty(rd_a.numel(), dtype=torch.uint8, device=dev)
-        d_rd_o = torch.empty(rd_o.numel(), dtype=torch.int64, device=dev)
+        # The replicated read set (offsets | ASCII) as one blob cut into `world` equal slices: every
+        # rank uploads ONE slice over its own PCIe link and an NCCL all-gather over NVLink assembles
+        # the whole set on every GPU (instead of rank 0 uploading all of it and broadcasting).
+        offs_bytes = rd_o.numel() * 8
+        blob_len = offs_bytes + rd_a.numel()
+        chunk = (((blob_len + world - 1) // world) + 255) // 256 * 256
+        h_part = torch.zeros(chunk, dtype=torch.uint8).pin_memory()
+        b0, b1 = rank * chunk, min(blob_len, (rank + 1) * chunk)
+        if b0 < offs_bytes:
+            n = min(b1, offs_bytes) - b0
+            h_part[:n] = rd_o.view(torch.uint8)[b0:b0 + n]
+        if b1 > offs_bytes:
+            a0 = max(b0, offs_bytes)
+            h_part[a0 - b0:b1 - b0] = rd_a[a0 - offs_bytes:b1 - offs_bytes]
+        d_blob = torch.empty(chunk * world, dtype=torch.uint8, device=dev)
+        d_part = torch.empty(chunk, dtype=torch.uint8, device=dev)
 
     def step_e2e():
         if world == 1:
             hp.set_reads_ptr(rd_a.data_ptr(), rd_o.data_ptr(), n_reads)
         else:
-            # the replicated read set crosses PCIe once (rank 0) and NVLink N-1 times (NCCL broadcast)
-            if rank == 0:
-                d_rd_a.copy_(rd_a, non_blocking=True)
-                d_rd_o.copy_(rd_o, non_blocking=True)
-            dist.broadcast(d_rd_a, src=0)
-            dist.broadcast(d_rd_o, src=0)
-            torch.cuda.synchronize()
-            hp.set_reads_device(d_rd_a.data_ptr(), d_rd_o.data_ptr(), n_reads, int(rd_a.numel()))
+            # every byte of the read set crosses PCIe once (1/N per rank, in parallel) and NVLink N-1
+            # times; copy and all-gather are ordered on the library's stream, so the table build that
+            # msc_set_reads_device enqueues follows them without a host synchronisation
+            with torch.cuda.stream(ext_stream):
+                d_part.copy_(h_part, non_blocking=True)
+                dist.all_gather_into_tensor(d_blob, d_part)
+            hp.set_reads_device(d_blob.data_ptr() + offs_bytes, d_blob.data_ptr(), n_reads, int(rd_a.numel()))
         hp.set_targets_ptr(tg_a.data_ptr(), tg_o.data_ptr(), n_tg)
         if world == 1:
             hp.run()
