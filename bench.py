@@ -329,10 +329,11 @@ def run_ours(args, rank, local_rank, world):
             hp.set_reads_ptr(rd_a.data_ptr(), rd_o.data_ptr(), n_reads)
         else:
             # every byte of the read set crosses PCIe once (1/N per rank, in parallel) and NVLink N-1
-            # times; copy and all-gather are ordered on the library's stream, so the table build that
-            # msc_set_reads_device enqueues follows them without a host synchronisation
+            # times; the all-gather is ordered on the library's stream (behind the copy), so the table
+            # build that msc_set_reads_device enqueues follows it without a host synchronisation
+            d_part.copy_(h_part, non_blocking=True)
+            ext_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(ext_stream):
-                d_part.copy_(h_part, non_blocking=True)
                 dist.all_gather_into_tensor(d_blob, d_part)
             hp.set_reads_device(d_blob.data_ptr() + offs_bytes, d_blob.data_ptr(), n_reads, int(rd_a.numel()))
         hp.set_targets_ptr(tg_a.data_ptr(), tg_o.data_ptr(), n_tg)
@@ -482,9 +483,16 @@ def run_ours(args, rank, local_rank, world):
                                     "sample": f"failed: {e}"}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    hp.close()
     if world > 1:
+        # d_blob / d_part were used on the library's stream (ExternalStream): give them back to
+        # torch's allocator and tear NCCL down BEFORE msc_destroy destroys that stream
+        torch.cuda.synchronize()
+        dist.barrier()
+        del d_blob, d_part, h_part
+        torch.cuda.empty_cache()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+    hp.close()
 
 
 def main():
