@@ -138,21 +138,34 @@ def _free_port():
     return p
 
 
-def _rank(rank, world, port, cfgd, seqs, genes, out_path):
+def _rank(rank, world, port, cfgd, seqs, genes, out_path, backend="gloo"):
     import torch
     import torch.distributed as dist
     from muscato_b200.engine import HotPath
-    torch.cuda.set_device(0)
-    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    device = rank if backend == "nccl" else 0
+    torch.cuda.set_device(device)
+    if backend == "nccl":
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", device))
+    else:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     cfg = Config(**{k: v for k, v in cfgd.items() if k in Config.__dataclass_fields__}).apply_defaults()
     offs = np.concatenate([[0], np.cumsum([len(g) for g in genes])]).astype(np.uint64)
     lo, hi = mdist.shard_targets(offs, world)[rank]
-    with HotPath(cfg, device=0) as hp:
+    with HotPath(cfg, device=device) as hp:
         hp.set_shards(world)
         hp.set_reads(seqs)
         hp.set_targets(genes[lo:hi])
-        got = mdist.sharded_matches(hp, lo, deferred=False)
+        if backend == "nccl":
+            # first pass sizes the buffers, the second one takes the stream-ordered (deferred) step:
+            # the MaxMatches flag must survive both and both must give the same result
+            first = mdist.sharded_matches(hp, lo, deferred=False)
+            got = mdist.sharded_matches(hp, lo, deferred=True)
+            assert rank != 0 or np.array_equal(first, got)
+        else:
+            got = mdist.sharded_matches(hp, lo, deferred=False)
         n_trunc = hp.stats()["n_overflow_groups"]
+        torch.cuda.synchronize()
     if rank == 0:
         np.save(out_path, got)
         np.save(out_path + ".trunc.npy", np.array([n_trunc]))
@@ -169,6 +182,22 @@ def test_two_gloo_ranks_through_dist(mode, mm, tmp_path, oracle_bin):
     cfg, seqs, want = _oracle(tmp_path, reads, genes, cfgd)
     out_path = str(tmp_path / "gathered.npy")
     mp.spawn(_rank, args=(2, _free_port(), cfgd, seqs, genes, out_path), nprocs=2, join=True)
+    got = np.load(out_path)
+    assert int(np.load(out_path + ".trunc.npy")[0]) > 0
+    assert formats.matches_lines(_as_matches(got), seqs, genes) == want
+
+
+@pytest.mark.parametrize("mode,mm", [("best", 3), ("first", 5)], ids=["best3", "first5"])
+def test_two_nccl_ranks_through_dist(mode, mm, tmp_path, oracle_bin):
+    """The same over NCCL on two GPUs, including the stream-ordered step (skipped on a one-GPU box)."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    reads, genes, cfgd = _case(mm, mode, 300 + mm)
+    cfg, seqs, want = _oracle(tmp_path, reads, genes, cfgd)
+    out_path = str(tmp_path / "gathered.npy")
+    mp.spawn(_rank, args=(2, _free_port(), cfgd, seqs, genes, out_path, "nccl"), nprocs=2, join=True)
     got = np.load(out_path)
     assert int(np.load(out_path + ".trunc.npy")[0]) > 0
     assert formats.matches_lines(_as_matches(got), seqs, genes) == want
