@@ -78,6 +78,13 @@ struct DevBuf {
   template <typename T>
   T* as() const { return reinterpret_cast<T*>(p); }
 };
+// A DevBuf that is a local of a host function: freed on every exit path.
+struct ScopedDevBuf : DevBuf {
+  ScopedDevBuf() = default;
+  ScopedDevBuf(const ScopedDevBuf&) = delete;
+  ScopedDevBuf& operator=(const ScopedDevBuf&) = delete;
+  ~ScopedDevBuf() { release(); }
+};
 
 // Device counter block (unsigned long long each).
 enum Counter {
@@ -1579,7 +1586,7 @@ int msc_dump_candidates(msc_ctx* ctx, msc_cand_rec** out, uint64_t* n) {
   if (!ctx || !out || !n) return MSC_ERR_STATE;
   if (!ctx->have_cand) return ctx->fail(MSC_ERR_STATE, "msc_dump_candidates: run msc_screen first");
   CK(cudaSetDevice(ctx->device));
-  DevBuf tmp;
+  ScopedDevBuf tmp;
   uint64_t cnt = 0;
   int rc = MSC_OK;
   for (int attempt = 0; attempt < 5; attempt++) {
