@@ -98,7 +98,9 @@ const char* msc_last_error(const msc_ctx* ctx);
  * read i is ascii[offs[i] .. offs[i+1]).  Alphabet A,C,G,T,X (any other byte is
  * treated as X).  Uploads, 2-bit packs on the device and builds the window-key
  * table: replaces buildBloom (cmd/muscato_screen/main.go:116-207), muscato_window_reads
- * (cmd/muscato_window_reads/main.go:94-141) and sortWindows (cmd/muscato/main.go:237-304). */
+ * (cmd/muscato_window_reads/main.go:94-141) and sortWindows (cmd/muscato/main.go:237-304).
+ * n_reads * n_windows <= 2^30 per call; larger read sets are fed in batches (reads are independent
+ * of each other: every rule of the path, MMTol included, is per read). */
 int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint64_t n_reads);
 
 /* Same as msc_set_reads for buffers that are already in the memory of ctx's device (e.g. the

@@ -951,7 +951,10 @@ const char* msc_last_error(const msc_ctx* ctx) { return ctx ? ctx->err.c_str() :
 // Size every read-side buffer and the key table for n_reads reads / total ASCII bytes.
 static int reads_reserve(msc_ctx* ctx, uint64_t n_reads, uint64_t total) {
   const uint64_t nwin = (uint64_t)ctx->win.nwin;
-  if (n_reads * nwin >= 0xffffffffull) return ctx->fail(MSC_ERR_INPUT, "reads: n_reads * n_windows must be < 2^32");
+  // item ids, table slots (+1 in dup_slot) and CSR offsets are 32-bit: at most 2^30 (read, window) items,
+  // i.e. a table of at most 2^31 slots, per read set -- larger sets are fed in batches (reads are independent)
+  if (n_reads * nwin > (1ull << 30))
+    return ctx->fail(MSC_ERR_INPUT, "reads: n_reads * n_windows must be <= 2^30 per read set (feed larger sets in batches)");
   ctx->n_reads = n_reads;
   const int S = ctx->win.S;
   CK(ctx->rd_ascii.reserve(total + 64));
