@@ -22,9 +22,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from muscato_b200.config import Config  # noqa: E402
 from muscato_b200.engine import HotPath  # noqa: E402
 
-if os.environ.get("MSC_SCALE_DRY"):   # CPU dry run of the generator and the checks (fake engine)
-    from profiles._fake_engine import HotPath  # noqa: E402,F811
-
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
 n_genes = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 GL = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
