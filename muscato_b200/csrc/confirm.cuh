@@ -59,9 +59,12 @@ __global__ void __launch_bounds__(256) cand_prepare_kernel(const uint2* __restri
   }
 }
 
-// First candidate of every kPairBlock-pair block of the confirm kernel (one parallel binary
-// search per block, so that the search inside the kernel only spans the block's few
-// candidates).  Entry n_blocks is a sentinel.
+// First candidate of every kPairBlock-pair block of the confirm kernel, so that the search inside
+// the kernel only spans the block's few candidates.  Entry n_blocks is a sentinel.  block_first[b]
+// is the candidate whose pair range [pstart[c], pstart[c+1]) contains the block's first pair
+// (the last pair for the sentinel of a complete list): instead of one binary search per block, every
+// candidate writes the entries of the blocks that start inside its range (coalesced reads of
+// pstart, ~n_blocks scattered 4-byte stores in total).
 __global__ void __launch_bounds__(256) pair_block_starts_kernel(const uint64_t* __restrict__ pstart,
                                                                 const unsigned long long* __restrict__ n_cand_ptr,
                                                                 uint64_t cand_cap,
@@ -72,9 +75,13 @@ __global__ void __launch_bounds__(256) pair_block_starts_kernel(const uint64_t* 
   const uint64_t n_pairs = *n_pairs_ptr;
   if (n_pairs == 0) return;
   const uint64_t n_blocks = min((uint64_t)((n_pairs + kPairBlock - 1) >> kPairBlockShift), block_cap);
-  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= n_blocks; b += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t first = min((uint64_t)(b << kPairBlockShift), (uint64_t)(n_pairs - 1));
-    block_first[b] = (uint32_t)(upper_bound_dev<uint64_t>(pstart, 0, n_cand, first) - 1);
+  const bool complete = (n_blocks << kPairBlockShift) >= n_pairs;  // false while block_first is still too small
+  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cand; c += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t s = __ldg(pstart + c), e = __ldg(pstart + c + 1);
+    if (e <= s) continue;  // no pairs
+    const uint64_t b1 = min((uint64_t)((e - 1) >> kPairBlockShift), n_blocks);
+    for (uint64_t b = (s + kPairBlock - 1) >> kPairBlockShift; b <= b1; b++) block_first[b] = (uint32_t)c;
+    if (complete && e == n_pairs) block_first[n_blocks] = (uint32_t)c;  // sentinel: the candidate of the last pair
   }
 }
 
