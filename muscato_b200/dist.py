@@ -79,6 +79,29 @@ def allgather_concat(t, group=None):
     return torch.cat([b[:k] for b, k in zip(bufs, sizes)], dim=0)
 
 
+def gather_concat(t, dst: int = 0, group=None):
+    """Concatenation over ranks, on rank `dst` only (None elsewhere), of tensors that differ in their
+    first dimension: sizes are all-gathered, the payload travels as one padded gather."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return t
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x.item()) for x in sizes]
+    mx = max(max(sizes), 1)
+    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([b[:k] for b, k in zip(bufs, sizes)], dim=0)
+
+
 def resolve_shard_overflow(hp, gene_offset: int, group=None, dst: int = 0):
     """Rare path, entered by ALL ranks when hp.shard_overflow() is set after a sharded step: some
     (window, k-mer) group may hold more than MaxMatches passing pairs over all shards
@@ -96,22 +119,12 @@ def resolve_shard_overflow(hp, gene_offset: int, group=None, dst: int = 0):
     allk = allgather_concat(torch.from_numpy(keys.view(np.int64)).to(xdev), group=group)
     allk = np.unique(allk.cpu().numpy().view(np.uint64))
     recs = hp.divert_groups(allk, gene_offset)      # the context now holds the undiverted matches and their best
-    rb = recs.shape[1]
-    # records go to one rank only (they can be large): padded gather
-    n = torch.tensor([recs.shape[0]], dtype=torch.int64, device=xdev)
-    sizes = [torch.zeros_like(n) for _ in range(dist.get_world_size(group))]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(x.item()) for x in sizes]
-    mx = max(max(sizes), 1)
-    pad = torch.zeros((mx, rb), dtype=torch.uint8, device=xdev)
-    pad[: recs.shape[0]] = torch.from_numpy(recs).to(xdev)
-    bufs = [torch.zeros_like(pad) for _ in sizes] if rank == dst else None
-    dist.gather(pad, bufs, dst=dst, group=group)
+    # records go to one rank only (they can be large)
+    allr = gather_concat(torch.from_numpy(recs).to(xdev), dst=dst, group=group)
     best = torch.as_tensor(hp.best_device(), device=dev)
     surv = None
     if rank == dst:
-        allr = torch.cat([b[:k] for b, k in zip(bufs, sizes)], dim=0).cpu().numpy()
-        surv = hp.replay_diverted(allr)
+        surv = hp.replay_diverted(allr.cpu().numpy())
         if len(surv):
             rid, inv = np.unique(surv["read_id"], return_inverse=True)
             mn = np.full(len(rid), np.iinfo(np.int32).max, dtype=np.int64)
@@ -193,24 +206,7 @@ def sharded_step(hp, rebuild_what: int = 0, group=None, deferred: bool = True):
 def gather_matches(local, gene_offset: int, dst: int = 0, group=None):
     """local: int32 tensor [n, 4] = (read, gene, pos, nx) with shard-local gene ids.
     Returns on rank `dst` the concatenation over ranks with global gene ids (else None)."""
-    import torch
-    import torch.distributed as dist
     local = local.reshape(-1, 4).clone()
     if local.numel():
         local[:, 1] += int(gene_offset)
-    if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return local
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    mx = max(max(sizes), 1)
-    pad = torch.zeros((mx, 4), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == dst else None
-    dist.gather(pad, bufs, dst=dst, group=group)
-    if rank != dst:
-        return None
-    return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+    return gather_concat(local, dst=dst, group=group)

@@ -107,6 +107,10 @@ def _ragged_worker(rank, world, port, out_path):
     allr = mdist.allgather_concat(recs)
     best = torch.tensor([5, 9, 0x7F7F7F7F, 3 + rank], dtype=torch.int32)
     mdist._allreduce_min(best)
+    onr = mdist.gather_concat(recs, dst=1)                                    # records go to ONE rank
+    assert (onr is None) == (rank != 1)
+    if rank == 1:
+        assert onr.tolist() == [[1] * 5, [1] * 5, [2] * 5]
     if rank == 0:
         np.savez(out_path, k=allk.numpy(), r=allr.numpy(), b=best.numpy())
     dist.barrier()
