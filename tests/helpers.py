@@ -116,3 +116,42 @@ def write_case(workdir: str, raw_reads: List[bytes], names: Optional[List[bytes]
             nm = gene_names[i] if gene_names else b"gene_%d" % i
             f.write(b"%011d\t%s\t%d\n" % (i, nm, len(g)))
     return fq, gs, gi
+
+
+# ---- second, independent restatement of the path: the closed form of SURVEY.md App. A --------------
+# Plain string search per read; used to cross-check the oracle on the CPU (tests/test_oracle_closed_form.py)
+# and the CUDA path at full size (tests/test_gpu_fullsize.py).  `cfg` is a muscato_b200.config.Config.
+def count_dinuc(s: bytes) -> int:
+    return len({s[i:i + 2] for i in range(len(s) - 1)})
+
+
+def closed_form_matches(read: bytes, tgt: bytes, offs: np.ndarray, cfg: Config):
+    """All (gene, pos, nx) the reference produces for one read before the MMTol rule (App. A.2)."""
+    W, MRL, L = cfg.WindowWidth, cfg.MaxReadLength, len(read)
+    nmiss = cfg.nmiss(L)
+    out = {}
+    r = np.frombuffer(read, dtype=np.uint8)
+    for q1 in cfg.Windows:
+        q2 = q1 + W
+        if L < q2 or count_dinuc(read[q1:q2]) < cfg.MinDinuc:
+            continue
+        key = read[q1:q2]
+        at = tgt.find(key)
+        while at >= 0:
+            g = int(np.searchsorted(offs, at, side="right") - 1)
+            goff, glen = int(offs[g]), int(offs[g + 1] - offs[g])
+            p = at - goff
+            pos = p - q1
+            ok = p + W <= glen and pos >= 0
+            if ok:
+                if p == 0:
+                    ok = L <= min(100 - W, glen)                      # the literal 100 (Q1)
+                else:
+                    ok = L - q2 <= min(p + W + MRL - q2, glen) - (p + W)
+            if ok:
+                t = np.frombuffer(tgt[goff + pos:goff + pos + L], dtype=np.uint8)
+                nx = int((t != r).sum())
+                if nx <= nmiss:
+                    out[(g, pos)] = nx
+            at = tgt.find(key, at + 1)
+    return out
