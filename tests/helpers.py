@@ -155,3 +155,77 @@ def closed_form_matches(read: bytes, tgt: bytes, offs: np.ndarray, cfg: Config):
                     out[(g, pos)] = nx
             at = tgt.find(key, at + 1)
     return out
+
+
+def sequential_restatement(seqs, genes, cfg):
+    """Third restatement, this time of the reference's SEQUENTIAL structure (needed for MaxMatches, Q7,
+    which the closed form cannot express): per window the read records `key left right`
+    (cmd/muscato_window_reads/main.go:100-126) and the candidate records `key left right %011d pos`
+    (cmd/muscato_screen/main.go:294-365, incl. the position-0 record with its literal 100) in bytewise
+    line order (`LC_ALL=C sort`, cmd/muscato/main.go:237-385), the candidate-major / read-minor double
+    loop of searchpairs with its bounded result list (cmd/muscato_confirm/main.go:171-250, qinsert
+    :424-448), the union with exact de-duplication and the MMTol rule
+    (cmd/muscato_combine_windows/main.go:36-60).  Returns the set of matches.txt lines.  Pure Python,
+    small cases only."""
+    W, MRL, MM = cfg.WindowWidth, cfg.MaxReadLength, int(cfg.MaxMatches)
+    first = cfg.MatchMode == "first"
+    lines = set()
+    for q1 in cfg.Windows:
+        q2 = q1 + W
+        readrecs = {}
+        for r in seqs:
+            if len(r) >= q2 and (cfg.MinDinuc <= 0 or count_dinuc(r[q1:q2]) >= cfg.MinDinuc):
+                readrecs.setdefault(r[q1:q2], []).append((r[:q1], r[q2:]))
+        candrecs = {}
+        for g, t in enumerate(genes):
+            for p in range(0, len(t) - W + 1):
+                key = t[p:p + W]
+                if key not in readrecs:              # the merge join drops every other candidate
+                    continue
+                if p == 0:
+                    if q1 != 0:
+                        continue
+                    left, right = b"", t[W:min(100 - q2, len(t))]
+                else:
+                    if p - q1 < 0:
+                        continue
+                    left, right = t[p - q1:p], t[p + W:min(p + W + MRL - q2, len(t))]
+                candrecs.setdefault(key, []).append((left, right, b"%011d" % g, b"%d" % p))
+        for key, rr in readrecs.items():
+            rr = sorted(rr, key=lambda x: x[0] + b"\t" + x[1])
+            cc = sorted(candrecs.get(key, []), key=lambda x: b"\t".join(x))
+            kept = []                                # (nx, line)
+            stop = False
+            for ml, mr, mg, mp in cc:
+                for sl, sr in rr:
+                    if len(sr) > len(mr):
+                        continue
+                    nx = sum(a != b for a, b in zip(ml, sl)) + sum(a != b for a, b in zip(mr[:len(sr)], sr))
+                    if nx > int((1 - cfg.PMatch) * float(W + len(sl) + len(sr))):
+                        continue
+                    line = b"%s\t%s\t%d\t%d\t%s" % (sl + key + sr, ml + key + mr[:len(sr)], int(mp) - len(ml), nx, mg)
+                    if first:
+                        kept.append((nx, line))
+                        if len(kept) > MM:
+                            stop = True
+                            break
+                    else:
+                        kept.append((nx, line))
+                        i = len(kept) - 1
+                        while i > 0:
+                            j = (i - 1) // 2
+                            if kept[j][0] > kept[i][0]:
+                                kept[j], kept[i] = kept[i], kept[j]
+                                i = j
+                            else:
+                                break
+                        if len(kept) > MM:
+                            del kept[MM:]
+                if stop:
+                    break
+            lines.update(ln for _, ln in kept)
+    best = {}
+    for ln in lines:
+        f = ln.split(b"\t")
+        best[f[0]] = min(best.get(f[0], 1 << 30), int(f[3]))
+    return {ln for ln in lines if int(ln.split(b"\t")[3]) <= best[ln.split(b"\t")[0]] + cfg.MMTol}

@@ -113,3 +113,51 @@ def test_closed_form_knows_the_quirks():
     rx = gx[30:90]
     assert helpers.closed_form_matches(rx, gx, offs, cfg) == {(0, 30): 0}
     assert helpers.closed_form_matches(rx, g, offs, cfg) == {(0, 30): 1}
+
+
+def _repeats_case(seed):
+    """Tandem-repeat targets and many near-identical reads: key groups with far more passing pairs than
+    a small MaxMatches (the workload of the MaxMatches parity tests on the GPU)."""
+    rng = np.random.default_rng(seed)
+    unit = helpers.random_dna(rng, 37)
+    genes = [_mutate(rng, unit * 6, 0.02) + helpers.random_dna(rng, int(rng.integers(0, 30))) for _ in range(12)]
+    reads = []
+    for _ in range(150):
+        g = genes[int(rng.integers(0, len(genes)))]
+        p = int(rng.integers(0, len(g) - 50))
+        reads.append(_mutate(rng, g[p:p + 50], 0.03))
+    return reads, genes
+
+
+@pytest.mark.parametrize("mode,mm", [("best", 1), ("best", 3), ("best", 7), ("best", 40), ("first", 1), ("first", 5),
+                                     ("first", 40), ("best", 1000000)],
+                         ids=lambda v: str(v))
+def test_oracle_maxmatches_agrees_with_the_sequential_restatement(mode, mm, tmp_path, oracle_bin):
+    """Q7: the kept set depends on the order in which the reference meets the pairs; the oracle (C++,
+    GNU sort) and a pure-Python restatement of the same code lines must keep the same lines."""
+    reads, genes = _repeats_case(100 + mm)
+    cfgd = dict(Windows=[0, 12, 30], WindowWidth=10, MaxReadLength=50, PMatch=0.9, MinDinuc=0, MMTol=2,
+                BloomSize=1000000, NumHash=6, MaxMatches=mm, MatchMode=mode, MaxConfirmProcs=3)
+    fq, gs, gi = helpers.write_case(str(tmp_path), reads, None, genes)
+    out = helpers.oracle_pipeline(str(tmp_path), fq, gs, gi, cfgd)
+    cfg = Config(**{k: v for k, v in cfgd.items() if k in Config.__dataclass_fields__}).apply_defaults()
+    seqs, _, _ = formats.load_reads_sorted(out["reads_sorted"])
+    want = helpers.sequential_restatement(seqs, genes, cfg)
+    got = helpers.read_lines(out["matches"])
+    assert len(got) == len(set(got)) and set(got) == want
+    if mm < 1000:
+        full = helpers.sequential_restatement(seqs, genes, Config(**dict(cfg.__dict__, MaxMatches=1000000)))
+        assert want != full, "the limit must actually truncate"
+
+
+def test_sequential_restatement_equals_closed_form_without_truncation(tmp_path, oracle_bin):
+    """With MaxMatches out of reach the sequential structure and the closed form describe the same set."""
+    cfgd, n_genes, gene_lens, n_reads, read_lens, sub_rate, x_rate = CASES["x_bases_everywhere"]
+    cfgd = dict(cfgd, BloomSize=1000000, NumHash=6, MaxMatches=1000000, MatchMode="best")
+    rng = np.random.default_rng(99)
+    reads, genes = _case(rng, n_genes, gene_lens, n_reads, read_lens, sub_rate, x_rate)
+    fq, gs, gi = helpers.write_case(str(tmp_path), reads, None, genes)
+    out = helpers.oracle_pipeline(str(tmp_path), fq, gs, gi, cfgd)
+    cfg = Config(**{k: v for k, v in cfgd.items() if k in Config.__dataclass_fields__}).apply_defaults()
+    seqs, _, _ = formats.load_reads_sorted(out["reads_sorted"])
+    assert helpers.sequential_restatement(seqs, genes, cfg) == set(helpers.read_lines(out["matches"]))
