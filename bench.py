@@ -431,11 +431,11 @@ def run_ours(args, rank, local_rank, world):
     alg_bytes = shard_bases / 4.0 + 16.0 * n_cand   # T/4 + 16*H (Bloom front is L2-resident)
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
     # DRAM traffic of the scan kernel per launch from the committed `ncu --set full` capture of this
-    # exact workload (profiles/ncu_full_r01_v9_cold.txt: dram__bytes_read.sum 45.74 MB +
-    # dram__bytes_write.sum 0.75 MB, cold caches as ncu flushes them; 8.5 MB with warm caches,
-    # profiles/ncu_full_r01_v9_warm.txt).
+    # exact workload (profiles/ncu_full_r01_v10_cold.txt: dram__bytes_read.sum 45.66 MB +
+    # dram__bytes_write.sum 0.66 MB, cold caches as ncu flushes them; 6.6 + 2.6 MB with warm caches,
+    # profiles/ncu_full_r01_v10_warm.txt).
     default_workload = (world == 1 and args.reads == WORK["num_read"] and args.genes == WORK["num_gene"])
-    scan_traffic = 46.5e6 if default_workload else None
+    scan_traffic = 46.3e6 if default_workload else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
         "ms_per_step": 1000.0 * t_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
