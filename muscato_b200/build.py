@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libmuscato_b200.so")
 EXE_PATH = os.path.join(HERE, "bin", "muscato_b200_hotpath")
+GENDAT_PATH = os.path.join(HERE, "libmsc_gendat.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -34,9 +35,9 @@ def _deps():
 
 
 def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH) or not os.path.exists(EXE_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(EXE_PATH) or not os.path.exists(GENDAT_PATH):
         return True
-    t = min(os.path.getmtime(LIB_PATH), os.path.getmtime(EXE_PATH))
+    t = min(os.path.getmtime(LIB_PATH), os.path.getmtime(EXE_PATH), os.path.getmtime(GENDAT_PATH))
     return any(os.path.getmtime(p) > t for p in _deps() if os.path.exists(p))
 
 
@@ -54,7 +55,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(res.stderr)
     build_host_exe()
+    build_gendat()
     return LIB_PATH
+
+
+def build_gendat() -> str:
+    """The synthetic-workload generator (host C++, no CUDA): bench / test tooling in the shape of
+    muscato_gendat, kept out of libmuscato_b200.so."""
+    cxx = shutil.which("g++") or "g++"
+    cmd = [cxx, "-O3", "-std=c++17", "-Wall", "-shared", "-fPIC", "-o", GENDAT_PATH,
+           os.path.join(CSRC, "host", "gendat.cc")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return GENDAT_PATH
 
 
 def build_host_exe() -> str:

@@ -263,11 +263,30 @@ int enqueue_exclusive_scan(msc_ctx* ctx, const uint32_t* in, const unsigned long
   // one block per SM: the whole grid is resident, which the kernel's grid barrier relies on
   const unsigned grid = (unsigned)std::min(ctx->sm_count, kScanThreads);
   if (ctx->tile_sums.cap == 0) CK(ctx->tile_sums.reserve((size_t)kScanThreads * sizeof(uint64_t)));
-  ctx->scan_arrivals += grid;
-  launch_k(ctx->pdl, scan_resident_kernel<OutT>, grid, kScanThreads, 0, ctx->stream, in, n_ptr, n_host, out, write_end ? 1 : 0, total,
-                                                                     ctx->tile_sums.as<uint64_t>(),
-                                                                     ctx->scan_state.as<unsigned long long>(),
-                                                                     ctx->scan_arrivals);
+  // COOPERATIVE launch: the runtime starts the grid only when all of its blocks can be resident at
+  // the same time (or fails the launch), so the barrier cannot deadlock when other contexts or
+  // processes share the GPU (up to MaxConfirmProcs concurrent callers, cmd/muscato/main.go:391-420).
+  // The arrival target is advanced only once the launch is known to have been accepted.
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kScanThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const unsigned long long target = ctx->scan_arrivals + grid;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, scan_resident_kernel<OutT>, in, n_ptr, (uint64_t)n_host, out, write_end ? 1 : 0, total,
+                                       ctx->tile_sums.as<uint64_t>(), ctx->scan_state.as<unsigned long long>(), target);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      return ctx->fail(MSC_ERR_CUDA, "cooperative launch of the resident scan failed: %s", cudaGetErrorString(e));
+    }
+    ctx->scan_arrivals = target;
+  }
   LAUNCH_CHECK();
   return MSC_OK;
 }
@@ -276,8 +295,12 @@ int enqueue_exclusive_scan(msc_ctx* ctx, const uint32_t* in, const unsigned long
 // over-allocated by at least 256 bytes, so the round-up stays inside the allocation.
 struct Filler {
   FillJob job{};
+  bool overflow = false;  // more than kMaxFillJobs jobs: reported by enqueue_fill as an error
   void add(void* p, size_t bytes, unsigned int value = 0) {
-    if (job.n >= kMaxFillJobs) abort();  // programming error: raise kMaxFillJobs
+    if (job.n >= kMaxFillJobs) {
+      overflow = true;
+      return;
+    }
     job.ptr[job.n] = p;
     job.bytes[job.n] = (bytes + 15) & ~(size_t)15;
     job.value[job.n] = value;
@@ -316,6 +339,7 @@ void add_combine_fills(msc_ctx* ctx, Filler& f) {
 }
 
 int enqueue_fill(msc_ctx* ctx, const Filler& f) {
+  if (f.overflow) return ctx->fail(MSC_ERR_STATE, "internal: more than %d fill jobs in one prologue", kMaxFillJobs);
   if (f.job.n == 0) return MSC_OK;
   launch_k(ctx->pdl, fill_buffers_kernel, (unsigned)ctx->sm_count * 8, 256, 0, ctx->stream, f.job);
   LAUNCH_CHECK();
@@ -859,6 +883,9 @@ msc_ctx* msc_create(const msc_config* config, char* errbuf, uint64_t errlen) {
     if (c.windows[k] < 0) return fail("Windows: negative offset");
   if (c.match_mode != MSC_MATCH_FIRST && c.match_mode != MSC_MATCH_BEST)
     return fail("MatchMode must be 'first' or 'best'");
+  // nmiss = int((1 - PMatch) * L) is packed into 11 bits next to the read length: PMatch outside [0, 1]
+  // (negative budgets reject everything in the reference, budgets beyond L are meaningless) is refused
+  if (!(c.pmatch >= 0.0 && c.pmatch <= 1.0)) return fail("PMatch must be in [0, 1]");
   if (c.max_matches < 1) return fail("MaxMatches must be >= 1");
   if (c.mmtol < 0) return fail("MMTol must be >= 0");
 
@@ -948,6 +975,17 @@ void msc_destroy(msc_ctx* ctx) {
 
 const char* msc_last_error(const msc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+// Entry points that replace inputs or reuse the pair scratch must not run while a deferred
+// (MSC_STAGE_DEFER) screen + confirm is still in flight on the stream: the pending run is completed
+// and dropped first (its kernels may still be reading the buffers about to be overwritten).
+static int drop_deferred(msc_ctx* ctx) {
+  if (!ctx->deferred) return MSC_OK;
+  ctx->deferred = false;
+  RC(sync_counters(ctx));
+  ctx->have_cand = ctx->have_confirm = ctx->have_combine = false;
+  return MSC_OK;
+}
+
 // Size every read-side buffer and the key table for n_reads reads / total ASCII bytes.
 static int reads_reserve(msc_ctx* ctx, uint64_t n_reads, uint64_t total) {
   const uint64_t nwin = (uint64_t)ctx->win.nwin;
@@ -1013,6 +1051,7 @@ int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint
   if (!ctx) return MSC_ERR_STATE;
   if (n_reads && (!offs || (!ascii && offs[n_reads] != offs[0]))) return ctx->fail(MSC_ERR_INPUT, "reads: NULL buffer");
   CK(cudaSetDevice(ctx->device));
+  RC(drop_deferred(ctx));
   uint64_t total = 0;
   if (n_reads) {
     if (offs[0] != 0) return ctx->fail(MSC_ERR_INPUT, "reads: offs[0] must be 0");
@@ -1061,6 +1100,7 @@ int msc_set_reads_device(msc_ctx* ctx, const uint8_t* d_ascii, const uint64_t* d
   if (!ctx) return MSC_ERR_STATE;
   if (n_reads && (!d_offs || (!d_ascii && total_bytes))) return ctx->fail(MSC_ERR_INPUT, "reads: NULL device buffer");
   CK(cudaSetDevice(ctx->device));
+  RC(drop_deferred(ctx));
   RC(reads_reserve(ctx, n_reads, total_bytes));
   if (total_bytes) CK(cudaMemcpyAsync(ctx->rd_ascii.p, d_ascii, total_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   if (n_reads) CK(cudaMemcpyAsync(ctx->rd_offs.p, d_offs, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1095,6 +1135,7 @@ int msc_prep_reads(msc_ctx* ctx, const uint8_t* raw_ascii, const uint64_t* raw_o
   if (n_raw && (!raw_offs || (!raw_ascii && raw_offs[n_raw] != raw_offs[0]))) return ctx->fail(MSC_ERR_INPUT, "raw reads: NULL buffer");
   if (n_raw >= 0xffffffffull) return ctx->fail(MSC_ERR_INPUT, "raw reads: more than 2^32-1 reads in one call");
   CK(cudaSetDevice(ctx->device));
+  RC(drop_deferred(ctx));
   uint64_t total = 0;
   if (n_raw) {
     if (raw_offs[0] != 0) return ctx->fail(MSC_ERR_INPUT, "raw reads: offs[0] must be 0");
@@ -1278,6 +1319,7 @@ int msc_set_targets(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, ui
   if (!ctx) return MSC_ERR_STATE;
   if (n_targets && (!offs || (!ascii && offs[n_targets] != offs[0]))) return ctx->fail(MSC_ERR_INPUT, "targets: NULL buffer");
   CK(cudaSetDevice(ctx->device));
+  RC(drop_deferred(ctx));
   uint64_t total = 0;
   std::vector<uint32_t> off32(n_targets + 1, 0);
   if (n_targets) {
@@ -1589,6 +1631,7 @@ int msc_dump_candidates(msc_ctx* ctx, msc_cand_rec** out, uint64_t* n) {
   if (!ctx || !out || !n) return MSC_ERR_STATE;
   if (!ctx->have_cand) return ctx->fail(MSC_ERR_STATE, "msc_dump_candidates: run msc_screen first");
   CK(cudaSetDevice(ctx->device));
+  RC(drop_deferred(ctx));
   ScopedDevBuf tmp;
   uint64_t cnt = 0;
   int rc = MSC_OK;

@@ -152,7 +152,7 @@ def merge_survivors(gathered: np.ndarray, surv: Optional[np.ndarray], best_of_su
     return g
 
 
-def sharded_matches(hp, gene_offset: int, rebuild_what: int = 0, group=None, deferred: bool = True, dst: int = 0):
+def sharded_matches(hp, gene_offset: int, rebuild_what: int = 0, group=None, deferred: bool = False, dst: int = 0):
     """One complete sharded pass: step, the MaxMatches protocol when a shard flagged a group, gather.
     Returns on `dst` an int64 [n, 4] array (read, global gene, pos, nx) ordered by (read, gene, pos)."""
     import torch
@@ -177,14 +177,19 @@ def sharded_matches(hp, gene_offset: int, rebuild_what: int = 0, group=None, def
     return merge_survivors(allm.cpu().numpy(), surv, best_of, hp.cfg.MMTol)
 
 
-def sharded_step(hp, rebuild_what: int = 0, group=None, deferred: bool = True):
+def sharded_step(hp, rebuild_what: int = 0, group=None, deferred: bool = False):
     """One hot-path step over this rank's target shard: screen + confirm, MIN all-reduce of the
     per-read best array, combine.  deferred=True is the stream-ordered form (MSC_STAGE_DEFER): the
     stages are only enqueued on the context's stream, the all-reduce is ordered behind them on that
-    stream and the combine call synchronises once.  Use deferred=False for the first step on new
-    inputs (it sizes the bounded output buffers, so that a deferred step cannot ask for a repeat)."""
+    stream and the combine call synchronises once.  A deferred step can end in MSC_ERR_AGAIN on ONE
+    rank only (a bounded output buffer of that rank was grown, or MaxMatches truncation applies
+    there): no rank may raise between collectives, so the outcome is MAX-all-reduced as a status
+    word and, if any rank has to repeat, ALL ranks repeat the step together in the synchronising
+    form (which sizes the buffers and cannot ask for a repeat)."""
     import torch
     import torch.distributed as dist
+    from . import _capi
+    from .engine import MuscatoError
     multi = dist.is_initialized() and dist.get_world_size(group) > 1
     if not multi:
         hp.run_stages(rebuild_what, 1 | 2 | 4)
@@ -195,11 +200,22 @@ def sharded_step(hp, rebuild_what: int = 0, group=None, deferred: bool = True):
         best = torch.as_tensor(hp.best_device(), device=dev)
         with torch.cuda.stream(torch.cuda.ExternalStream(hp.stream(), device=dev)):
             dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
-    else:
-        hp.run_stages(rebuild_what, 1 | 2)
-        best = torch.as_tensor(hp.best_device(), device=dev)
-        _allreduce_min(best, group)
-        torch.cuda.synchronize()
+        again = 0
+        try:
+            hp.run_stages(0, 4)
+        except MuscatoError as e:
+            if e.code != _capi.MSC_ERR_AGAIN:
+                raise
+            again = 1
+        flag = torch.tensor([again], dtype=torch.int32, device=dev if _is_nccl(group) else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if int(flag.item()) == 0:
+            return
+        rebuild_what = 0   # the inputs are packed; only the stages are repeated
+    hp.run_stages(rebuild_what, 1 | 2)
+    best = torch.as_tensor(hp.best_device(), device=dev)
+    _allreduce_min(best, group)
+    torch.cuda.synchronize()
     hp.run_stages(0, 4)
 
 

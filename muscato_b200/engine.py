@@ -286,3 +286,112 @@ class HotPath:
 
     def reset_stats(self):
         self._lib.msc_reset_stats(self._ctx)
+
+
+# ---------------------------------------------------------------------------------------------
+# Inputs larger than one context call: read batches x target ranges.
+#
+# The reference streams inputs of any size (cmd/muscato_screen/main.go:408-480 reads the target
+# file line by line; cmd/muscato_confirm/main.go:98-148 streams the sorted record files).  One
+# msc_set_reads call takes at most 2^30 (read, window) items and one msc_set_targets call fewer than
+# 2^32 - 4096 bases (include/muscato_b200.h), so larger inputs are cut into tiles.  Reads are
+# independent of each other -- every rule of the path, MMTol included, is per read -- so read batches
+# need no exchange at all; target ranges of one read batch share the per-read minimum of the MMTol
+# rule (cmd/muscato_combine_windows/main.go:36-60): every tile is combined against its LOCAL minimum
+# (a superset of what survives globally, because the local minimum is >= the global one) and the
+# union is filtered once more against the minimum over all ranges.
+# ---------------------------------------------------------------------------------------------
+MAX_ITEMS_PER_READ_SET = 1 << 30
+MAX_BASES_PER_TARGET_SET = (1 << 32) - 8192
+
+
+def split_read_batches(n_reads: int, n_windows: int, max_items: int = MAX_ITEMS_PER_READ_SET):
+    """[lo, hi) read-index ranges with (hi - lo) * n_windows <= max_items, sizes as equal as possible."""
+    if n_reads <= 0:
+        return [(0, 0)]
+    per = max(1, max_items // max(1, n_windows))
+    nb = (n_reads + per - 1) // per
+    return [(n_reads * i // nb, n_reads * (i + 1) // nb) for i in range(nb)]
+
+
+def split_target_ranges(offs: np.ndarray, max_bases: int = MAX_BASES_PER_TARGET_SET):
+    """[lo, hi) target-index ranges of whole targets with at most max_bases bases each (greedy)."""
+    offs = np.asarray(offs)
+    G = len(offs) - 1
+    if G <= 0:
+        return [(0, 0)]
+    out = []
+    lo = 0
+    while lo < G:
+        limit = int(offs[lo]) + max_bases
+        hi = int(np.searchsorted(offs, limit, side="right")) - 1
+        if hi <= lo:
+            raise ValueError(f"target {lo} alone exceeds {max_bases} bases")
+        hi = min(hi, G)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def filter_by_global_best(parts, mmtol: int) -> np.ndarray:
+    """Union of per-range match arrays of ONE read batch (each already combined against its local
+    per-read minimum) -> the matches with nx <= global per-read minimum + MMTol, ordered by
+    (read, gene, pos)."""
+    parts = [p for p in parts if len(p)]
+    if not parts:
+        return np.zeros(0, dtype=MATCH_DTYPE)
+    if len(parts) == 1:
+        return parts[0]
+    m = np.concatenate(parts)
+    rid = m["read_id"].astype(np.int64)
+    order = np.lexsort((m["pos"], m["gene_id"], rid))
+    m = m[order]
+    rid = rid[order]
+    first = np.ones(len(m), dtype=bool)
+    first[1:] = rid[1:] != rid[:-1]
+    seg = np.cumsum(first) - 1
+    best = np.minimum.reduceat(m["nx"].astype(np.int64), np.nonzero(first)[0])
+    return m[m["nx"].astype(np.int64) <= best[seg] + int(mmtol)]
+
+
+def run_tiled(hp: "HotPath", reads, targets, max_items: int = MAX_ITEMS_PER_READ_SET,
+              max_bases: int = MAX_BASES_PER_TARGET_SET, on_tile=None) -> np.ndarray:
+    """The whole hot path over inputs of any size on one context: loops over read batches and target
+    ranges (see above), returns the matches with GLOBAL read and gene indices ordered by
+    (read, gene, pos).  reads / targets = (ascii uint8, offs uint64[n+1]).  MaxMatches truncation
+    is exact within a tile; a (window, k-mer) group that exceeds MaxMatches only through several
+    target ranges together is reported by raising MuscatoError (use one target range, or the sharded
+    protocol of dist.py, for such inputs)."""
+    ra, ro = HotPath._as_arrays(reads)
+    ta, to = HotPath._as_arrays(targets)
+    nwin = len(hp.cfg.Windows)
+    batches = split_read_batches(len(ro) - 1, nwin, max_items)
+    ranges = split_target_ranges(to, max_bases)
+    if len(ranges) > 1:
+        hp.set_shards(len(ranges))       # flag key groups above MaxMatches / n_ranges instead of truncating per range
+    out = []
+    try:
+        for (r0, r1) in batches:
+            a0, a1 = int(ro[r0]), int(ro[r1])
+            hp.set_reads((ra[a0:a1], ro[r0:r1 + 1] - ro[r0]))
+            parts = []
+            for (g0, g1) in ranges:
+                b0, b1 = int(to[g0]), int(to[g1])
+                hp.set_targets((ta[b0:b1], to[g0:g1 + 1] - to[g0]))
+                hp.run()
+                if len(ranges) > 1 and hp.shard_overflow():
+                    raise MuscatoError(_capi.MSC_ERR_STATE, "a key group may exceed MaxMatches across target ranges: "
+                                       "run it as one range or through dist.sharded_matches")
+                m = hp.fetch()
+                if on_tile is not None:
+                    on_tile((r0, r1), (g0, g1), hp.stats())
+                if len(m):
+                    m["gene_id"] += np.uint32(g0)
+                    m["read_id"] += np.uint32(r0)
+                parts.append(m)
+            out.append(filter_by_global_best(parts, hp.cfg.MMTol))
+    finally:
+        if len(ranges) > 1:
+            hp.set_shards(1)
+    out = [p for p in out if len(p)]
+    return np.concatenate(out) if out else np.zeros(0, dtype=MATCH_DTYPE)

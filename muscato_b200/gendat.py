@@ -133,3 +133,121 @@ def write_oracle_inputs(syn: Synthetic, fastq_path: str, genes_path: str, ids_pa
     with open(ids_path, "wb") as f:
         for i, t in enumerate(tg):
             f.write(b"%011d\tgene_%d\t%d\n" % (i, i, len(t)))
+
+
+# ---------------------------------------------------------------------------------------------
+# Block-structured generator for the large configurations (csrc/host/gendat.cc): S2 / S3 / S4.
+# ---------------------------------------------------------------------------------------------
+@dataclasses.dataclass(frozen=True)
+class BlockSpec:
+    """A workload of `n_blocks` independent blocks; block b depends on (seed, b) only.  Reads of a
+    block are `planted_per_block` copies (with sub256/256 substitutions per base) of windows of
+    the block's own targets followed by iid uniform reads."""
+    seed: int
+    n_blocks: int
+    reads_per_block: int
+    read_len: int
+    planted_per_block: int
+    sub256: int
+    genes_per_block: int
+    gene_len: int
+    rev: bool = True
+    period: int = 0           # > 0: tandem-repeat targets with units of 1..period bases (S4)
+    target_sub256: int = 0    # substitutions inside tandem-repeat targets
+
+    @property
+    def targets_per_block(self) -> int:
+        return self.genes_per_block * (2 if self.rev else 1)
+
+    @property
+    def n_reads(self) -> int:
+        return self.n_blocks * self.reads_per_block
+
+    @property
+    def n_targets(self) -> int:
+        return self.n_blocks * self.targets_per_block
+
+    @property
+    def target_bases(self) -> int:
+        return self.n_targets * self.gene_len
+
+    def prefix(self, n_blocks: int) -> "BlockSpec":
+        return dataclasses.replace(self, n_blocks=n_blocks)
+
+
+_gen_lib = None
+
+
+def _gendat_lib():
+    global _gen_lib
+    if _gen_lib is None:
+        import ctypes as C
+        import os
+        from . import build as _b
+        if not os.path.exists(_b.GENDAT_PATH):
+            _b.build_gendat()
+        lib = C.CDLL(_b.GENDAT_PATH)
+        lib.msc_gen_targets.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32,
+                                        C.c_void_p]
+        lib.msc_gen_targets.restype = None
+        lib.msc_gen_reads.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                      C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.msc_gen_reads.restype = None
+        _gen_lib = lib
+    return _gen_lib
+
+
+def generate_blocks(spec: BlockSpec, blocks=None, reads_out: np.ndarray = None, targets_out: np.ndarray = None,
+                    want_reads: bool = True, want_targets: bool = True, want_plants: bool = False, threads: int = None):
+    """Generate blocks `blocks` (default: all) of `spec` on all host threads.  Returns
+    (reads uint8 [n*rpb*L] or None, targets uint8 [n*tpb*GL] or None, plants or None) where plants =
+    (gene int64 [n*planted] as GLOBAL-in-this-selection target index, pos int32).  reads_out /
+    targets_out may be preallocated (e.g. pinned) uint8 buffers of the right size."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    lib = _gendat_lib()
+    blocks = list(range(spec.n_blocks)) if blocks is None else list(blocks)
+    nb = len(blocks)
+    rbytes = spec.reads_per_block * spec.read_len
+    tbytes = spec.targets_per_block * spec.gene_len
+    reads = targets = None
+    if want_reads:
+        reads = reads_out if reads_out is not None else np.empty(nb * rbytes, dtype=np.uint8)
+        assert reads.dtype == np.uint8 and reads.size == nb * rbytes and reads.flags.c_contiguous
+    if want_targets:
+        targets = targets_out if targets_out is not None else np.empty(nb * tbytes, dtype=np.uint8)
+        assert targets.dtype == np.uint8 and targets.size == nb * tbytes and targets.flags.c_contiguous
+    pg = pp = None
+    if want_plants and want_reads:
+        pg = np.zeros(nb * spec.planted_per_block, dtype=np.int32)
+        pp = np.zeros(nb * spec.planted_per_block, dtype=np.int32)
+
+    def one(i):
+        b = blocks[i]
+        if want_targets:
+            tv = targets[i * tbytes:(i + 1) * tbytes]
+        else:
+            tv = np.empty(tbytes, dtype=np.uint8)
+        if want_targets or want_reads:
+            lib.msc_gen_targets(spec.seed, b, spec.genes_per_block, spec.gene_len, int(spec.rev), spec.period,
+                                spec.target_sub256, tv.ctypes.data)
+        if want_reads:
+            rv = reads[i * rbytes:(i + 1) * rbytes]
+            n_pl = spec.planted_per_block
+            lib.msc_gen_reads(spec.seed, b, spec.reads_per_block, spec.read_len, n_pl, spec.sub256, tv.ctypes.data,
+                              spec.targets_per_block, spec.gene_len, rv.ctypes.data,
+                              pg[i * n_pl:].ctypes.data if pg is not None and n_pl else None,
+                              pp[i * n_pl:].ctypes.data if pp is not None and n_pl else None)
+
+    threads = threads or min(32, os.cpu_count() or 1)
+    if nb <= 1 or threads <= 1:
+        for i in range(nb):
+            one(i)
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(one, range(nb)))
+    plants = None
+    if pg is not None:
+        g = pg.astype(np.int64) + np.repeat(np.arange(nb, dtype=np.int64) * spec.targets_per_block, spec.planted_per_block)
+        plants = (g, pp)
+    return reads, targets, plants

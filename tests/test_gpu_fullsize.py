@@ -152,3 +152,37 @@ def test_sharded_halves_reproduce_the_whole(workload):
     got = np.concatenate(parts)
     got = got[np.lexsort((got["pos"], got["gene_id"], got["read_id"]))]
     assert np.array_equal(got, m)
+
+
+@pytest.mark.parametrize("rev", [False, True], ids=["fwd", "rev"])
+def test_full_size_outputs_equal_the_oracle_byte_for_byte(rev, tmp_path, oracle_bin):
+    """BASELINE.json config[1] at FULL size (1M reads x 10k x 2 kb targets; with -rev 20k targets /
+    40 Mbp): matches.txt, results.txt and the non-match fastq of the CUDA path against the oracle's
+    files, byte for byte (cmd/muscato_confirm/main.go:171-250, cmd/muscato_combine_windows/main.go:36-60,
+    cmd/muscato/main.go:507-676, cmd/muscato_nonmatch/main.go:57-113)."""
+    import os
+    from muscato_b200 import formats
+    from muscato_b200.engine import HotPath
+    from tests import helpers
+    syn = gendat.generate(1_000_000, 100, 10_000, 2000, seed=1, mutated_fraction=0.5, sub_rate=0.02, rev=rev)
+    cfgd = dict(CFG, BloomSize=400000000, NumHash=20, Threads=os.cpu_count() or 4)
+    cfg = Config(**CFG).apply_defaults()
+    work = str(tmp_path)
+    fq, gs, gi = (os.path.join(work, n) for n in ("reads.fastq", "genes_seq.txt", "genes_ids.txt"))
+    gendat.write_oracle_inputs(syn, fq, gs, gi)
+    out = helpers.oracle_pipeline(work, fq, gs, gi, cfgd)
+    seqs, counts, names = formats.load_reads_sorted(out["reads_sorted"])
+    assert len(seqs) == syn.n_reads
+    targets = syn.targets_list()
+    with HotPath(cfg, device=0) as hp:
+        hp.set_reads((syn.read_ascii, syn.read_offs))
+        hp.set_targets((syn.target_ascii, syn.target_offs))
+        hp.run()
+        m = hp.fetch()
+        nm = hp.nonmatch_ids()
+    assert len(m) > 500_000
+    assert formats.matches_lines(m, seqs, targets) == helpers.read_lines(out["matches"])
+    gnames, glens = formats.load_gene_ids(gi)
+    res = b"".join(ln + b"\n" for ln in formats.results_lines(m, seqs, counts, names, targets, gnames, glens))
+    assert res == helpers.read_bytes(out["results"])
+    assert formats.nonmatch_fastq_from_ids(nm, seqs, counts, names) == helpers.read_bytes(out["nonmatch"])
