@@ -138,6 +138,20 @@ int msc_fetch_unique_reads(msc_ctx* ctx, uint8_t* ascii, uint64_t* offs);
  * (shard larger databases by target range).  Uploads and 2-bit packs on the device. */
 int msc_set_targets(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint64_t n_targets);
 
+/* Targets that are ALREADY 2-bit packed (the persistent target cache `<GeneFileName>.2bit` of the stage
+ * executable, SURVEY.md 8(f) row f4: the database is parsed and packed once, later runs upload
+ * 0.25 bytes per base instead of re-reading the text).  Layout of common.cuh: base i of the concatenated
+ * stream of all targets sits in word i >> 5 at bits 2*(i & 31), codes A=0 C=1 T=2 G=3; xplane (same
+ * spacing, bit 2*(i & 31) set = the base is X, its code bits 0) may be NULL when no target contains X.
+ * words / xplane have (offs[n_targets] + 31) / 32 entries.  Same limits as msc_set_targets. */
+int msc_set_targets_packed(msc_ctx* ctx, const uint64_t* words, const uint64_t* xplane, const uint64_t* offs,
+                           uint64_t n_targets);
+
+/* The packed form of the current targets (after msc_set_targets), to write such a cache: words and
+ * xplane need msc_packed_target_words() entries each; *has_x receives whether any base is X. */
+uint64_t msc_packed_target_words(const msc_ctx* ctx);
+int msc_fetch_packed_targets(msc_ctx* ctx, uint64_t* words, uint64_t* xplane, int32_t* has_x);
+
 /* Re-run the device-side pack/build from the resident ASCII copies (keep_ascii=1);
  * what: 1 = reads (+ key table), 2 = targets, 3 = both.  Used to time the hot path
  * with inputs already in HBM. */

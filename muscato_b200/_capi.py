@@ -82,6 +82,9 @@ _SIGS = [
     ("msc_unique_reads_bytes", C.c_uint64, [C.c_void_p]),
     ("msc_fetch_unique_reads", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("msc_set_targets", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    ("msc_set_targets_packed", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    ("msc_packed_target_words", C.c_uint64, [C.c_void_p]),
+    ("msc_fetch_packed_targets", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     ("msc_rebuild", C.c_int, [C.c_void_p, C.c_int]),
     ("msc_screen", C.c_int, [C.c_void_p]),
     ("msc_confirm", C.c_int, [C.c_void_p]),

@@ -14,6 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libmuscato_b200.so")
 EXE_PATH = os.path.join(HERE, "bin", "muscato_b200_hotpath")
 GENDAT_PATH = os.path.join(HERE, "libmsc_gendat.so")
+STAGE_NAMES = ("muscato_screen", "muscato_confirm", "muscato_combine_windows")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -81,6 +82,13 @@ def build_host_exe() -> str:
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    # the per-stage names of the unmodified reference driver (cmd/muscato/main.go:310, :402, :442-469):
+    # the same binary, dispatching on argv[0]
+    for name in STAGE_NAMES:
+        link = os.path.join(os.path.dirname(EXE_PATH), name)
+        if os.path.lexists(link):
+            os.remove(link)
+        os.symlink(os.path.basename(EXE_PATH), link)
     return EXE_PATH
 
 

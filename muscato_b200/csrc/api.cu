@@ -128,21 +128,26 @@ struct msc_ctx {
   uint64_t n_reads = 0;
   bool have_reads = false;
   DevBuf rd_ascii, rd_offs, rd_words, rd_x, len_flags, validmask, rmeta;
-  // key table
-  int lg_slots = 0, lg_bloom = 0;
+  // key table (common.cuh / build.cuh): 128-byte buckets, partitioned build
+  TableGeom tgeo{};
+  uint64_t n_slots = 0;  // kBucketSlots * n_buckets
+  int lg_bloom = 0;
   BloomGeom geom{};
   uint64_t n_keys = 0, n_groups = 0, n_dup = 0;
-  DevBuf tab_fp, tab_item0, tab_cnt, tab_start, tab_fill, pass_cnt, bloom, items, dup_slot;
+  DevBuf tab, recs, dups, part_count, pass_small, pass_cnt, bloom, items;
+  int lg_small = 22;          // hashed passing-pair counters of the MaxMatches pre-check (16 MB: L2-resident)
+  bool exact_counts = false;  // the pair kernel also keeps exact per-slot counts (after a small counter exceeded MaxMatches)
   // zero-fills already issued by a merged prologue launch (consumed by the stage that owns them)
   struct { bool reads = false, targets = false, scan = false, pairs = false, combine = false; } pro;
   // targets
   uint64_t n_targets = 0, n_bases = 0, n_words_alloc = 0, n_tiles = 0;
   bool have_targets = false;
+  bool targets_packed = false;  // set by msc_set_targets_packed: no ASCII copy, rebuild(2) has nothing to redo
   DevBuf tg_ascii, tg_off, tg_words, tg_x, xsum, blk2gene;
   // candidates / pairs
   uint64_t n_cand = 0, n_pairs = 0;
   bool have_cand = false;
-  DevBuf cand, cinfo, sizes, pstart, block_first;
+  DevBuf cand, cmeta, cinfo, sizes, pstart, block_first;
   // matches
   uint64_t n_match_pre = 0, n_match = 0;
   bool have_confirm = false, have_combine = false;
@@ -311,13 +316,11 @@ struct Filler {
 // The zero-fills every stage needs before it runs.  A fused run issues them all in ONE prologue
 // launch (add_*_fills + ctx->pro flags); a stage enqueued on its own issues just its own.
 void add_reads_fills(msc_ctx* ctx, Filler& f) {
-  const uint64_t slots = 1ull << ctx->lg_slots;
   f.add(ctx->len_flags.p, (ctx->n_reads + 1) * sizeof(uint32_t));
   f.add(ctx->ctr(C_NKEYS), 4 * sizeof(unsigned long long));  // C_NKEYS, C_NGROUPS, C_NDUP, C_SCRATCH
-  f.add(ctx->tab_fp.p, slots * sizeof(uint64_t));
-  f.add(ctx->tab_cnt.p, slots * sizeof(uint32_t));
-  f.add(ctx->tab_fill.p, slots * sizeof(uint32_t));
-  f.add(ctx->bloom.p, (1ull << ctx->lg_bloom) * sizeof(uint64_t));  // build_keys_insert_kernel sets the bits
+  f.add(ctx->part_count.p, kMaxParts * sizeof(unsigned int));
+  f.add(ctx->bloom.p, (1ull << ctx->lg_bloom) * sizeof(uint64_t));  // build_windows_kernel sets the bits
+  // (the table's fingerprints are cleared by table_clear_kernel: 64 of every 128 bytes)
 }
 void add_targets_fills(msc_ctx* ctx, Filler& f) {
   f.add(ctx->tg_x.p, ctx->n_words_alloc * sizeof(uint64_t));
@@ -330,7 +333,8 @@ void add_scan_fills(msc_ctx* ctx, Filler& f) {
 void add_pairs_fills(msc_ctx* ctx, Filler& f) {
   f.add(ctx->ctr(C_NMATCH), 4 * sizeof(unsigned long long));  // C_NMATCH, C_NPASS, C_NOVER, C_NOUT
   f.add(ctx->best.p, (ctx->n_reads + 1) * sizeof(uint32_t), MSC_NO_MATCH);
-  f.add(ctx->pass_cnt.p, (1ull << ctx->lg_slots) * sizeof(uint32_t));
+  f.add(ctx->pass_small.p, (1ull << ctx->lg_small) * sizeof(uint32_t));
+  if (ctx->exact_counts) f.add(ctx->pass_cnt.p, ctx->n_slots * sizeof(uint32_t));
 }
 void add_combine_fills(msc_ctx* ctx, Filler& f) {
   f.add(ctx->rcount.p, (ctx->n_reads + 1) * sizeof(uint32_t));
@@ -414,7 +418,6 @@ int enqueue_build_reads(msc_ctx* ctx) {
   CK(cudaEventRecord(ctx->ev_rd_free, ctx->stream));
   if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_PACKR1], ctx->stream));
 
-  const uint64_t n_items = U * (uint64_t)ctx->win.nwin;
   if (U) {
     BuildArgs a{};
     a.rd_words = ctx->rd_words.as<uint64_t>();
@@ -425,24 +428,35 @@ int enqueue_build_reads(msc_ctx* ctx) {
     a.validmask = ctx->validmask.as<uint32_t>();
     a.rmeta = ctx->rmeta.as<uint2>();
     a.n_keys = ctx->ctr(C_NKEYS);
-    a.tab_fp = ctx->tab_fp.as<uint64_t>();
-    a.tab_item0 = ctx->tab_item0.as<uint32_t>();
-    a.tab_cnt = ctx->tab_cnt.as<uint32_t>();
-    a.lg_slots = ctx->lg_slots;
-    a.dup_slot = ctx->dup_slot.as<uint32_t>();
+    a.tab = ctx->tab.as<uint8_t>();
+    a.tg = ctx->tgeo;
+    a.part_count = ctx->part_count.as<unsigned int>();
+    a.recs = ctx->recs.as<uint4>();
+    a.dups = ctx->dups.as<uint4>();
+    a.n_dup = ctx->ctr(C_NDUP);
+    a.n_alloc = ctx->ctr(C_SCRATCH);
+    a.items = ctx->items.as<uint2>();
     a.bloom = ctx->bloom.as<unsigned long long>();
     a.geom = ctx->geom;
-    launch_k(ctx->pdl, build_keys_insert_kernel, grid_for(U, 256), 256, 0, ctx->stream, ctx->win, a);
+    const unsigned g8 = (unsigned)ctx->sm_count * 8;
+    const uint64_t n_items = U * (uint64_t)ctx->win.nwin;
+    launch_k(ctx->pdl, table_clear_kernel, (unsigned)std::min<uint64_t>(grid_for(ctx->tgeo.n_buckets * 4, 256), (uint64_t)ctx->sm_count * 32),
+             256, 0, ctx->stream, ctx->tab.as<uint8_t>(), ctx->tgeo.n_buckets);
     LAUNCH_CHECK();
-  }
-  if (U) {
-    launch_k(ctx->pdl, build_alloc_kernel, grid_for(n_items, 256), 256, 0, ctx->stream, 
-        ctx->dup_slot.as<uint32_t>(), n_items, ctx->tab_cnt.as<uint32_t>(), ctx->tab_fill.as<uint32_t>(),
-        ctx->tab_start.as<uint32_t>(), ctx->ctr(C_NDUP));
+    launch_k(ctx->pdl, build_windows_kernel, (unsigned)std::min<uint64_t>(grid_for(U, 256), g8), 256, 0, ctx->stream, ctx->win, a);
     LAUNCH_CHECK();
-    launch_k(ctx->pdl, build_fill_kernel, grid_for(n_items, 256), 256, 0, ctx->stream, 
-        ctx->dup_slot.as<uint32_t>(), n_items, ctx->tab_start.as<uint32_t>(), ctx->tab_fill.as<uint32_t>(),
-        ctx->rmeta.as<uint2>(), (uint32_t)ctx->win.nwin, ctx->items.as<uint4>());
+    launch_k(ctx->pdl, build_offsets_kernel, 1, kMaxParts, 0, ctx->stream, ctx->part_count.as<unsigned int>(), (int)ctx->tgeo.n_parts);
+    LAUNCH_CHECK();
+    launch_k(ctx->pdl, build_scatter_kernel, (unsigned)std::min<uint64_t>(grid_for(n_items, kStageKeys), (uint64_t)ctx->sm_count * 5), 256, 0,
+             ctx->stream, ctx->win, a);
+    LAUNCH_CHECK();
+    launch_k(ctx->pdl, build_insert_kernel, (unsigned)std::min<uint64_t>(grid_for(n_items, 256), g8), 256, 0, ctx->stream, a);
+    LAUNCH_CHECK();
+    launch_k(ctx->pdl, build_dup_count_kernel, g8, 256, 0, ctx->stream, a);
+    LAUNCH_CHECK();
+    launch_k(ctx->pdl, build_dup_alloc_kernel, g8, 256, 0, ctx->stream, a);
+    LAUNCH_CHECK();
+    launch_k(ctx->pdl, build_dup_fill_kernel, g8, 256, 0, ctx->stream, a);
     LAUNCH_CHECK();
   }
   if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_BUILD1], ctx->stream));
@@ -458,7 +472,7 @@ void account_build_reads(msc_ctx* ctx) {
   ctx->st.n_reads = ctx->n_reads;
   ctx->st.n_keys = ctx->n_keys;
   ctx->st.n_key_groups = ctx->n_groups;
-  ctx->st.table_slots = 1ull << ctx->lg_slots;
+  ctx->st.table_slots = ctx->n_slots;
   ctx->st.bloom_bytes = (1ull << ctx->lg_bloom) * sizeof(uint64_t);
   if (ctx->stage_events) {
     ctx->st.ms_pack_reads += elapsed(ctx, EV_PACKR0, EV_PACKR1);
@@ -491,6 +505,13 @@ void account_pack_targets(msc_ctx* ctx) {
   ctx->st.target_bases = ctx->n_bases;
 }
 
+// The candidate list is two parallel arrays: (slot, position) and the slot's record.
+int reserve_cand(msc_ctx* ctx, uint64_t n) {
+  CK(ctx->cand.reserve(n * sizeof(uint2)));
+  CK(ctx->cmeta.reserve((ctx->cand.cap / sizeof(uint2) + 1) * sizeof(uint4)));
+  return MSC_OK;
+}
+
 // ---- enqueue: scan ---------------------------------------------------------------------------
 template <int KW>
 void (*pick_scan_wn(int wn))(const ScanArgs) {
@@ -511,7 +532,7 @@ void (*pick_scan_kernel(int W, int wn))(const ScanArgs) {
 }
 
 int enqueue_scan(msc_ctx* ctx) {
-  if (ctx->cand.cap == 0) CK(ctx->cand.reserve(std::max<uint64_t>(1u << 20, ctx->n_bases / 16) * sizeof(uint2)));
+  if (ctx->cand.cap == 0) RC(reserve_cand(ctx, std::max<uint64_t>(1u << 20, ctx->n_bases / 16)));
   void (*scan_fn)(const ScanArgs) = pick_scan_kernel(ctx->win.W, ctx->geom.wn);
   if (ctx->scan_grid == 0 || ctx->scan_fn_sized != (const void*)scan_fn) {
     int blocks_per_sm = 0;
@@ -536,9 +557,10 @@ int enqueue_scan(msc_ctx* ctx) {
     a.bloom = ctx->bloom.as<uint2>();
     a.geom = ctx->geom;
     for (int j = 0; j < 8; j++) a.mul[j] = j < ctx->geom.wn ? 1u << (32 - 2 * ctx->geom.m - 2 * j) : 0u;
-    a.tab_fp = ctx->tab_fp.as<uint64_t>();
-    a.lg_slots = ctx->lg_slots;
+    a.tab = ctx->tab.as<uint8_t>();
+    a.n_buckets = ctx->tgeo.n_buckets;
     a.cand = ctx->cand.as<uint2>();
+    a.cmeta = ctx->cmeta.as<uint4>();
     a.cand_cap = ctx->cand_cap();
     a.n_cand = ctx->ctr(C_NCAND);
     a.n_bloom_pass = ctx->ctr(C_BLOOMPASS);
@@ -560,11 +582,8 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   if (ctx->block_first.cap == 0) CK(ctx->block_first.reserve(((size_t)(1u << 19) + 2) * sizeof(uint32_t)));
   if (outbuf.cap == 0) CK(outbuf.reserve((size_t)(1u << 20) * sizeof(uint4)));
   const unsigned pgrid = (unsigned)ctx->sm_count * 8;
-  launch_k(ctx->pdl, cand_prepare_kernel, pgrid, 256, 0, ctx->stream, ctx->cand.as<uint2>(), ctx->ctr(C_NCAND), ccap,
-                                                      ctx->tab_cnt.as<uint32_t>(), ctx->tab_item0.as<uint32_t>(),
-                                                      ctx->tab_start.as<uint32_t>(), ctx->tg_off.as<uint32_t>(),
-                                                      ctx->blk2gene.as<uint32_t>(), ctx->win.W, ctx->rmeta.as<uint2>(),
-                                                      ctx->win.nwin == 1 ? 0ull : (~0ull / (uint64_t)ctx->win.nwin) + 1ull,
+  launch_k(ctx->pdl, cand_prepare_kernel, pgrid, 256, 0, ctx->stream, ctx->cand.as<uint2>(), ctx->cmeta.as<uint4>(), ctx->ctr(C_NCAND), ccap,
+                                                      ctx->tg_off.as<uint32_t>(), ctx->blk2gene.as<uint32_t>(), ctx->win.W,
                                                       ctx->cinfo.as<uint4>(), ctx->sizes.as<uint32_t>());
   LAUNCH_CHECK();
   RC(enqueue_exclusive_scan<uint64_t>(ctx, ctx->sizes.as<uint32_t>(), ctx->ctr(C_NCAND), ccap, ctx->pstart.as<uint64_t>(),
@@ -587,9 +606,12 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   a.pstart = ctx->pstart.as<uint64_t>();
   a.n_pairs_ptr = ctx->ctr(C_NPAIRS);
   a.block_cap = ctx->block_cap();
-  a.items = ctx->items.as<uint4>();
+  a.items = ctx->items.as<uint2>();
+  a.validmask = ctx->validmask.as<uint32_t>();
   a.cand = ctx->cand.as<uint2>();
-  a.pass_cnt = ctx->pass_cnt.as<uint32_t>();
+  a.pass_small = ctx->pass_small.as<uint32_t>();
+  a.lg_small = ctx->lg_small;
+  a.pass_cnt = ctx->exact_counts ? ctx->pass_cnt.as<uint32_t>() : nullptr;
   a.rd_words = ctx->rd_words.as<uint64_t>();
   a.rd_x = ctx->rd_x.as<uint64_t>();
   a.tg_words = ctx->tg_words.as<uint64_t>();
@@ -607,8 +629,8 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   a.mode = mode;
   if (mode == 2) {
     a.slot_over = ctx->pair_mode2.slot_over;
-    a.tab_fp = ctx->tab_fp.as<uint64_t>();
-    a.lg_slots = ctx->lg_slots;
+    a.tab = ctx->tab.as<uint8_t>();
+    a.n_buckets = ctx->tgeo.n_buckets;
     a.over = ctx->pair_mode2.over;
     a.over_cap = ctx->pair_mode2.over_cap;
     a.n_over_inst = ctx->ctr(C_NLONG);
@@ -626,11 +648,12 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   if (mode == 0) {
     // MaxMatches pre-check (cmd/muscato_confirm/main.go:233-242, :424-448): truncation can only
     // happen in a key group with more than MaxMatches passing pairs.
-    const uint64_t slots = 1ull << ctx->lg_slots;
     const unsigned long long thr = ctx->n_shards > 1 ? (unsigned long long)ctx->cfg.max_matches / (unsigned long long)ctx->n_shards
                                                      : (unsigned long long)ctx->cfg.max_matches;
-    launch_k(ctx->pdl, overflow_count_kernel, (unsigned)ctx->sm_count * 8, 256, 0, ctx->stream, 
-        ctx->pass_cnt.as<uint32_t>(), slots, thr, ctx->ctr(C_NPASS), ctx->ctr(C_NOVER),
+    // exact per-slot counts once they are kept, else the small hashed counters (upper bounds)
+    launch_k(ctx->pdl, overflow_count_kernel, (unsigned)ctx->sm_count * 8, 256, 0, ctx->stream,
+        ctx->exact_counts ? ctx->pass_cnt.as<uint32_t>() : ctx->pass_small.as<uint32_t>(),
+        ctx->exact_counts ? ctx->n_slots : (1ull << ctx->lg_small), thr, ctx->ctr(C_NPASS), ctx->ctr(C_NOVER),
         ctx->n_shards > 1 ? ctx->best.as<uint32_t>() + ctx->n_reads : (uint32_t*)nullptr);
     LAUNCH_CHECK();
   }
@@ -695,7 +718,7 @@ int finish_scan(msc_ctx* ctx) {
   ctx->st.ms_scan_kernel = ms;
   ctx->n_cand = ctx->h_counters[C_NCAND];
   if (ctx->n_cand > ctx->cand_cap()) {
-    CK(ctx->cand.reserve(ctx->n_cand * sizeof(uint2)));
+    RC(reserve_cand(ctx, ctx->n_cand));
     ctx->have_cand = false;
     return NEED_RETRY;
   }
@@ -739,6 +762,14 @@ int finish_confirm(msc_ctx* ctx) {
   ctx->st.n_pass = ctx->h_counters[C_NPASS];
   ctx->st.n_matches_pre = ctx->n_match_pre;
   ctx->st.n_overflow_groups = ctx->h_counters[C_NOVER];
+  if (ctx->st.n_overflow_groups && !ctx->exact_counts) {
+    // a small counter exceeds the limit: some key group MAY hold more than MaxMatches (/ n_shards) passing
+    // pairs.  Keep exact per-slot counts from now on and run the pair kernel again.
+    CK(ctx->pass_cnt.reserve(ctx->n_slots * sizeof(uint32_t)));
+    ctx->exact_counts = true;
+    ctx->st.n_overflow_groups = 0;
+    return NEED_RETRY;
+  }
   if (ctx->st.n_overflow_groups && ctx->n_shards <= 1) {
     // Some key group holds more passing pairs than MaxMatches: replay the reference's
     // order-dependent truncation for those groups (rare path, host assisted).
@@ -842,7 +873,10 @@ int run_pipeline(msc_ctx* ctx, int rebuild_what, bool do_scan, bool do_confirm, 
     }
     if (rc == MSC_OK && do_combine) rc = finish_combine(ctx);
     if (rc != NEED_RETRY) return rc;
-    if (!ctx->have_cand) do_scan = true;  // the candidate buffer was grown: scan again
+    do_scan = !ctx->have_cand;  // scan again only if the candidate buffer was grown
+    if (do_scan || do_confirm) {  // the prologue's zero-fills were consumed: the repeated stages issue their own
+      ctx->pro.scan = ctx->pro.pairs = false;
+    }
   }
   return ctx->fail(MSC_ERR_NOMEM, "output buffers kept overflowing");
 }
@@ -900,6 +934,12 @@ msc_ctx* msc_create(const msc_config* config, char* errbuf, uint64_t errlen) {
   if (cudaGetDeviceProperties(&prop, c.device) != cudaSuccess) return fail("cudaGetDeviceProperties failed");
   if (prop.major != 10) return fail("device is not sm_100 (Blackwell B200); kernels are built for sm_100a only");
 
+  // Random 32-byte sector reads (Bloom words, table buckets, read rows) are the bulk of the traffic
+  // at scale; the L2's default fetch granularity pulls whole 128-byte lines from HBM for them.
+  // MSC_L2_FETCH = 32 / 64 / 128 sets cudaLimitMaxL2FetchGranularity (a hint; device-wide).
+  if (const char* e = getenv("MSC_L2_FETCH")) {
+    if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)) != cudaSuccess) (void)cudaGetLastError();
+  }
   msc_ctx* ctx = new msc_ctx();
   ctx->cfg = c;
   ctx->device = c.device;
@@ -952,8 +992,8 @@ void msc_destroy(msc_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->rd_ascii,    &ctx->rd_offs,   &ctx->rd_words, &ctx->rd_x,      &ctx->len_flags, &ctx->validmask, &ctx->rmeta,
-                    &ctx->tab_fp,      &ctx->tab_item0, &ctx->tab_cnt,  &ctx->tab_start, &ctx->tab_fill,  &ctx->pass_cnt, &ctx->bloom,
-                    &ctx->items,       &ctx->dup_slot,  &ctx->tg_ascii,  &ctx->tg_off,    &ctx->tg_words,
+                    &ctx->tab,         &ctx->recs,      &ctx->dups,     &ctx->part_count, &ctx->pass_small, &ctx->pass_cnt, &ctx->bloom,
+                    &ctx->items,       &ctx->cmeta,     &ctx->tg_ascii,  &ctx->tg_off,    &ctx->tg_words,
                     &ctx->tg_x,        &ctx->xsum,      &ctx->blk2gene,  &ctx->prep_perm, &ctx->prep_gstart, &ctx->nm_flag, &ctx->nm_pos, &ctx->nm_list, &ctx->cand,     &ctx->cinfo,     &ctx->sizes,     &ctx->pstart,
                     &ctx->block_first, &ctx->match_pre, &ctx->best,     &ctx->rcount,    &ctx->rstart,    &ctx->rfill,
                     &ctx->match_out,   &ctx->long_list, &ctx->mid_list, &ctx->counters,  &ctx->tile_sums, &ctx->scan_state, &ctx->nmiss};
@@ -1003,7 +1043,24 @@ static int reads_reserve(msc_ctx* ctx, uint64_t n_reads, uint64_t total) {
   CK(ctx->validmask.reserve((n_reads + 1) * sizeof(uint32_t)));
   CK(ctx->rmeta.reserve((n_reads + 1) * sizeof(uint2)));
   const uint64_t kmax = std::max<uint64_t>(n_reads * nwin, 512);
-  ctx->lg_slots = ceil_log2(2 * kmax);
+  // Key table geometry: five-slot buckets at a load factor <= 0.45 of the possible keys, cut into
+  // partitions of 2^lg_bpp buckets (16 MB of table each, so that the partition-ordered insert works
+  // inside the L2); at most kMaxParts partitions.
+  {
+    const uint64_t need = (kmax * 4 + 8) / 9;  // buckets: kmax / (5 * 0.45)
+    int lg_bpp = 17;
+    if (need <= (1ull << lg_bpp)) lg_bpp = std::max(3, ceil_log2(need));
+    uint64_t parts = (need + (1ull << lg_bpp) - 1) >> lg_bpp;
+    while (parts > (uint64_t)kMaxParts) {
+      lg_bpp++;
+      parts = (need + (1ull << lg_bpp) - 1) >> lg_bpp;
+    }
+    ctx->tgeo.lg_bpp = lg_bpp;
+    ctx->tgeo.n_parts = (uint32_t)parts;
+    ctx->tgeo.n_buckets = parts << lg_bpp;
+    ctx->n_slots = ctx->tgeo.n_buckets * (uint64_t)kBucketSlots;
+    ctx->exact_counts = false;
+  }
   // Bloom front sizing (tuning only, never changes results): aim at 32-64 bits per key, but keep
   // the filter L2-resident (<= 64 MB of the 126 MB L2) as long as that still leaves >= 12 bits per
   // key -- a probe served from L2 is ~5x cheaper than one served from an HBM sector, and a 1 %
@@ -1030,16 +1087,13 @@ static int reads_reserve(msc_ctx* ctx, uint64_t n_reads, uint64_t total) {
     ctx->geom.wn = P - m + 1;
     ctx->geom.xr = 0x55555555u & (uint32_t)low_bases_mask(ctx->win.W);
   }
-  const uint64_t slots = 1ull << ctx->lg_slots;
-  CK(ctx->tab_fp.reserve(slots * sizeof(uint64_t)));
-  CK(ctx->tab_item0.reserve(slots * sizeof(uint32_t)));
-  CK(ctx->tab_cnt.reserve(slots * sizeof(uint32_t)));
-  CK(ctx->tab_start.reserve((slots + 1) * sizeof(uint32_t)));
-  CK(ctx->tab_fill.reserve(slots * sizeof(uint32_t)));
-  CK(ctx->pass_cnt.reserve(slots * sizeof(uint32_t)));
+  CK(ctx->tab.reserve(ctx->tgeo.n_buckets * (uint64_t)kBucketBytes));
+  CK(ctx->part_count.reserve((size_t)kMaxParts * sizeof(unsigned int)));
+  CK(ctx->pass_small.reserve((1ull << ctx->lg_small) * sizeof(uint32_t)));
   CK(ctx->bloom.reserve((1ull << ctx->lg_bloom) * sizeof(uint64_t)));
-  CK(ctx->items.reserve((n_reads * nwin + 1) * sizeof(uint4)));
-  CK(ctx->dup_slot.reserve((n_reads * nwin + 1) * sizeof(uint32_t)));
+  CK(ctx->recs.reserve((n_reads * nwin + 1) * sizeof(uint4)));
+  CK(ctx->dups.reserve((n_reads * nwin + 1) * sizeof(uint4)));
+  CK(ctx->items.reserve((n_reads * nwin + 1) * sizeof(uint2)));
   CK(ctx->best.reserve((n_reads + 1) * sizeof(uint32_t)));
   // rd_words / rd_x rows are read one word past their end by extract32: keep the pad defined.
   CK(cudaMemsetAsync(ctx->rd_words.as<uint64_t>() + n_reads * S, 0, 2 * sizeof(uint64_t), ctx->stream));
@@ -1361,12 +1415,99 @@ int msc_set_targets(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, ui
   RC(end_upload(ctx));
   ctx->st.h2d_bytes += total + (n_targets + 1) * sizeof(uint32_t) + n_blk * sizeof(uint32_t);
   ctx->have_targets = true;
+  ctx->targets_packed = false;
   RC(enqueue_pack_targets(ctx));
   RC(wait_upload(ctx));  // off32 is a local; the caller's buffers are only borrowed
   if (!ctx->cfg.keep_ascii) {
     RC(sync_counters(ctx));
     ctx->tg_ascii.release();
   }
+  return MSC_OK;
+}
+
+int msc_set_targets_packed(msc_ctx* ctx, const uint64_t* words, const uint64_t* xplane, const uint64_t* offs, uint64_t n_targets) {
+  if (!ctx) return MSC_ERR_STATE;
+  if (n_targets && (!offs || (!words && offs[n_targets] != offs[0]))) return ctx->fail(MSC_ERR_INPUT, "packed targets: NULL buffer");
+  CK(cudaSetDevice(ctx->device));
+  RC(drop_deferred(ctx));
+  uint64_t total = 0;
+  std::vector<uint32_t> off32(n_targets + 1, 0);
+  if (n_targets) {
+    if (offs[0] != 0) return ctx->fail(MSC_ERR_INPUT, "targets: offs[0] must be 0");
+    total = offs[n_targets];
+    if (total >= 0xffffffffull - 4096ull)
+      return ctx->fail(MSC_ERR_INPUT, "targets: more than 2^32-4096 bases in one call; shard the database by target range");
+    for (uint64_t i = 0; i <= n_targets; i++) {
+      if (i && offs[i] < offs[i - 1]) return ctx->fail(MSC_ERR_INPUT, "targets: offsets not monotone at %llu", (unsigned long long)i);
+      off32[i] = (uint32_t)offs[i];
+    }
+  }
+  ctx->n_targets = n_targets;
+  ctx->n_bases = total;
+  const uint64_t words_n = (total + 31) / 32;
+  ctx->n_tiles = (words_n + kTileWords - 1) / kTileWords;
+  ctx->n_words_alloc = ctx->n_tiles * kTileWords + 64;
+  CK(ctx->tg_off.reserve((n_targets + 2) * sizeof(uint32_t)));
+  CK(ctx->tg_words.reserve(ctx->n_words_alloc * sizeof(uint64_t)));
+  CK(ctx->tg_x.reserve(ctx->n_words_alloc * sizeof(uint64_t)));
+  CK(ctx->xsum.reserve((ctx->n_words_alloc / 32 + 4) * sizeof(uint32_t)));
+  const uint64_t n_blk = (total >> kGeneBlockShift) + 2;
+  std::vector<uint32_t> blk(n_blk, n_targets ? (uint32_t)(n_targets - 1) : 0u);
+  {
+    uint64_t g = 0;
+    for (uint64_t b = 0; b < n_blk && n_targets; b++) {
+      const uint64_t pos = b << kGeneBlockShift;
+      while (g + 1 < n_targets && off32[g + 1] <= pos) g++;
+      blk[b] = (uint32_t)g;
+    }
+  }
+  CK(ctx->blk2gene.reserve(n_blk * sizeof(uint32_t)));
+  ctx->tg_ascii.release();  // no ASCII copy exists for packed targets (msc_rebuild(2) is a no-op on them)
+  RC(begin_upload(ctx, ctx->ev_tg_free));
+  CK(cudaMemcpyAsync(ctx->blk2gene.p, blk.data(), n_blk * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+  if (words_n) CK(cudaMemcpyAsync(ctx->tg_words.p, words, words_n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+  if (words_n && xplane) CK(cudaMemcpyAsync(ctx->tg_x.p, xplane, words_n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+  else if (words_n) CK(cudaMemsetAsync(ctx->tg_x.p, 0, words_n * sizeof(uint64_t), ctx->copy_stream));
+  CK(cudaMemcpyAsync(ctx->tg_off.p, off32.data(), (n_targets + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+  RC(end_upload(ctx));
+  ctx->st.h2d_bytes += words_n * sizeof(uint64_t) * (xplane ? 2 : 1) + (n_targets + 1) * sizeof(uint32_t) + n_blk * sizeof(uint32_t);
+  ctx->have_targets = true;
+  ctx->targets_packed = true;
+  if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_PACKT0], ctx->stream));
+  {
+    Filler f;
+    f.add(ctx->xsum.p, (ctx->n_words_alloc / 32 + 4) * sizeof(uint32_t));
+    f.add(ctx->ctr(C_TGX), 2 * sizeof(unsigned long long));
+    RC(enqueue_fill(ctx, f));
+  }
+  launch_k(ctx->pdl, packed_targets_finish_kernel, grid_for(ctx->n_words_alloc, 256), 256, 0, ctx->stream, ctx->tg_words.as<uint64_t>(),
+           ctx->tg_x.as<uint64_t>(), ctx->n_bases, ctx->n_words_alloc, ctx->xsum.as<uint32_t>(), ctx->ctr(C_TGX));
+  LAUNCH_CHECK();
+  CK(cudaEventRecord(ctx->ev_tg_free, ctx->stream));
+  if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_PACKT1], ctx->stream));
+  ctx->have_cand = ctx->have_confirm = ctx->have_combine = false;
+  ctx->pend_targets = true;
+  RC(wait_upload(ctx));  // off32 / blk are locals; the caller's buffers are only borrowed
+  return MSC_OK;
+}
+
+uint64_t msc_packed_target_words(const msc_ctx* ctx) { return (ctx && ctx->have_targets) ? (ctx->n_bases + 31) / 32 : 0; }
+
+int msc_fetch_packed_targets(msc_ctx* ctx, uint64_t* words, uint64_t* xplane, int32_t* has_x) {
+  if (!ctx) return MSC_ERR_STATE;
+  if (!ctx->have_targets) return ctx->fail(MSC_ERR_STATE, "msc_fetch_packed_targets: no targets set");
+  CK(cudaSetDevice(ctx->device));
+  RC(drop_deferred(ctx));
+  RC(sync_counters(ctx));
+  const uint64_t n = (ctx->n_bases + 31) / 32;
+  if (n && (!words || !xplane)) return ctx->fail(MSC_ERR_INPUT, "msc_fetch_packed_targets: NULL buffer");
+  if (n) {
+    CK(cudaMemcpyAsync(words, ctx->tg_words.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(xplane, ctx->tg_x.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->st.d2h_bytes += 2 * n * sizeof(uint64_t);
+  }
+  if (has_x) *has_x = ctx->h_counters[C_TGX] ? 1 : 0;
   return MSC_OK;
 }
 
@@ -1597,17 +1738,29 @@ int msc_dump_keys(msc_ctx* ctx, msc_key_rec** out, uint64_t* n) {
   CK(cudaSetDevice(ctx->device));
   RC(sync_counters(ctx));
   // group members: slot-resident first items + the CSR of further members
-  const uint64_t slots = 1ull << ctx->lg_slots;
-  std::vector<uint64_t> fps(slots);
-  std::vector<uint32_t> item0(slots), items;
-  CK(cudaMemcpy(fps.data(), ctx->tab_fp.p, slots * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(item0.data(), ctx->tab_item0.p, slots * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-  for (uint64_t sl = 0; sl < slots; sl++)
-    if (fps[sl]) items.push_back(item0[sl]);
+  std::vector<uint32_t> items;
   {
-    std::vector<uint4> dups(ctx->n_dup);  // CSR entries: (item, read record)
-    if (ctx->n_dup) CK(cudaMemcpy(dups.data(), ctx->items.p, ctx->n_dup * sizeof(uint4), cudaMemcpyDeviceToHost));
-    for (const uint4& e : dups) items.push_back(e.x);
+    const uint64_t nb = ctx->tgeo.n_buckets;
+    const uint64_t chunk = 1ull << 18;  // buckets per D2H chunk (32 MB)
+    std::vector<uint8_t> buf(chunk * kBucketBytes);
+    for (uint64_t b0 = 0; b0 < nb; b0 += chunk) {
+      const uint64_t n = std::min(chunk, nb - b0);
+      CK(cudaMemcpy(buf.data(), ctx->tab.as<uint8_t>() + b0 * kBucketBytes, n * kBucketBytes, cudaMemcpyDeviceToHost));
+      for (uint64_t b = 0; b < n; b++) {
+        const uint8_t* bp = buf.data() + b * kBucketBytes;
+        for (int sl = 0; sl < kBucketSlots; sl++) {
+          uint64_t fp;
+          memcpy(&fp, bp + 8 * sl, 8);
+          if (!fp) continue;
+          uint32_t item0;
+          memcpy(&item0, bp + kBucketRecOff + 16 * sl, 4);
+          items.push_back(item0);
+        }
+      }
+    }
+    std::vector<uint2> dupv(ctx->n_dup);  // CSR entries: (item, read record word)
+    if (ctx->n_dup) CK(cudaMemcpy(dupv.data(), ctx->items.p, ctx->n_dup * sizeof(uint2), cudaMemcpyDeviceToHost));
+    for (const uint2& e : dupv) items.push_back(e.x);
   }
   if (items.size() != ctx->n_keys)
     return ctx->fail(MSC_ERR_STATE, "key table inconsistent: %llu items for %llu keys", (unsigned long long)items.size(),

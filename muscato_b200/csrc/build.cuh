@@ -54,6 +54,19 @@ __device__ __forceinline__ int dinuc_count_wide(uint64_t k0, uint64_t k1, uint64
   return __popc(seen);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Key table build (round 2).  The table layout is described in common.cuh: buckets of five slots,
+// one 128-byte line each, holding the fingerprints AND the per-group records {item0, rmx0, start, cnt};
+// items[] = uint2 {item, rmx} of the FURTHER members of every key group (CSR).
+//
+// The build is PARTITIONED so that the random accesses of the insert stay inside the L2: the keys
+// are first distributed into partitions by the range of their home bucket (count, offsets, scatter
+// through a shared-memory stage: sequential traffic only), then inserted partition after partition
+// -- the table region one partition touches is 16 MB, so the bucket reads, the CAS claims and
+// the record writes are served by the L2 instead of one 128-byte HBM line each (the round-1 insert
+// moved 383 B of DRAM traffic per key).
+// Replaces buildBloom (cmd/muscato_screen/main.go:116-207) + sortWindows (cmd/muscato/main.go:237-304).
+// ---------------------------------------------------------------------------------------------
 struct BuildArgs {
   // reads
   const uint64_t* rd_words;
@@ -66,130 +79,103 @@ struct BuildArgs {
   uint2* rmeta;
   unsigned long long* n_keys;
   // key table
-  uint64_t* tab_fp;
-  uint32_t* tab_item0;   // first (read, window) item of the slot's key group
-  uint32_t* tab_cnt;     // number of FURTHER items of the group (they go to the CSR `items`)
-  int lg_slots;
-  uint32_t* dup_slot;    // per item: 1 + slot if the item is a further member of its group, else 0
+  uint8_t* tab;
+  TableGeom tg;
+  // partitioning
+  unsigned int* part_count;     // [n_parts]: keys per partition (pass A), then the write cursors (pass B)
+  uint4* recs;                  // partition-ordered key records {fp.lo, fp.hi, item, rmx}
+  // further members
+  uint4* dups;                  // {slot, item, rmx, ordinal}
+  unsigned long long* n_dup;
+  unsigned long long* n_alloc;  // bump allocator of the CSR
+  uint2* items;
   // Bloom front
   unsigned long long* bloom;
   BloomGeom geom;
 };
-// (The number of further members, n_dup, is the grand total of the bump allocation in pass B1 and
-// the number of distinct fingerprints is n_keys - n_dup: no per-warp counter atomics in the insert
-// kernel -- ~10^6 same-address atomics cost more than the inserts themselves.)
 
-#ifndef MSC_INSERT_BATCH
-#define MSC_INSERT_BATCH 1
-#endif
-#ifndef MSC_INSERT_CTAS
-#define MSC_INSERT_CTAS 8
-#endif
-constexpr int kInsertBatch = MSC_INSERT_BATCH;  // home buckets in flight per thread
+constexpr int kMaxParts = 1024;
 
-// Pass A: one thread per read.  Which windows are valid (length rule + entropy rule), the
-// fingerprint of each valid window key, its Bloom bits, and the claim of its table slot: the
-// first item of a key group lives in the slot itself (most groups have exactly one member);
-// further members are flagged in dup_slot and scattered into the slot's CSR range by pass B.
-// The home buckets (32 bytes, one 256-bit load each) of up to kInsertBatch windows are fetched
-// before any claim is made; a claim is then one atomicCAS on the first slot seen free.
-// item = read * nwin + window.
-__global__ void __launch_bounds__(256, MSC_INSERT_CTAS) build_keys_insert_kernel(const WinCfg cfg, const BuildArgs a) {
+__device__ __forceinline__ uint32_t key_partition(uint64_t fp, const TableGeom& tg) {
+  return (uint32_t)(table_home_bucket(fp, tg.n_buckets) >> tg.lg_bpp);
+}
+
+// Fingerprint of window k of read r, as every pass derives it; optionally the key words and X masks.
+__device__ __forceinline__ uint64_t window_fp(const WinCfg& cfg, const uint64_t* __restrict__ row,
+                                              const uint64_t* __restrict__ xrow, bool hasx, int k, uint64_t* key_out,
+                                              uint64_t* key1_out, uint64_t* xm0_out, uint64_t* xm1_out) {
+  const int q1 = cfg.windows[k];
+  const bool wide = cfg.W > 32;
+  const uint64_t kmask = low_bases_mask(min(cfg.W, 32));
+  const uint64_t key = extract32(row, (uint64_t)q1) & kmask;
+  const uint64_t xm0 = hasx ? (extract32(xrow, (uint64_t)q1) & kmask) : 0ull;
+  uint64_t key1 = 0, xm1 = 0;
+  if (wide) {  // bases 32..W-1 of the window
+    const uint64_t kmask1 = low_bases_mask(cfg.W - 32);
+    key1 = extract32(row, (uint64_t)q1 + 32) & kmask1;
+    xm1 = hasx ? (extract32(xrow, (uint64_t)q1 + 32) & kmask1) : 0ull;
+  }
+  if (key_out) *key_out = key;
+  if (key1_out) *key1_out = key1;
+  if (xm0_out) *xm0_out = xm0;
+  if (xm1_out) *xm1_out = xm1;
+  return wide ? key_fp_wide(key, key1, xm0, xm1) : key_fp(key, xm0);
+}
+
+// Clears the fingerprints of every bucket: the first 64 of its 128 bytes (two whole sectors; the
+// records behind them are only ever read after their fingerprint was claimed).  Four threads per bucket.
+__global__ void __launch_bounds__(256) table_clear_kernel(uint8_t* __restrict__ tab, uint64_t n_buckets) {
   pdl_enter();
-  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t n = n_buckets * 4;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    *reinterpret_cast<uint4*>(tab + (i >> 2) * (uint64_t)kBucketBytes + (i & 3ull) * 16ull) = z;
+}
+
+// Pass A: one thread per read (grid-stride).  Which windows are valid (length rule + entropy rule,
+// cmd/muscato_window_reads/main.go:109-118, cmd/muscato_screen/main.go:174-185), the read record,
+// the Bloom bits of every valid key, and the number of keys per partition (shared-memory histogram,
+// one global atomic per block and non-empty partition).  item = read * nwin + window.
+__global__ void __launch_bounds__(256) build_windows_kernel(const WinCfg cfg, const BuildArgs a) {
+  pdl_enter();
+  __shared__ unsigned int s_hist[kMaxParts];
+  const int P = (int)a.tg.n_parts;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) s_hist[p] = 0u;
+  __syncthreads();
   uint32_t nk = 0;
-  if (r < a.n_reads) {
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t lf = a.len_flags[r];
     const int L = (int)(lf & 0x7fffffffu);
     const bool hasx = lf >> 31;
     const uint64_t* row = a.rd_words + r * (uint64_t)cfg.S;
     const uint64_t* xrow = a.rd_x + r * (uint64_t)cfg.S;
-    const bool wide = cfg.W > 32;
-    const uint64_t kmask = low_bases_mask(min(cfg.W, 32));
-    const uint64_t kmask1 = wide ? low_bases_mask(cfg.W - 32) : 0ull;
-    const uint64_t bmask = (1ull << (a.lg_slots - 2)) - 1ull;
     uint32_t vm = 0;
-    for (int k0 = 0; k0 < cfg.nwin; k0 += kInsertBatch) {
-      uint64_t fp[kInsertBatch], bk[kInsertBatch];
-      uint64_t q[kInsertBatch][4];
-#pragma unroll
-      for (int u = 0; u < kInsertBatch; u++) {
-        const int k = k0 + u;
-        fp[u] = 0;
-        bk[u] = 0;
-        q[u][0] = q[u][1] = q[u][2] = q[u][3] = 0;
-        if (k < cfg.nwin) {
-          const int q1 = cfg.windows[k], q2 = q1 + cfg.W;
-          if (L >= q2) {  // cmd/muscato_window_reads/main.go:109-112, cmd/muscato_screen/main.go:177-179
-            const uint64_t key = extract32(row, (uint64_t)q1) & kmask;
-            const uint64_t xm0 = hasx ? (extract32(xrow, (uint64_t)q1) & kmask) : 0ull;
-            uint64_t key1 = 0, xm1 = 0;
-            if (wide) {  // bases 32..W-1 of the window
-              key1 = extract32(row, (uint64_t)q1 + 32) & kmask1;
-              xm1 = hasx ? (extract32(xrow, (uint64_t)q1 + 32) & kmask1) : 0ull;
-            }
-            const uint64_t xm = xm0 | xm1;
-            const int nd = cfg.min_dinuc <= 0 ? 0
-                           : wide ? dinuc_count_wide(key, key1, xm0, xm1, cfg.W) : dinuc_count(key, xm0, cfg.W);
-            if (cfg.min_dinuc <= 0 || nd >= cfg.min_dinuc) {  // :183-185 / :116-118
-              fp[u] = wide ? key_fp_wide(key, key1, xm0, xm1) : key_fp(key, xm0);
-              vm |= 1u << k;
-              nk++;
-              uint64_t widx;
-              uint32_t mlo, mhi;
-              bloom_locate(key, xm, fp[u], cfg.W, a.geom, widx, mlo, mhi, key1);
-              atomicOr(a.bloom + widx, (unsigned long long)mlo | ((unsigned long long)mhi << 32));
-              bk[u] = table_home_bucket(fp[u], a.lg_slots);
-              ldcg256(a.tab_fp + (bk[u] << 2), q[u][0], q[u][1], q[u][2], q[u][3]);  // the home bucket as it stands
-            }
-          }
-        }
+    for (int k = 0; k < cfg.nwin; k++) {
+      if (L < cfg.windows[k] + cfg.W) continue;  // cmd/muscato_window_reads/main.go:109-112, cmd/muscato_screen/main.go:177-179
+      uint64_t key, key1, xm0, xm1;
+      const uint64_t fp = window_fp(cfg, row, xrow, hasx, k, &key, &key1, &xm0, &xm1);
+      if (cfg.min_dinuc > 0) {  // :183-185 / :116-118
+        const int nd = cfg.W > 32 ? dinuc_count_wide(key, key1, xm0, xm1, cfg.W) : dinuc_count(key, xm0, cfg.W);
+        if (nd < cfg.min_dinuc) continue;
       }
-#pragma unroll
-      for (int u = 0; u < kInsertBatch; u++) {
-        const int k = k0 + u;
-        if (k >= cfg.nwin) break;
-        const uint64_t item = r * (uint64_t)cfg.nwin + (uint64_t)k;
-        uint32_t dup = 0;
-        if (fp[u]) {
-          // first slot of the probe sequence that holds fp (further member) or that this thread
-          // claims with a CAS (first member); a slot seen free may have been taken meanwhile --
-          // the CAS returns what is there now
-          int64_t slot = -1;
-          bool first = false;
-          while (slot < 0) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              if (slot >= 0) break;
-              uint64_t v = q[u][i];
-              if (v == 0ull)
-                v = atomicCAS(reinterpret_cast<unsigned long long*>(a.tab_fp + (bk[u] << 2) + i), 0ull, (unsigned long long)fp[u]);
-              if (v == 0ull) {
-                slot = (int64_t)((bk[u] << 2) + i);
-                first = true;
-              } else if (v == fp[u]) {
-                slot = (int64_t)((bk[u] << 2) + i);
-              }
-            }
-            if (slot < 0) {  // bucket full of other keys: next bucket
-              bk[u] = (bk[u] + 1) & bmask;
-              ldcg256(a.tab_fp + (bk[u] << 2), q[u][0], q[u][1], q[u][2], q[u][3]);
-            }
-          }
-          if (first) {
-            a.tab_item0[slot] = (uint32_t)item;
-          } else {
-            atomicAdd(a.tab_cnt + slot, 1u);
-            dup = (uint32_t)slot + 1u;
-          }
-        }
-        a.dup_slot[item] = dup;
-      }
+      const uint64_t xm = xm0 | xm1;
+      vm |= 1u << k;
+      nk++;
+      uint64_t widx;
+      uint32_t mlo, mhi;
+      bloom_locate(key, xm, fp, cfg.W, a.geom, widx, mlo, mhi, key1);
+      atomicOr(a.bloom + widx, (unsigned long long)mlo | ((unsigned long long)mhi << 32));
+      atomicAdd(&s_hist[key_partition(fp, a.tg)], 1u);
     }
     a.validmask[r] = vm;
-    // what the confirm kernel needs of a read in one 8-byte load: length (11 bits), mismatch
-    // budget nmiss(L) (11 bits), has-X flag, valid-window mask
+    // what the confirm kernel needs of a read: length (11 bits), mismatch budget nmiss(L) (11 bits),
+    // has-X flag; .y = valid-window mask
     a.rmeta[r] = make_uint2((uint32_t)L | ((uint32_t)__ldg(a.nmiss + L) << 11) | (lf & 0x80000000u), vm);
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    const unsigned int c = s_hist[p];
+    if (c) atomicAdd(a.part_count + p, c);
   }
   // one counter atomic per block (same-address atomics serialise)
   __shared__ uint32_t s_nk[8];
@@ -203,48 +189,169 @@ __global__ void __launch_bounds__(256, MSC_INSERT_CTAS) build_keys_insert_kernel
   }
 }
 
-// Pass B1: CSR ranges for the further members.  Only slots that own further members need one, so
-// instead of scanning the counts of ALL slots the first further member of a slot to arrive
-// reserves the slot's range from a bump counter (tab_cnt is final by now).  tab_fill[s] ends up
-// equal to tab_cnt[s] and is consumed by pass B2.
-__global__ void __launch_bounds__(256) build_alloc_kernel(const uint32_t* __restrict__ dup_slot, uint64_t n_items,
-                                                          const uint32_t* __restrict__ tab_cnt,
-                                                          uint32_t* __restrict__ tab_fill,
-                                                          uint32_t* __restrict__ tab_start,
-                                                          unsigned long long* __restrict__ n_dup) {
+// Partition sizes -> start offsets (in place: part_count becomes the write cursor of every partition).
+// One block; P <= kMaxParts.
+__global__ void __launch_bounds__(kMaxParts) build_offsets_kernel(unsigned int* __restrict__ part_count, int P) {
   pdl_enter();
-  // the reservations of a block are summed in shared memory: ONE bump of the global counter per
-  // block (same-address global atomics serialise)
-  __shared__ uint32_t s_total;
-  __shared__ unsigned long long s_base;
-  if (threadIdx.x == 0) s_total = 0u;
+  __shared__ unsigned int s[kMaxParts];
+  const int t = threadIdx.x;
+  const unsigned int v = t < P ? part_count[t] : 0u;
+  s[t] = v;
   __syncthreads();
-  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t d = idx < n_items ? __ldg(dup_slot + idx) : 0u;
-  const bool first = d && atomicAdd(tab_fill + (d - 1), 1u) == 0u;
-  uint32_t local = 0;
-  if (first) local = atomicAdd(&s_total, __ldg(tab_cnt + (d - 1)));
-  __syncthreads();
-  if (threadIdx.x == 0 && s_total) s_base = atomicAdd(n_dup, (unsigned long long)s_total);
-  __syncthreads();
-  if (first) tab_start[d - 1] = (uint32_t)(s_base + local);
+  for (int o = 1; o < kMaxParts; o <<= 1) {
+    const unsigned int add = t >= o ? s[t - o] : 0u;
+    __syncthreads();
+    s[t] += add;
+    __syncthreads();
+  }
+  if (t < P) part_count[t] = s[t] - v;
 }
 
-// Pass B2: scatter the further members into their slot's CSR range.  A CSR entry is 16 bytes:
-// (item, read record) -- the confirm kernel gets the read's length / budget / window mask with
-// the item itself instead of through one more dependent look-up.
-__global__ void __launch_bounds__(256) build_fill_kernel(const uint32_t* __restrict__ dup_slot, uint64_t n_items,
-                                                         const uint32_t* __restrict__ tab_start,
-                                                         uint32_t* __restrict__ tab_fill,
-                                                         const uint2* __restrict__ rmeta, uint32_t nwin,
-                                                         uint4* __restrict__ items) {
+// Pass B: distribute the key records into partition order.  One thread per (read, window) item; a
+// block stages kStageKeys items in shared memory, reserves one run per non-empty partition with a
+// single global atomic each and writes the runs (16-byte records; the two halves of a 32-byte
+// sector arrive from the same block within one flush, so DRAM sees whole sectors).
+constexpr int kStageRounds = 8;
+constexpr int kStageKeys = kStageRounds * 256;
+
+__global__ void __launch_bounds__(256) build_scatter_kernel(const WinCfg cfg, const BuildArgs a) {
   pdl_enter();
-  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_items) return;
-  const uint32_t d = __ldg(dup_slot + idx);
-  if (d) {
-    const uint2 rm = __ldg(rmeta + (uint32_t)idx / nwin);
-    items[tab_start[d - 1] + (atomicSub(tab_fill + (d - 1), 1u) - 1u)] = make_uint4((uint32_t)idx, rm.x, rm.y, 0u);
+  __shared__ uint4 s_rec[kStageKeys];
+  __shared__ uint16_t s_part[kStageKeys];
+  __shared__ unsigned int s_cnt[kMaxParts];
+  __shared__ unsigned int s_base[kMaxParts];
+  const int P = (int)a.tg.n_parts;
+  const uint64_t n_items = a.n_reads * (uint64_t)cfg.nwin;
+  const uint64_t n_tiles = (n_items + kStageKeys - 1) / kStageKeys;
+  for (int p = threadIdx.x; p < P; p += 256) s_cnt[p] = 0u;
+  __syncthreads();
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll 1
+    for (int j = 0; j < kStageRounds; j++) {
+      const int idx = j * 256 + (int)threadIdx.x;
+      const uint64_t item = tile * (uint64_t)kStageKeys + (uint64_t)idx;
+      uint32_t part = 0xFFFFu;
+      if (item < n_items) {
+        const uint64_t r = cfg.nwin == 1 ? item : (uint64_t)((uint32_t)item / (uint32_t)cfg.nwin);  // items are 32-bit
+        const int k = (int)(item - r * (uint64_t)cfg.nwin);
+        if ((__ldg(a.validmask + r) >> k) & 1u) {
+          const uint32_t rmx = __ldg(&a.rmeta[r].x);
+          const uint64_t fp = window_fp(cfg, a.rd_words + r * (uint64_t)cfg.S, a.rd_x + r * (uint64_t)cfg.S, rmx >> 31, k,
+                                        nullptr, nullptr, nullptr, nullptr);
+          part = key_partition(fp, a.tg);
+          s_rec[idx] = make_uint4((uint32_t)fp, (uint32_t)(fp >> 32), (uint32_t)item, rmx);
+          atomicAdd(&s_cnt[part], 1u);
+        }
+      }
+      s_part[idx] = (uint16_t)part;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < P; p += 256) {
+      const unsigned int c = s_cnt[p];
+      if (c) s_base[p] = atomicAdd(a.part_count + p, c);
+      s_cnt[p] = 0u;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < kStageRounds; j++) {
+      const int idx = j * 256 + (int)threadIdx.x;
+      const uint32_t part = s_part[idx];
+      if (part != 0xFFFFu) a.recs[s_base[part] + atomicAdd(&s_cnt[part], 1u)] = s_rec[idx];
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < P; p += 256) s_cnt[p] = 0u;
+    __syncthreads();
+  }
+}
+
+// Pass C: insert the records in partition order (one thread per record).  The first member of a key
+// group claims a slot with one CAS on the first slot it saw free in the bucket (the CAS returns what
+// is there now if another thread was faster) and writes the slot's record; further members are
+// appended to the dups list (their CSR position is settled by passes D-F, after every claim is done).
+__global__ void __launch_bounds__(256) build_insert_kernel(const BuildArgs a) {
+  pdl_enter();
+  const uint64_t n = *a.n_keys;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 rc = a.recs[i];
+    const uint64_t fp = (uint64_t)rc.x | ((uint64_t)rc.y << 32);
+    uint64_t bk = table_home_bucket(fp, a.tg.n_buckets);
+    int64_t slot = -1;
+    bool first = false;
+    while (slot < 0) {
+      uint8_t* bp = bucket_ptr(a.tab, bk);
+      uint64_t q[kBucketSlots];
+      ldcg256(bp, q[0], q[1], q[2], q[3]);  // the bucket as it stands (L2: other SMs are claiming slots)
+      q[4] = ldcg64(bp + 32);
+#pragma unroll
+      for (int s = 0; s < kBucketSlots; s++) {
+        if (slot >= 0) break;
+        uint64_t v = q[s];
+        if (v == 0ull) v = atomicCAS(reinterpret_cast<unsigned long long*>(bp) + s, 0ull, (unsigned long long)fp);
+        if (v == 0ull) {
+          slot = (int64_t)(bk * kBucketSlots + s);
+          first = true;
+        } else if (v == fp) {
+          slot = (int64_t)(bk * kBucketSlots + s);
+        }
+      }
+      if (slot < 0) bk = bk + 1 == a.tg.n_buckets ? 0 : bk + 1;  // bucket full of other keys: next bucket
+    }
+    if (first) {
+      *slot_rec_ptr(a.tab, (uint64_t)slot) = make_uint4(rc.z, rc.w, 0u, 0u);
+    } else {
+      const unsigned long long at = warp_agg_inc(a.n_dup);
+      a.dups[at] = make_uint4((uint32_t)slot, rc.z, rc.w, 0u);
+    }
+  }
+}
+
+// Pass D: every further member takes its ordinal inside its group (the cnt word of the slot record counts them).
+__global__ void __launch_bounds__(256) build_dup_count_kernel(const BuildArgs a) {
+  pdl_enter();
+  const uint64_t n = *a.n_dup;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t slot = a.dups[i].x;
+    a.dups[i].w = atomicAdd(&slot_rec_ptr(a.tab, slot)->w, 1u);
+  }
+}
+
+// Pass E: the member with ordinal 0 reserves the group's CSR range (counts are final by now); the
+// reservations of a block are summed in shared memory: ONE bump of the global counter per block.
+__global__ void __launch_bounds__(256) build_dup_alloc_kernel(const BuildArgs a) {
+  pdl_enter();
+  __shared__ uint32_t s_total;
+  __shared__ unsigned long long s_base;
+  const uint64_t n = *a.n_dup;
+  const uint64_t n_rounds = (n + (uint64_t)gridDim.x * blockDim.x - 1) / ((uint64_t)gridDim.x * blockDim.x);
+  for (uint64_t rd = 0; rd < n_rounds; rd++) {
+    const uint64_t i = (rd * gridDim.x + blockIdx.x) * (uint64_t)blockDim.x + threadIdx.x;
+    if (threadIdx.x == 0) s_total = 0u;
+    __syncthreads();
+    uint32_t slot = 0, local = 0;
+    bool head = false;
+    if (i < n) {
+      const uint4 d = a.dups[i];
+      if (d.w == 0u) {
+        head = true;
+        slot = d.x;
+        local = atomicAdd(&s_total, slot_rec_ptr(a.tab, slot)->w);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_total) s_base = atomicAdd(a.n_alloc, (unsigned long long)s_total);
+    __syncthreads();
+    if (head) slot_rec_ptr(a.tab, slot)->z = (uint32_t)(s_base + local);
+    __syncthreads();
+  }
+}
+
+// Pass F: scatter the further members into their group's CSR range.
+__global__ void __launch_bounds__(256) build_dup_fill_kernel(const BuildArgs a) {
+  pdl_enter();
+  const uint64_t n = *a.n_dup;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 d = a.dups[i];
+    a.items[slot_rec_ptr(a.tab, d.x)->z + d.w] = make_uint2(d.y, d.z);
   }
 }
 

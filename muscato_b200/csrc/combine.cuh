@@ -200,22 +200,26 @@ __global__ void __launch_bounds__(256) best_from_matches_kernel(const uint4* __r
   if (i < n) atomicMin(best + m[i].x, m[i].w);
 }
 
-// Number of key groups whose passing-pair count exceeds MaxMatches (the only groups for
-// which qinsert / "first" truncation, cmd/muscato_confirm/main.go:233-242 and :424-448, can
-// drop anything).
-__global__ void __launch_bounds__(256) overflow_count_kernel(const uint32_t* __restrict__ pass_cnt, uint64_t n_slots,
+// Number of counters above MaxMatches.  `cnt` is either the small hashed counter array of the confirm
+// kernel (every counter is an upper bound for the key groups that map to it: none above the limit
+// means no group can lose anything to qinsert / "first" truncation,
+// cmd/muscato_confirm/main.go:233-242 and :424-448) or, in the re-run that follows, the exact
+// per-slot counts.
+__global__ void __launch_bounds__(256) overflow_count_kernel(const uint32_t* __restrict__ cnt, uint64_t n,
                                                              unsigned long long max_matches,
                                                              const unsigned long long* __restrict__ n_pass,
                                                              unsigned long long* __restrict__ n_over,
                                                              uint32_t* __restrict__ shard_flag) {
   pdl_enter();
-  if (*n_pass <= max_matches) return;  // no group can exceed MaxMatches (the usual case: nothing to read)
-  uint32_t over = 0;  // n_slots is a power of two >= 1024: 16-byte loads
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots / 4; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(pass_cnt) + i);
+  if (*n_pass <= max_matches) return;  // no group can exceed MaxMatches (nothing to read)
+  uint32_t over = 0;
+  const uint64_t n4 = n / 4;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(cnt) + i);
     over += ((unsigned long long)v.x > max_matches) + ((unsigned long long)v.y > max_matches) +
             ((unsigned long long)v.z > max_matches) + ((unsigned long long)v.w > max_matches);
   }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3u)) over += (unsigned long long)cnt[n4 * 4 + threadIdx.x] > max_matches;
   over = __reduce_add_sync(0xffffffffu, over);
   if ((threadIdx.x & 31u) == 0 && over) {
     atomicAdd(n_over, (unsigned long long)over);
@@ -223,6 +227,32 @@ __global__ void __launch_bounds__(256) overflow_count_kernel(const uint32_t* __r
     // array and reaches every rank with the MIN all-reduce of that array
     if (shard_flag) *shard_flag = 0u;
   }
+}
+
+// Fingerprints of the key groups whose exact passing-pair count exceeds `thr` (sharded MaxMatches
+// protocol: a fingerprint names a k-mer independently of the rank's table layout).
+__global__ void __launch_bounds__(256) overflow_keys_kernel(const uint32_t* __restrict__ pass_cnt, const uint8_t* __restrict__ tab,
+                                                            uint64_t n_slots, unsigned long long thr, uint64_t* __restrict__ out,
+                                                            unsigned long long cap, unsigned long long* __restrict__ n_out) {
+  pdl_enter();
+  for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += (uint64_t)gridDim.x * blockDim.x) {
+    if ((unsigned long long)pass_cnt[s] <= thr) continue;
+    const uint64_t b = s / kBucketSlots;
+    const uint64_t fp = reinterpret_cast<const uint64_t*>(tab + b * (uint64_t)kBucketBytes)[s - b * kBucketSlots];
+    if (!fp) continue;
+    const unsigned long long at = atomicAdd(n_out, 1ull);
+    if (at < cap) out[at] = fp;
+  }
+}
+
+// slot_over[slot] = 1 for every listed fingerprint that is a key of this table.
+__global__ void __launch_bounds__(256) flag_keys_kernel(const uint64_t* __restrict__ fps, uint64_t n, const uint8_t* __restrict__ tab,
+                                                        uint64_t n_buckets, uint8_t* __restrict__ slot_over) {
+  pdl_enter();
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t s = table_find(tab, n_buckets, fps[i]);
+  if (s >= 0) slot_over[s] = 1;
 }
 
 // After the all-reduce: copy the flag into the counter block the host reads anyway.

@@ -163,14 +163,37 @@ __host__ __device__ __forceinline__ void bloom_locate(uint64_t key, uint64_t xm,
   }
 }
 // ---------------------------------------------------------------------------
-// Key table: open addressing over BUCKETS of four 64-bit fingerprints (32 bytes = one sector, read
-// with one 256-bit load).  A key lives in the first free slot of the first bucket of its probe
-// sequence that is not full (home bucket from one multiplicative hash, then linear); there are no
-// deletions, so a bucket with a free slot ends every look-up.  At the table's load factor (<= 0.5,
-// two keys per bucket on average) ~95 % of the look-ups and inserts touch exactly one sector.
+// Key table: open addressing over BUCKETS that are exactly one 128-byte L2 line.
+//
+// Measured on B200 (profiles/README.md, round 2): a 32-byte sector miss brings the whole 128-byte line
+// from HBM (dram__bytes per random 4..32-byte access = 118..128 B, cudaLimitMaxL2FetchGranularity
+// ignored), so every random access costs one line whatever it reads.  A bucket therefore holds
+// everything a look-up needs in ONE line:
+//     bytes   0.. 39  fp[5]    64-bit fingerprints, 0 = empty
+//     bytes  48..127  rec[5]   uint4 {item0, rmx0, start, cnt}: first (read, window) item of the key
+//                              group, that read's record word (length | nmiss << 11 | hasX << 31) and
+//                              the CSR range [start, start + cnt) of the group's FURTHER members
+// A key lives in the first free slot of the first bucket of its probe sequence that is not full (home
+// bucket from one multiplicative hash, then linear); there are no deletions, so a bucket with a free
+// slot ends every look-up.  slot id = 5 * bucket + position.  The bucket count is partitions x 2^k
+// (not a power of two): the home bucket is umulhi(hash, n_buckets), its partition home >> k.
 // ---------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint64_t table_home_bucket(uint64_t fp, int lg_slots) {
-  return (fp * 0x9E3779B97F4A7C15ull) >> (66 - lg_slots);  // lg_buckets = lg_slots - 2
+constexpr int kBucketSlots = 5;
+constexpr int kBucketBytes = 128;
+constexpr int kBucketRecOff = 48;
+
+struct TableGeom {
+  uint64_t n_buckets;   // partitions << lg_bpp
+  int lg_bpp;           // log2(buckets per partition)
+  uint32_t n_parts;
+};
+
+__host__ __device__ __forceinline__ uint64_t table_home_bucket(uint64_t fp, uint64_t n_buckets) {
+#ifdef __CUDA_ARCH__
+  return __umul64hi(fp * 0x9E3779B97F4A7C15ull, n_buckets);
+#else
+  return (uint64_t)(((unsigned __int128)(fp * 0x9E3779B97F4A7C15ull) * n_buckets) >> 64);
+#endif
 }
 
 // One 256-bit read-only global load (sm_100: LDG.E.256) of a 32-byte aligned record.
@@ -181,28 +204,54 @@ __device__ __forceinline__ void ldg256(const void* p, uint64_t& a, uint64_t& b, 
 __device__ __forceinline__ void ldcg256(const void* p, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d) {
   asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
 }
-
-// Position of fp in a bucket's four fingerprints: 0..3 = found, 4 = not here but the bucket has a
-// free slot (the key is not in the table), 5 = bucket full, go on.
-__device__ __forceinline__ int bucket_probe(uint64_t fp, uint64_t q0, uint64_t q1, uint64_t q2, uint64_t q3) {
-  if (q0 == fp) return 0;
-  if (q1 == fp) return 1;
-  if (q2 == fp) return 2;
-  if (q3 == fp) return 3;
-  return (q0 == 0ull) | (q1 == 0ull) | (q2 == 0ull) | (q3 == 0ull) ? 4 : 5;
+__device__ __forceinline__ uint64_t ldcg64(const void* p) {
+  uint64_t v;
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
 
-// Look-up.  Returns slot (= 4 * bucket + position) or -1.
-__device__ __forceinline__ int64_t table_find(const uint64_t* __restrict__ tab_fp, int lg_slots, uint64_t fp) {
-  const uint64_t bmask = (1ull << (lg_slots - 2)) - 1ull;
-  uint64_t b = table_home_bucket(fp, lg_slots);
+__device__ __forceinline__ const uint8_t* bucket_ptr(const uint8_t* tab, uint64_t b) { return tab + b * (uint64_t)kBucketBytes; }
+__device__ __forceinline__ uint8_t* bucket_ptr(uint8_t* tab, uint64_t b) { return tab + b * (uint64_t)kBucketBytes; }
+__device__ __forceinline__ const uint4* slot_rec_ptr(const uint8_t* tab, uint64_t slot) {
+  const uint64_t b = slot / kBucketSlots;
+  return reinterpret_cast<const uint4*>(tab + b * (uint64_t)kBucketBytes + kBucketRecOff) + (slot - b * kBucketSlots);
+}
+__device__ __forceinline__ uint4* slot_rec_ptr(uint8_t* tab, uint64_t slot) {
+  const uint64_t b = slot / kBucketSlots;
+  return reinterpret_cast<uint4*>(tab + b * (uint64_t)kBucketBytes + kBucketRecOff) + (slot - b * kBucketSlots);
+}
+
+// The five fingerprints of a bucket (read-only path: the table is final).
+__device__ __forceinline__ void bucket_load_fps(const uint8_t* bp, uint64_t q[kBucketSlots]) {
+  ldg256(bp, q[0], q[1], q[2], q[3]);
+  q[4] = __ldg(reinterpret_cast<const unsigned long long*>(bp + 32));
+}
+
+// Position of fp among a bucket's fingerprints: 0..4 = found, 5 = not here but the bucket has a free
+// slot (the key is not in the table), 6 = bucket full, go on.
+__device__ __forceinline__ int bucket_probe(uint64_t fp, const uint64_t q[kBucketSlots]) {
+  int r = 6;
+#pragma unroll
+  for (int s = kBucketSlots - 1; s >= 0; s--) {
+    if (q[s] == 0ull) r = 5;
+  }
+#pragma unroll
+  for (int s = kBucketSlots - 1; s >= 0; s--) {
+    if (q[s] == fp) r = s;
+  }
+  return r;
+}
+
+// Look-up.  Returns slot (= 5 * bucket + position) or -1.
+__device__ __forceinline__ int64_t table_find(const uint8_t* __restrict__ tab, uint64_t n_buckets, uint64_t fp) {
+  uint64_t b = table_home_bucket(fp, n_buckets);
   while (true) {
-    uint64_t q0, q1, q2, q3;
-    ldg256(tab_fp + (b << 2), q0, q1, q2, q3);
-    const int r = bucket_probe(fp, q0, q1, q2, q3);
-    if (r < 4) return (int64_t)((b << 2) + (uint64_t)r);
-    if (r == 4) return -1;
-    b = (b + 1) & bmask;
+    uint64_t q[kBucketSlots];
+    bucket_load_fps(bucket_ptr(tab, b), q);
+    const int r = bucket_probe(fp, q);
+    if (r < kBucketSlots) return (int64_t)(b * kBucketSlots + (uint64_t)r);
+    if (r == kBucketSlots) return -1;
+    b = b + 1 == n_buckets ? 0 : b + 1;
   }
 }
 

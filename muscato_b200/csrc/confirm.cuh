@@ -26,36 +26,31 @@ constexpr int kGeneBlockShift = 10;  // granularity of the position -> target in
 
 // Per candidate: locate its gene once (block index + short binary search in the target offsets) and store what every
 // pair of the candidate needs in ONE 32-byte sector (two uint4): (global position of the window,
-// window start p inside the gene, global end of the gene, read record .x of the first item) and
-// (first item of the key group, CSR start of the further items, gene index, read record .y of
-// the first item).  The table slot stays in cand[] (only pairs that pass need it).  sizes[] = number of (read, window)
-// items of its key group.  A W-mer that straddles a target boundary is not a window of any target
+// window start p inside the gene, global end of the gene, read record word of the first item) and
+// (first item of the key group, CSR start of the further items, gene index, 0).  The key group's
+// record {item0, rmx0, start, cnt} came with the candidate from the scan kernel (cmeta), so this
+// kernel is a pure stream: no table memory, no per-read look-up.  sizes[] = number of (read, window)
+// items of the key group.  A W-mer that straddles a target boundary is not a window of any target
 // (processSeq only rolls inside one target, cmd/muscato_screen/main.go:319): size 0.
-__global__ void __launch_bounds__(256) cand_prepare_kernel(const uint2* __restrict__ cand,
+__global__ void __launch_bounds__(256) cand_prepare_kernel(const uint2* __restrict__ cand, const uint4* __restrict__ cmeta,
                                                            const unsigned long long* __restrict__ n_cand_ptr,
-                                                           uint64_t cand_cap, const uint32_t* __restrict__ tab_cnt,
-                                                           const uint32_t* __restrict__ tab_item0,
-                                                           const uint32_t* __restrict__ tab_start,
-                                                           const uint32_t* __restrict__ tg_off,
+                                                           uint64_t cand_cap, const uint32_t* __restrict__ tg_off,
                                                            const uint32_t* __restrict__ blk2gene, int W,
-                                                           const uint2* __restrict__ rmeta, uint64_t nwin_magic,
                                                            uint4* __restrict__ cinfo, uint32_t* __restrict__ sizes) {
   pdl_enter();
   const uint64_t n_cand = min((uint64_t)*n_cand_ptr, cand_cap);
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint2 cd = cand[i];
+    const uint4 rec = cmeta[i];
     // blk2gene[b] = target that holds base b << kGeneBlockShift: the search spans the few targets
     // that start inside the candidate's block instead of the whole offset table
     const uint64_t g_lo = __ldg(blk2gene + (cd.y >> kGeneBlockShift)), g_hi = __ldg(blk2gene + (cd.y >> kGeneBlockShift) + 1);
     const uint64_t g = upper_bound_dev<uint32_t>(tg_off, g_lo + 1, g_hi + 1, cd.y) - 1;
     const uint32_t goff = __ldg(tg_off + g);
     const uint32_t gend = __ldg(tg_off + g + 1);
-    const uint32_t further = __ldg(tab_cnt + cd.x);
-    const uint32_t item0 = __ldg(tab_item0 + cd.x);
-    const uint2 rm0 = __ldg(rmeta + (nwin_magic ? (uint32_t)__umul64hi((uint64_t)item0, nwin_magic) : item0));
-    cinfo[2 * i] = make_uint4(cd.y, cd.y - goff, gend, rm0.x);
-    cinfo[2 * i + 1] = make_uint4(item0, further ? __ldg(tab_start + cd.x) : 0u, (uint32_t)g, rm0.y);
-    sizes[i] = ((uint64_t)cd.y + (uint64_t)W <= (uint64_t)gend) ? 1u + further : 0u;
+    cinfo[2 * i] = make_uint4(cd.y, cd.y - goff, gend, rec.y);
+    cinfo[2 * i + 1] = make_uint4(rec.x, rec.z, (uint32_t)g, 0u);
+    sizes[i] = ((uint64_t)cd.y + (uint64_t)W <= (uint64_t)gend) ? 1u + rec.w : 0u;
   }
 }
 
@@ -94,8 +89,15 @@ struct ConfirmArgs {
   const unsigned long long* n_pairs_ptr;  // device-side pair count (grand total of the size scan)
   uint64_t block_cap;                     // capacity of block_first (in kPairBlock-pair blocks)
   // key table
-  const uint4* items;          // CSR of further group members: (item, read record)
-  uint32_t* pass_cnt;  // per slot: pairs that passed (MaxMatches pre-check)
+  const uint2* items;          // CSR of further group members: (item, read record word)
+  const uint32_t* validmask;   // per read: valid-window mask (only read for pairs that pass through a window k > 0)
+  // MaxMatches pre-check: passing pairs are counted per key group in a SMALL hashed counter array that
+  // stays in the L2 (a counter is an upper bound for every group that maps to it: if none exceeds
+  // MaxMatches no group does); the exact per-slot counts (pass_cnt != nullptr) are only taken in the
+  // rare re-run that follows a counter above the limit
+  uint32_t* pass_small;
+  int lg_small;
+  uint32_t* pass_cnt;
   // reads
   const uint64_t* rd_words;
   const uint64_t* rd_x;
@@ -122,8 +124,8 @@ struct ConfirmArgs {
   // order-dependent truncation (cmd/muscato_confirm/main.go:233-242, :424-448); the
   // cross-window de-duplication only counts windows whose group is not flagged.
   const uint8_t* slot_over;
-  const uint64_t* tab_fp;
-  int lg_slots;
+  const uint8_t* tab;
+  uint64_t n_buckets;
   uint4* over;
   unsigned long long over_cap;
   unsigned long long* n_over_inst;
@@ -206,11 +208,11 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
   const uint32_t j = (uint32_t)(i - c_start);
   // (item, read record): member 0 comes with the candidate record, further members from the CSR
   uint32_t item = cj.x;
-  uint2 rm = make_uint2(ci.w, cj.w);
+  uint32_t rmx = ci.w;
   if (j) {
-    const uint4 e = __ldg(a.items + cj.y + (j - 1));
+    const uint2 e = __ldg(a.items + cj.y + (j - 1));
     item = e.x;
-    rm = make_uint2(e.y, e.z);
+    rmx = e.y;
   }
   const uint32_t r = cfg.nwin == 1 ? item : (uint32_t)__umul64hi((uint64_t)item, a.nwin_magic);  // item / nwin
   const int k = (int)(item - r * (uint32_t)cfg.nwin);
@@ -219,9 +221,9 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
   const int64_t pos = p - q1;      // jw = jx - q1 >= 0 (cmd/muscato_screen/main.go:345, :355)
   if (pos < 0) return false;
 
-  const int L = (int)(rm.x & 0x7ffu);
-  const int budget = (int)((rm.x >> 11) & 0x7ffu);
-  const bool rx = rm.x >> 31;
+  const int L = (int)(rmx & 0x7ffu);
+  const int budget = (int)((rmx >> 11) & 0x7ffu);
+  const bool rx = rmx >> 31;
   const uint64_t* row = a.rd_words + (uint64_t)r * cfg.S;
   const uint64_t gstart = gpos - (uint64_t)q1;  // global base index of the read's first base
   const int64_t glen = (int64_t)gend - (int64_t)(gpos - (uint64_t)p);
@@ -322,7 +324,8 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
 
   // The pair passes through window k.
   const uint32_t slot = __ldg(a.cand + c).x;
-  atomicAdd(a.pass_cnt + slot, 1u);
+  atomicAdd(a.pass_small + ((slot * 0x9E3779B1u) >> (32 - a.lg_small)), 1u);
+  if (a.pass_cnt) atomicAdd(a.pass_cnt + slot, 1u);
   n_pass++;
   if (MODE == 2 && a.slot_over[slot]) {
     const unsigned long long at = warp_agg_inc(a.n_over_inst);
@@ -333,7 +336,7 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
   // Cross-window de-duplication: emit only through the lowest window index that delivers
   // this (read, gene, pos).  Window k' delivers it iff it is valid for the read, its k-mer
   // matches exactly, and -- when it would sit at target position 0 -- the literal-100 rule holds.
-  uint32_t vm = rm.y & ((1u << k) - 1u);
+  uint32_t vm = k ? (__ldg(a.validmask + r) & ((1u << k) - 1u)) : 0u;
   while (vm) {
     const int k2 = __ffs(vm) - 1;
     vm &= vm - 1;
@@ -342,7 +345,7 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
     if (!window_match(row, xrow, rx, a.tg_words, a.tg_x, tx, (uint64_t)q1b, gstart + (uint64_t)q1b, W)) continue;
     if (MODE == 2) {
       // a window whose key group is subject to truncation does not "own" the pair
-      const int64_t s2 = table_find(a.tab_fp, a.lg_slots, read_window_fp(row, xrow, rx, (uint64_t)q1b, W));
+      const int64_t s2 = table_find(a.tab, a.n_buckets, read_window_fp(row, xrow, rx, (uint64_t)q1b, W));
       if (s2 >= 0 && a.slot_over[s2]) continue;
     }
     return false;  // an earlier window owns this pair

@@ -156,4 +156,33 @@ __global__ void __launch_bounds__(256) pack_targets_kernel(const uint8_t* __rest
   }
 }
 
+// Targets that arrive already packed (msc_set_targets_packed: the persistent 2-bit target cache):
+// words / xplane were copied into place; this kernel zeroes the padding behind the stream, clears
+// the bits of the last word past the stream's end and derives the per-word X summary bits.
+__global__ void __launch_bounds__(256) packed_targets_finish_kernel(uint64_t* __restrict__ words, uint64_t* __restrict__ xplane,
+                                                                    uint64_t n_bases, uint64_t n_words_alloc,
+                                                                    uint32_t* __restrict__ xsum,
+                                                                    unsigned long long* __restrict__ any_x) {
+  pdl_enter();
+  const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words_alloc) return;
+  const uint64_t b0 = w * 32;
+  if (b0 >= n_bases) {
+    words[w] = 0ull;
+    xplane[w] = 0ull;
+    return;
+  }
+  uint64_t xb = xplane[w];
+  if (b0 + 32 > n_bases) {
+    const uint64_t keep = low_bases_mask((int)(n_bases - b0));
+    words[w] &= keep;
+    xb &= keep & kEvenBits;
+    xplane[w] = xb;
+  }
+  if (xb) {
+    atomicOr(xsum + (w >> 5), 1u << (unsigned)(w & 31u));
+    atomicOr(any_x, 1ull);
+  }
+}
+
 }  // namespace msc

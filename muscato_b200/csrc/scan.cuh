@@ -44,9 +44,10 @@ struct ScanArgs {
   const uint2* bloom;
   BloomGeom geom;
   uint32_t mul[8];        // mul[j] = 1 << (32 - 2m - 2j): m-mer j of a key to the top of a word
-  const uint64_t* tab_fp;
-  int lg_slots;
-  uint2* cand;
+  const uint8_t* tab;     // key table: 128-byte buckets (common.cuh)
+  uint64_t n_buckets;
+  uint2* cand;            // (slot, global target position)
+  uint4* cmeta;           // the slot's record {item0, rmx0, start, cnt}, same index as cand
   unsigned long long cand_cap;
   unsigned long long* n_cand;
   unsigned long long* n_bloom_pass;
@@ -122,8 +123,18 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
     unsigned long long out0 = 0;
     if (lane == 0) out0 = atomicAdd(a.n_cand, (unsigned long long)n_st);
     out0 = __shfl_sync(0xffffffffu, out0, 0);
-    for (uint32_t i = lane; i < n_st; i += 32)
-      if (out0 + i < a.cand_cap) a.cand[out0 + i] = st[i];
+    // The slot's record travels with the candidate: it sits in the bucket line the look-up has just
+    // brought into the L2, so this is the ONE dependent access a candidate costs (the expansion
+    // reads no table memory at all).
+#pragma unroll 4
+    for (uint32_t i = lane; i < n_st; i += 32) {
+      const uint2 e = st[i];
+      const uint4 rec = __ldg(slot_rec_ptr(a.tab, (uint64_t)e.x));
+      if (out0 + i < a.cand_cap) {
+        a.cand[out0 + i] = e;
+        a.cmeta[out0 + i] = rec;
+      }
+    }
     __syncwarp();
     n_st = 0;
   };
@@ -233,7 +244,6 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
       // load) of each is fetched before any is resolved -- the look-ups are independent and a
       // single one costs an L2 / HBM round trip.
       constexpr int kDrain = 2;
-      const uint64_t bmask = (1ull << (a.lg_slots - 2)) - 1ull;
       for (uint32_t base = 0; base < total; base += 32 * kDrain) {
         uint64_t fp[kDrain], bk[kDrain], q[kDrain][4];
         uint32_t e[kDrain];
@@ -256,23 +266,36 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
             } else {
               fp[u] = key_fp(window_at(tile[src], tile[src + 1], j, kmask), xm);
             }
-            bk[u] = table_home_bucket(fp[u], a.lg_slots);
-            ldg256(a.tab_fp + (bk[u] << 2), q[u][0], q[u][1], q[u][2], q[u][3]);
+            bk[u] = table_home_bucket(fp[u], a.n_buckets);
+            ldg256(bucket_ptr(a.tab, bk[u]), q[u][0], q[u][1], q[u][2], q[u][3]);  // the first four fingerprints of the home bucket
           }
         }
 #pragma unroll
         for (int u = 0; u < kDrain; u++) {
           if (base + 32 * u >= total) break;  // warp-uniform
-          int r = fp[u] ? bucket_probe(fp[u], q[u][0], q[u][1], q[u][2], q[u][3]) : 4;
-          while (r == 5) {  // home bucket full of other keys (rare): walk on
-            bk[u] = (bk[u] + 1) & bmask;
-            ldg256(a.tab_fp + (bk[u] << 2), q[u][0], q[u][1], q[u][2], q[u][3]);
-            r = bucket_probe(fp[u], q[u][0], q[u][1], q[u][2], q[u][3]);
+          // slots fill in order, so the fifth fingerprint only matters when the first four are taken
+          // by other keys (rare at the table's load factor): it is fetched on demand
+          int r = 5;  // 0..4 found, 5 = not in the table
+          if (fp[u]) {
+            while (true) {
+              if (q[u][0] == fp[u]) { r = 0; break; }
+              if (q[u][1] == fp[u]) { r = 1; break; }
+              if (q[u][2] == fp[u]) { r = 2; break; }
+              if (q[u][3] == fp[u]) { r = 3; break; }
+              if ((q[u][0] == 0ull) | (q[u][1] == 0ull) | (q[u][2] == 0ull) | (q[u][3] == 0ull)) break;
+              const uint64_t q4 = __ldg(reinterpret_cast<const unsigned long long*>(bucket_ptr(a.tab, bk[u]) + 32));
+              if (q4 == fp[u]) { r = 4; break; }
+              if (q4 == 0ull) break;
+              bk[u] = bk[u] + 1 == a.n_buckets ? 0 : bk[u] + 1;  // bucket full of other keys: walk on
+              ldg256(bucket_ptr(a.tab, bk[u]), q[u][0], q[u][1], q[u][2], q[u][3]);
+            }
           }
-          const bool hit = r < 4;
+          const bool hit = r < kBucketSlots;
           const unsigned found = __ballot_sync(0xffffffffu, hit);
           if (found) {
-            if (hit) st[n_st + __popc(found & ((1u << lane) - 1u))] = make_uint2((uint32_t)((bk[u] << 2) + r), (uint32_t)(wbase + e[u]));
+            if (hit)
+              st[n_st + __popc(found & ((1u << lane) - 1u))] =
+                  make_uint2((uint32_t)(bk[u] * kBucketSlots + (uint64_t)r), (uint32_t)(wbase + e[u]));
             n_st += __popc(found);
             __syncwarp();
             if (n_st > kStageCap - 32) flush_stage();

@@ -123,6 +123,26 @@ class HotPath:
         self.n_targets = len(o) - 1
         self._check(self._lib.msc_set_targets(self._ctx, a.ctypes.data, o.ctypes.data, self.n_targets))
 
+    def set_targets_packed(self, words: np.ndarray, xplane, offs: np.ndarray):
+        """Targets that are already 2-bit packed (the persistent target cache): words / xplane are uint64
+        arrays of (total bases + 31) // 32 entries in the layout of include/muscato_b200.h; xplane may
+        be None when no target contains X."""
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        xp = None if xplane is None else np.ascontiguousarray(xplane, dtype=np.uint64)
+        self.n_targets = len(offs) - 1
+        self._check(self._lib.msc_set_targets_packed(self._ctx, words.ctypes.data, xp.ctypes.data if xp is not None else None,
+                                                     offs.ctypes.data, self.n_targets))
+
+    def fetch_packed_targets(self):
+        """(words, xplane, has_x): the packed form of the current targets."""
+        n = int(self._lib.msc_packed_target_words(self._ctx))
+        words = np.zeros(max(1, n), dtype=np.uint64)
+        xp = np.zeros(max(1, n), dtype=np.uint64)
+        hx = C.c_int32(0)
+        self._check(self._lib.msc_fetch_packed_targets(self._ctx, words.ctypes.data, xp.ctypes.data, C.byref(hx)))
+        return words[:n], xp[:n], bool(hx.value)
+
     def set_reads_ptr(self, ascii_ptr: int, offs_ptr: int, n: int):
         """Raw-pointer variant (e.g. pinned host buffers owned by the caller)."""
         self.n_reads = n
