@@ -80,10 +80,11 @@ def test_fused_executable_cache_tiles_devices(case):
     _check_outputs(case, w)
     rep = json.load(open(w / "muscato_b200_hotpath.json"))
     assert rep["target_cache"] == "hit"
-    assert rep["h2d_bytes"] < h2d_text - 0.7 * 1_200_000 * 0.75
+    n_bases = 3 * 100 * 2 * 1000                       # 600 targets x 1 kb: 1 B/base as text, 0.25 B/base packed (no X plane)
+    assert rep["h2d_bytes"] <= h2d_text - 0.7 * n_bases * 0.75
     # 3. read batches x target ranges (the loop configs[3] needs) on two contexts
     w = _workdir(case, "tiled")
-    r = subprocess.run([build.EXE_PATH, str(w / "config.json"), "--no-target-cache", "--max-items", "50000", "--max-bases", "500000",
+    r = subprocess.run([build.EXE_PATH, str(w / "config.json"), "--no-target-cache", "--max-items", "50000", "--max-bases", "250000",
                         "--devices", "0,0"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     _check_outputs(case, w)
