@@ -110,6 +110,7 @@ struct msc_ctx {
   int device = 0;
   int sm_count = 148;
   int scan_grid = 0, confirm_grid = 0;
+  bool scatter_attr_set = false;
   const void* scan_fn_sized = nullptr;  // the scan kernel instance scan_grid was computed for
   cudaStream_t stream = nullptr;       // every kernel runs here
   cudaStream_t copy_stream = nullptr;  // input H2D copies: overlap with kernels of the previous input
@@ -147,7 +148,7 @@ struct msc_ctx {
   // candidates / pairs
   uint64_t n_cand = 0, n_pairs = 0;
   bool have_cand = false;
-  DevBuf cand, cmeta, cinfo, sizes, pstart, block_first;
+  DevBuf cand, cinfo, sizes, pstart, block_first;
   // matches
   uint64_t n_match_pre = 0, n_match = 0;
   bool have_confirm = false, have_combine = false;
@@ -447,8 +448,12 @@ int enqueue_build_reads(msc_ctx* ctx) {
     LAUNCH_CHECK();
     launch_k(ctx->pdl, build_offsets_kernel, 1, kMaxParts, 0, ctx->stream, ctx->part_count.as<unsigned int>(), (int)ctx->tgeo.n_parts);
     LAUNCH_CHECK();
-    launch_k(ctx->pdl, build_scatter_kernel, (unsigned)std::min<uint64_t>(grid_for(n_items, kStageKeys), (uint64_t)ctx->sm_count * 5), 256, 0,
-             ctx->stream, ctx->win, a);
+    if (!ctx->scatter_attr_set) {
+      CK(cudaFuncSetAttribute((const void*)build_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+      ctx->scatter_attr_set = true;
+    }
+    launch_k(ctx->pdl, build_scatter_kernel, (unsigned)std::min<uint64_t>(grid_for(n_items, kStageKeys), (uint64_t)ctx->sm_count * 2),
+             kScatterThreads, sizeof(ScatterSmem), ctx->stream, ctx->win, a);
     LAUNCH_CHECK();
     launch_k(ctx->pdl, build_insert_kernel, (unsigned)std::min<uint64_t>(grid_for(n_items, 256), g8), 256, 0, ctx->stream, a);
     LAUNCH_CHECK();
@@ -508,7 +513,10 @@ void account_pack_targets(msc_ctx* ctx) {
 // The candidate list is two parallel arrays: (slot, position) and the slot's record.
 int reserve_cand(msc_ctx* ctx, uint64_t n) {
   CK(ctx->cand.reserve(n * sizeof(uint2)));
-  CK(ctx->cmeta.reserve((ctx->cand.cap / sizeof(uint2) + 1) * sizeof(uint4)));
+  // the scan kernel writes the pair kernel's per-candidate record and the group size next to (slot, position)
+  const uint64_t ccap = ctx->cand.cap / sizeof(uint2);
+  CK(ctx->sizes.reserve((ccap + 1) * sizeof(uint32_t)));
+  CK(ctx->cinfo.reserve((ccap + 1) * 2 * sizeof(uint4)));
   return MSC_OK;
 }
 
@@ -536,7 +544,8 @@ int enqueue_scan(msc_ctx* ctx) {
   void (*scan_fn)(const ScanArgs) = pick_scan_kernel(ctx->win.W, ctx->geom.wn);
   if (ctx->scan_grid == 0 || ctx->scan_fn_sized != (const void*)scan_fn) {
     int blocks_per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_fn, kScanBlock, 0));
+    CK(cudaFuncSetAttribute((const void*)scan_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_fn, kScanBlock, sizeof(ScanSmem)));
     ctx->scan_grid = ctx->sm_count * std::max(1, blocks_per_sm);
     ctx->scan_fn_sized = (const void*)scan_fn;
   }
@@ -552,6 +561,7 @@ int enqueue_scan(msc_ctx* ctx) {
     a.tg_words = ctx->tg_words.as<uint64_t>();
     a.tg_x = ctx->tg_x.as<uint64_t>();
     a.xsum = ctx->xsum.as<uint32_t>();
+    a.targets_have_x = ctx->ctr(C_TGX);
     a.n_bases = ctx->n_bases;
     a.n_tiles = ctx->n_tiles;
     a.bloom = ctx->bloom.as<uint2>();
@@ -560,13 +570,19 @@ int enqueue_scan(msc_ctx* ctx) {
     a.tab = ctx->tab.as<uint8_t>();
     a.n_buckets = ctx->tgeo.n_buckets;
     a.cand = ctx->cand.as<uint2>();
-    a.cmeta = ctx->cmeta.as<uint4>();
+    a.cinfo = ctx->cinfo.as<uint4>();
+    a.sizes = ctx->sizes.as<uint32_t>();
+    a.tg_off = ctx->tg_off.as<uint32_t>();
+    a.blk2gene = ctx->blk2gene.as<uint32_t>();
+    a.n_targets = ctx->n_targets;
     a.cand_cap = ctx->cand_cap();
     a.n_cand = ctx->ctr(C_NCAND);
     a.n_bloom_pass = ctx->ctr(C_BLOOMPASS);
     a.W = ctx->win.W;
+    a.prefetch = 0;  // measured slower at S2 (72 vs 60 ms): the memory system is saturated, more requests in flight only add queueing
+    if (const char* e = getenv("MSC_SCAN_PREFETCH")) a.prefetch = atoi(e) != 0;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ctx->n_tiles, (uint64_t)ctx->scan_grid));
-    launch_k(ctx->pdl, scan_fn, grid, kScanBlock, 0, ctx->stream, a);
+    launch_k(ctx->pdl, scan_fn, grid, kScanBlock, sizeof(ScanSmem), ctx->stream, a);
     LAUNCH_CHECK();
   }
   CK(cudaEventRecord(ctx->ev[EV_SCAN1], ctx->stream));
@@ -576,16 +592,10 @@ int enqueue_scan(msc_ctx* ctx) {
 // ---- enqueue: expansion + pair kernel -------------------------------------------------------
 int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   const uint64_t ccap = ctx->cand_cap();
-  CK(ctx->sizes.reserve((ccap + 1) * sizeof(uint32_t)));
-  CK(ctx->cinfo.reserve((ccap + 1) * 2 * sizeof(uint4)));
   CK(ctx->pstart.reserve((ccap + 2) * sizeof(uint64_t)));
   if (ctx->block_first.cap == 0) CK(ctx->block_first.reserve(((size_t)(1u << 19) + 2) * sizeof(uint32_t)));
   if (outbuf.cap == 0) CK(outbuf.reserve((size_t)(1u << 20) * sizeof(uint4)));
   const unsigned pgrid = (unsigned)ctx->sm_count * 8;
-  launch_k(ctx->pdl, cand_prepare_kernel, pgrid, 256, 0, ctx->stream, ctx->cand.as<uint2>(), ctx->cmeta.as<uint4>(), ctx->ctr(C_NCAND), ccap,
-                                                      ctx->tg_off.as<uint32_t>(), ctx->blk2gene.as<uint32_t>(), ctx->win.W,
-                                                      ctx->cinfo.as<uint4>(), ctx->sizes.as<uint32_t>());
-  LAUNCH_CHECK();
   RC(enqueue_exclusive_scan<uint64_t>(ctx, ctx->sizes.as<uint32_t>(), ctx->ctr(C_NCAND), ccap, ctx->pstart.as<uint64_t>(),
                                       true, ctx->ctr(C_NPAIRS)));
   launch_k(ctx->pdl, pair_block_starts_kernel, pgrid, 256, 0, ctx->stream, ctx->pstart.as<uint64_t>(), ctx->ctr(C_NCAND), ccap,
@@ -968,6 +978,16 @@ msc_ctx* msc_create(const msc_config* config, char* errbuf, uint64_t errlen) {
     volatile double prod = one_minus * (double)L;
     nm[L] = (int32_t)prod;
   }
+  {
+    // read record word layout (build.cuh, WinCfg): length | budget | sketch | has-X
+    int max_nm = 0;
+    for (int32_t v : nm) max_nm = std::max(max_nm, (int)v);
+    ctx->win.lbits = std::max(1, ceil_log2((uint64_t)c.max_read_length + 1));
+    ctx->win.nbits = std::max(1, ceil_log2((uint64_t)max_nm + 1));
+    int sk = std::min(12, (31 - ctx->win.lbits - ctx->win.nbits) / 2);
+    if (const char* e = getenv("MSC_SKETCH")) sk = std::min(sk, atoi(e));
+    ctx->win.sk = sk >= 4 ? sk : 0;
+  }
   ok = ok && ctx->nmiss.reserve(nm.size() * sizeof(int32_t)) == cudaSuccess;
   ok = ok && cudaMemcpy(ctx->nmiss.p, nm.data(), nm.size() * sizeof(int32_t), cudaMemcpyHostToDevice) == cudaSuccess;
   ok = ok && cudaMemset(ctx->counters.p, 0, C_COUNT * sizeof(unsigned long long)) == cudaSuccess;
@@ -993,7 +1013,7 @@ void msc_destroy(msc_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->rd_ascii,    &ctx->rd_offs,   &ctx->rd_words, &ctx->rd_x,      &ctx->len_flags, &ctx->validmask, &ctx->rmeta,
                     &ctx->tab,         &ctx->recs,      &ctx->dups,     &ctx->part_count, &ctx->pass_small, &ctx->pass_cnt, &ctx->bloom,
-                    &ctx->items,       &ctx->cmeta,     &ctx->tg_ascii,  &ctx->tg_off,    &ctx->tg_words,
+                    &ctx->items,       &ctx->tg_ascii,  &ctx->tg_off,    &ctx->tg_words,
                     &ctx->tg_x,        &ctx->xsum,      &ctx->blk2gene,  &ctx->prep_perm, &ctx->prep_gstart, &ctx->nm_flag, &ctx->nm_pos, &ctx->nm_list, &ctx->cand,     &ctx->cinfo,     &ctx->sizes,     &ctx->pstart,
                     &ctx->block_first, &ctx->match_pre, &ctx->best,     &ctx->rcount,    &ctx->rstart,    &ctx->rfill,
                     &ctx->match_out,   &ctx->long_list, &ctx->mid_list, &ctx->counters,  &ctx->tile_sums, &ctx->scan_state, &ctx->nmiss};
@@ -1049,6 +1069,7 @@ static int reads_reserve(msc_ctx* ctx, uint64_t n_reads, uint64_t total) {
   {
     const uint64_t need = (kmax * 4 + 8) / 9;  // buckets: kmax / (5 * 0.45)
     int lg_bpp = 17;
+    if (const char* e = getenv("MSC_TABLE_LG_BPP")) lg_bpp = std::min(22, std::max(10, atoi(e)));  // tuning: partition size
     if (need <= (1ull << lg_bpp)) lg_bpp = std::max(3, ceil_log2(need));
     uint64_t parts = (need + (1ull << lg_bpp) - 1) >> lg_bpp;
     while (parts > (uint64_t)kMaxParts) {
@@ -1078,7 +1099,13 @@ static int reads_reserve(msc_ctx* ctx, uint64_t n_reads, uint64_t total) {
   // at most 8 m-mers compete (ALU cost per probed position).  MSC_MINIMIZER_M overrides m.
   {
     const int P = std::min(ctx->win.W, 16);
-    int m = (ctx->lg_bloom - 2 + 2 + 1) / 2;
+    // a filter beyond the L2 is addressed in 128-byte lines (what one HBM access delivers), an L2-resident one in
+    // 32-byte sectors (what one L1/L2 request moves); MSC_BLOOM_LG_BLK overrides (2 or 4)
+    int lg_blk = ctx->lg_bloom > 23 ? 4 : 2;
+    if (const char* e = getenv("MSC_BLOOM_LG_BLK")) lg_blk = atoi(e) >= 4 ? 4 : 2;
+    lg_blk = std::min(lg_blk, ctx->lg_bloom - 4);
+    ctx->geom.lg_blk = lg_blk;
+    int m = (ctx->lg_bloom - lg_blk + 2 + 1) / 2;
     if (const char* e = getenv("MSC_MINIMIZER_M")) m = atoi(e);
     m = std::max(m, P - 7);
     m = std::min(std::max(m, 1), P);
@@ -1396,7 +1423,7 @@ int msc_set_targets(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, ui
   CK(ctx->tg_words.reserve(ctx->n_words_alloc * sizeof(uint64_t)));
   CK(ctx->tg_x.reserve(ctx->n_words_alloc * sizeof(uint64_t)));
   CK(ctx->xsum.reserve((ctx->n_words_alloc / 32 + 4) * sizeof(uint32_t)));
-  // position -> target index at 2^kGeneBlockShift-base granularity (cand_prepare_kernel)
+  // position -> target index at 2^kGeneBlockShift-base granularity (scan kernel, flush_stage)
   const uint64_t n_blk = (total >> kGeneBlockShift) + 2;
   std::vector<uint32_t> blk(n_blk, n_targets ? (uint32_t)(n_targets - 1) : 0u);
   {

@@ -14,8 +14,29 @@ namespace msc {
 
 struct WinCfg {
   int nwin, W, MRL, S, min_dinuc;
+  // layout of the 32-bit read record word that travels with every (read, window) item:
+  //   bits [0, lbits) read length, [lbits, lbits + nbits) mismatch budget nmiss(L), then 2 * sk bits of SKETCH
+  //   (sk read bases next to the window, see item_sketch), bit 31 = the read contains X
+  int lbits, nbits, sk;
   int windows[32];
 };
+
+__host__ __device__ __forceinline__ int rmx_len(const WinCfg& c, uint32_t rmx) { return (int)(rmx & ((1u << c.lbits) - 1u)); }
+__host__ __device__ __forceinline__ int rmx_budget(const WinCfg& c, uint32_t rmx) {
+  return (int)((rmx >> c.lbits) & ((1u << c.nbits) - 1u));
+}
+__host__ __device__ __forceinline__ uint32_t rmx_sketch(const WinCfg& c, uint32_t rmx) {
+  return (rmx >> (c.lbits + c.nbits)) & ((1u << (2 * c.sk)) - 1u);
+}
+// First read base of the sketch of window k of a read of length L: the sk bases right of the window when the read
+// has them, else the sk bases left of it, else none (-1).  Build and confirm evaluate the same rule.
+__host__ __device__ __forceinline__ int sketch_start(const WinCfg& c, int k, int L) {
+  const int q1 = c.windows[k], q2 = q1 + c.W;
+  if (c.sk == 0) return -1;
+  if (q2 + c.sk <= L) return q2;
+  if (q1 >= c.sk) return q1 - c.sk;
+  return -1;
+}
 
 // utils.CountDinuc (utils/entropy.go:5-40) on a packed window: number of distinct adjacent
 // symbol pairs over a 5-letter alphabet (4 bases + X).  The count is invariant under
@@ -168,9 +189,9 @@ __global__ void __launch_bounds__(256) build_windows_kernel(const WinCfg cfg, co
       atomicAdd(&s_hist[key_partition(fp, a.tg)], 1u);
     }
     a.validmask[r] = vm;
-    // what the confirm kernel needs of a read: length (11 bits), mismatch budget nmiss(L) (11 bits),
-    // has-X flag; .y = valid-window mask
-    a.rmeta[r] = make_uint2((uint32_t)L | ((uint32_t)__ldg(a.nmiss + L) << 11) | (lf & 0x80000000u), vm);
+    // what the confirm kernel needs of a read: length, mismatch budget nmiss(L), has-X flag (WinCfg);
+    // .y = valid-window mask
+    a.rmeta[r] = make_uint2((uint32_t)L | ((uint32_t)__ldg(a.nmiss + L) << cfg.lbits) | (lf & 0x80000000u), vm);
   }
   __syncthreads();
   for (int p = threadIdx.x; p < P; p += blockDim.x) {
@@ -208,27 +229,38 @@ __global__ void __launch_bounds__(kMaxParts) build_offsets_kernel(unsigned int* 
 }
 
 // Pass B: distribute the key records into partition order.  One thread per (read, window) item; a
-// block stages kStageKeys items in shared memory, reserves one run per non-empty partition with a
-// single global atomic each and writes the runs (16-byte records; the two halves of a 32-byte
-// sector arrive from the same block within one flush, so DRAM sees whole sectors).
-constexpr int kStageRounds = 8;
-constexpr int kStageKeys = kStageRounds * 256;
+// block stages kStageKeys items in shared memory (dynamic, 98 KB: two blocks per SM), reserves one run per
+// non-empty partition with a single global atomic each and writes the runs of 16-byte records.  The
+// stage is as large as two resident blocks allow: the global atomics on the 1024 partition cursors
+// (one per partition and flush) were what bounded the 2048-record version (1.2 TB/s).
+constexpr int kScatterThreads = 512;
+constexpr int kStageRounds = 10;
+constexpr int kStageKeys = kStageRounds * kScatterThreads;  // 5120 records per flush: ~5 per partition and global atomic at 1024 partitions
 
-__global__ void __launch_bounds__(256) build_scatter_kernel(const WinCfg cfg, const BuildArgs a) {
+struct ScatterSmem {
+  alignas(16) uint4 rec[kStageKeys];
+  unsigned int cnt[kMaxParts];
+  unsigned int base[kMaxParts];
+  uint16_t part[kStageKeys];
+};
+
+__global__ void __launch_bounds__(kScatterThreads, 2) build_scatter_kernel(const WinCfg cfg, const BuildArgs a) {
   pdl_enter();
-  __shared__ uint4 s_rec[kStageKeys];
-  __shared__ uint16_t s_part[kStageKeys];
-  __shared__ unsigned int s_cnt[kMaxParts];
-  __shared__ unsigned int s_base[kMaxParts];
+  extern __shared__ __align__(16) unsigned char scatter_smem[];
+  ScatterSmem& sm = *reinterpret_cast<ScatterSmem*>(scatter_smem);
+  uint4* s_rec = sm.rec;
+  uint16_t* s_part = sm.part;
+  unsigned int* s_cnt = sm.cnt;
+  unsigned int* s_base = sm.base;
   const int P = (int)a.tg.n_parts;
   const uint64_t n_items = a.n_reads * (uint64_t)cfg.nwin;
   const uint64_t n_tiles = (n_items + kStageKeys - 1) / kStageKeys;
-  for (int p = threadIdx.x; p < P; p += 256) s_cnt[p] = 0u;
+  for (int p = threadIdx.x; p < P; p += kScatterThreads) s_cnt[p] = 0u;
   __syncthreads();
   for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 #pragma unroll 1
     for (int j = 0; j < kStageRounds; j++) {
-      const int idx = j * 256 + (int)threadIdx.x;
+      const int idx = j * kScatterThreads + (int)threadIdx.x;
       const uint64_t item = tile * (uint64_t)kStageKeys + (uint64_t)idx;
       uint32_t part = 0xFFFFu;
       if (item < n_items) {
@@ -239,14 +271,19 @@ __global__ void __launch_bounds__(256) build_scatter_kernel(const WinCfg cfg, co
           const uint64_t fp = window_fp(cfg, a.rd_words + r * (uint64_t)cfg.S, a.rd_x + r * (uint64_t)cfg.S, rmx >> 31, k,
                                         nullptr, nullptr, nullptr, nullptr);
           part = key_partition(fp, a.tg);
-          s_rec[idx] = make_uint4((uint32_t)fp, (uint32_t)(fp >> 32), (uint32_t)item, rmx);
+          // the item's sketch rides in the spare bits of the read record word (X-free reads only)
+          uint32_t rw = rmx;
+          const int s0 = (rmx >> 31) ? -1 : sketch_start(cfg, k, rmx_len(cfg, rmx));
+          if (s0 >= 0)
+            rw |= (uint32_t)(extract32(a.rd_words + r * (uint64_t)cfg.S, (uint64_t)s0) & low_bases_mask(cfg.sk)) << (cfg.lbits + cfg.nbits);
+          s_rec[idx] = make_uint4((uint32_t)fp, (uint32_t)(fp >> 32), (uint32_t)item, rw);
           atomicAdd(&s_cnt[part], 1u);
         }
       }
       s_part[idx] = (uint16_t)part;
     }
     __syncthreads();
-    for (int p = threadIdx.x; p < P; p += 256) {
+    for (int p = threadIdx.x; p < P; p += kScatterThreads) {
       const unsigned int c = s_cnt[p];
       if (c) s_base[p] = atomicAdd(a.part_count + p, c);
       s_cnt[p] = 0u;
@@ -254,12 +291,12 @@ __global__ void __launch_bounds__(256) build_scatter_kernel(const WinCfg cfg, co
     __syncthreads();
 #pragma unroll 1
     for (int j = 0; j < kStageRounds; j++) {
-      const int idx = j * 256 + (int)threadIdx.x;
+      const int idx = j * kScatterThreads + (int)threadIdx.x;
       const uint32_t part = s_part[idx];
       if (part != 0xFFFFu) a.recs[s_base[part] + atomicAdd(&s_cnt[part], 1u)] = s_rec[idx];
     }
     __syncthreads();
-    for (int p = threadIdx.x; p < P; p += 256) s_cnt[p] = 0u;
+    for (int p = threadIdx.x; p < P; p += kScatterThreads) s_cnt[p] = 0u;
     __syncthreads();
   }
 }

@@ -82,6 +82,9 @@ __host__ __device__ __forceinline__ uint32_t wide_khi(uint64_t k0, uint64_t k1) 
 // ---------------------------------------------------------------------------
 struct BloomGeom {
   int lg_words;    // log2(number of 64-bit words), 10..32
+  int lg_blk;      // log2(words per minimiser-addressed block): 2 = one 32-byte sector (filter resident in the L2:
+                   // the L1/L2 sector count is what a probe costs), 4 = one 128-byte line (filter beyond the L2: HBM
+                   // delivers whole lines, measured 118..128 B per random access, so the line is the unit to share)
   int m;           // minimiser length in bases, 1..16
   int wn;          // m-mers per key that compete: P - m + 1, 1..8
   uint32_t xr;     // alphabet relabelling of the key's low 32 bits: 0x55555555 cut to W bases
@@ -129,18 +132,18 @@ __device__ __forceinline__ uint32_t bloom_min_mmer(uint32_t prex, const uint32_t
   for (int j = 1; j < WN; j++) v = min(v, prex * mul[j]);
   return v;
 }
-__host__ __device__ __forceinline__ uint32_t bloom_sector_of(uint32_t vmin, int m, int lg_words) {
-  return ((vmin >> (32u - 2u * (unsigned)m)) * 0x9E3779B1u) >> (34 - lg_words);  // lg_sectors = lg_words - 2
+__host__ __device__ __forceinline__ uint32_t bloom_sector_of(uint32_t vmin, int m, int lg_words, int lg_blk) {
+  return ((vmin >> (32u - 2u * (unsigned)m)) * 0x9E3779B1u) >> (32 + lg_blk - lg_words);  // lg_blocks = lg_words - lg_blk
 }
 
-__host__ __device__ __forceinline__ uint32_t bloom_sector_rt(uint32_t prex, int wn, int m, int lg_words) {
+__host__ __device__ __forceinline__ uint32_t bloom_sector_rt(uint32_t prex, int wn, int m, int lg_words, int lg_blk) {
   const unsigned s0 = 32u - 2u * (unsigned)m;
   uint32_t v = prex << s0;
   for (int j = 1; j < wn; j++) {
     const uint32_t c = prex << (s0 - 2u * j);
     v = c < v ? c : v;
   }
-  return bloom_sector_of(v, m, lg_words);
+  return bloom_sector_of(v, m, lg_words, lg_blk);
 }
 
 // Word index and the two 32-bit half masks of a key (build side and the scan's X path; the
@@ -153,8 +156,8 @@ __host__ __device__ __forceinline__ void bloom_locate(uint64_t key, uint64_t xm,
     const uint32_t prex = (uint32_t)key ^ g.xr;
     const uint32_t h = W <= 16 ? bloom_hash32<true>(prex, 0u)
                                : bloom_hash32<false>(prex, W <= 32 ? (uint32_t)(key >> 32) : wide_khi(key, key1));
-    const uint32_t sec = bloom_sector_rt(prex, g.wn, g.m, g.lg_words);
-    widx = ((uint64_t)sec << 2) | (uint64_t)(h >> 30);
+    const uint32_t sec = bloom_sector_rt(prex, g.wn, g.m, g.lg_words, g.lg_blk);
+    widx = ((uint64_t)sec << g.lg_blk) | (uint64_t)(h >> (32 - g.lg_blk));
     bloom_masks32(h, mlo, mhi);
   } else {
     widx = fp >> (64 - g.lg_words);
@@ -209,6 +212,9 @@ __device__ __forceinline__ uint64_t ldcg64(const void* p) {
   asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+
+// Request a line into the L2 without a destination register.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ const uint8_t* bucket_ptr(const uint8_t* tab, uint64_t b) { return tab + b * (uint64_t)kBucketBytes; }
 __device__ __forceinline__ uint8_t* bucket_ptr(uint8_t* tab, uint64_t b) { return tab + b * (uint64_t)kBucketBytes; }

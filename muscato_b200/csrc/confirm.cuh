@@ -22,37 +22,10 @@ namespace msc {
 constexpr int kPairBlockShift = 5;
 constexpr int kPairBlock = 1 << kPairBlockShift;
 
-constexpr int kGeneBlockShift = 10;  // granularity of the position -> target index (msc_set_targets)
-
-// Per candidate: locate its gene once (block index + short binary search in the target offsets) and store what every
-// pair of the candidate needs in ONE 32-byte sector (two uint4): (global position of the window,
-// window start p inside the gene, global end of the gene, read record word of the first item) and
-// (first item of the key group, CSR start of the further items, gene index, 0).  The key group's
-// record {item0, rmx0, start, cnt} came with the candidate from the scan kernel (cmeta), so this
-// kernel is a pure stream: no table memory, no per-read look-up.  sizes[] = number of (read, window)
-// items of the key group.  A W-mer that straddles a target boundary is not a window of any target
-// (processSeq only rolls inside one target, cmd/muscato_screen/main.go:319): size 0.
-__global__ void __launch_bounds__(256) cand_prepare_kernel(const uint2* __restrict__ cand, const uint4* __restrict__ cmeta,
-                                                           const unsigned long long* __restrict__ n_cand_ptr,
-                                                           uint64_t cand_cap, const uint32_t* __restrict__ tg_off,
-                                                           const uint32_t* __restrict__ blk2gene, int W,
-                                                           uint4* __restrict__ cinfo, uint32_t* __restrict__ sizes) {
-  pdl_enter();
-  const uint64_t n_cand = min((uint64_t)*n_cand_ptr, cand_cap);
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint2 cd = cand[i];
-    const uint4 rec = cmeta[i];
-    // blk2gene[b] = target that holds base b << kGeneBlockShift: the search spans the few targets
-    // that start inside the candidate's block instead of the whole offset table
-    const uint64_t g_lo = __ldg(blk2gene + (cd.y >> kGeneBlockShift)), g_hi = __ldg(blk2gene + (cd.y >> kGeneBlockShift) + 1);
-    const uint64_t g = upper_bound_dev<uint32_t>(tg_off, g_lo + 1, g_hi + 1, cd.y) - 1;
-    const uint32_t goff = __ldg(tg_off + g);
-    const uint32_t gend = __ldg(tg_off + g + 1);
-    cinfo[2 * i] = make_uint4(cd.y, cd.y - goff, gend, rec.y);
-    cinfo[2 * i + 1] = make_uint4(rec.x, rec.z, (uint32_t)g, 0u);
-    sizes[i] = ((uint64_t)cd.y + (uint64_t)W <= (uint64_t)gend) ? 1u + rec.w : 0u;
-  }
-}
+// The candidates arrive from the scan kernel complete (scan.cuh, flush_stage): (slot, position), the key group's
+// size, and one 32-byte record per candidate -- (global position of the window, window start p inside the gene,
+// global end of the gene, read record word of the first item) and (first item of the key group, CSR start of the
+// further items, gene index, 0).  The expansion is therefore the exclusive scan of the sizes plus the block index below.
 
 // First candidate of every kPairBlock-pair block of the confirm kernel, so that the search inside
 // the kernel only spans the block's few candidates.  Entry n_blocks is a sentinel.  block_first[b]
@@ -82,7 +55,7 @@ __global__ void __launch_bounds__(256) pair_block_starts_kernel(const uint64_t* 
 
 struct ConfirmArgs {
   // candidates and their pair prefix
-  const uint4* cinfo;          // two per candidate, see cand_prepare_kernel
+  const uint4* cinfo;          // two per candidate, written by the scan kernel
   const uint2* cand;           // (slot, position): the slot is only needed by pairs that pass
   const uint32_t* block_first; // first candidate of each kPairBlock-pair block (+1 sentinel entry)
   const uint64_t* pstart;  // n_cand + 1
@@ -221,8 +194,8 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
   const int64_t pos = p - q1;      // jw = jx - q1 >= 0 (cmd/muscato_screen/main.go:345, :355)
   if (pos < 0) return false;
 
-  const int L = (int)(rmx & 0x7ffu);
-  const int budget = (int)((rmx >> 11) & 0x7ffu);
+  const int L = rmx_len(cfg, rmx);
+  const int budget = rmx_budget(cfg, rmx);
   const bool rx = rmx >> 31;
   const uint64_t* row = a.rd_words + (uint64_t)r * cfg.S;
   const uint64_t gstart = gpos - (uint64_t)q1;  // global base index of the read's first base
@@ -243,6 +216,19 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
   const bool tx = targets_have_x && tg_range_has_x(a.xsum, gstart >> 5, ((gstart + (uint64_t)L) >> 5) + 1);
   const bool anyx = rx | tx;
   const uint64_t* xrow = a.rd_x + (uint64_t)r * cfg.S;
+
+  // Sketch pre-filter: the item carries sk read bases next to its window (build.cuh, sketch_start); the target bases
+  // they would lie on are in lines the neighbouring candidates share.  More mismatches there than the budget allows
+  // rejects the pair (exact: the sketch bases are part of the full compare) WITHOUT touching the read's row -- at
+  // scale a row costs one 128-byte HBM line per pair and most pairs of a short window are chance hits.
+  if (MODE != 1 && !anyx) {
+    const int s0 = sketch_start(cfg, k, L);
+    if (s0 >= 0) {
+      const uint32_t tb = (uint32_t)(extract32(a.tg_words, gstart + (uint64_t)s0) & low_bases_mask(cfg.sk));
+      const uint32_t x = tb ^ rmx_sketch(cfg, rmx);
+      if (__popc((x | (x >> 1)) & 0x55555555u) > budget) return false;
+    }
+  }
 
   // Exact key equality for the window that produced this pair (merge join on the k-mer bytes,
   // cmd/muscato_confirm/main.go:382-393).  Fingerprints of X-free W<32 windows are exact, so only

@@ -27,6 +27,8 @@ constexpr int kWarpTileWords = 32;                    // one 32-base word per la
 constexpr int kWarpCopyWords = kWarpTileWords + 2;    // halo word + 1 (byte count multiple of 16)
 constexpr int kWarpSmemWords = kWarpTileWords + 8;    // keeps every buffer 64-byte aligned
 constexpr int kStageCap = 128;                        // per-warp candidate staging (entries)
+constexpr int kGeneBlockShift = 10;                   // granularity of the position -> target index (msc_set_targets)
+constexpr int kGeneTab = 64;                          // target offsets a warp keeps in shared memory per tile
 #ifndef MSC_SCAN_BATCH
 #define MSC_SCAN_BATCH 8
 #endif
@@ -39,6 +41,7 @@ struct ScanArgs {
   const uint64_t* tg_words;
   const uint64_t* tg_x;
   const uint32_t* xsum;
+  const unsigned long long* targets_have_x;  // device flag: 0 = no target word contains X (no summary look-ups at all)
   uint64_t n_bases;
   uint64_t n_tiles;       // 256-word tiles; the buffers are padded to n_tiles * 256 + 64 words
   const uint2* bloom;
@@ -47,11 +50,28 @@ struct ScanArgs {
   const uint8_t* tab;     // key table: 128-byte buckets (common.cuh)
   uint64_t n_buckets;
   uint2* cand;            // (slot, global target position)
-  uint4* cmeta;           // the slot's record {item0, rmx0, start, cnt}, same index as cand
+  // the candidate's 32-byte record for the pair kernel (two uint4, see flush_stage) and its key group's size
+  uint4* cinfo;
+  uint32_t* sizes;
+  const uint32_t* tg_off;    // n_targets + 1 base offsets of the concatenated stream
+  const uint32_t* blk2gene;  // target that holds base b << kGeneBlockShift
+  uint64_t n_targets;
   unsigned long long cand_cap;
   unsigned long long* n_cand;
   unsigned long long* n_bloom_pass;
   int W;
+  int prefetch;           // 1 = request every queued position's bucket line into the L2 before the drain (MSC_SCAN_PREFETCH)
+};
+
+// Shared memory of one scan CTA (dynamic: 50 KB, above the 48 KB static limit).
+struct ScanSmem {
+  alignas(128) uint64_t tiles[kScanWarps][2][kWarpSmemWords];
+  alignas(16) uint4 stage_rec[kScanWarps][kStageCap];  // the key group record of every staged candidate
+  alignas(8) uint64_t bars[kScanWarps][2];
+  uint2 stage[kScanWarps][kStageCap];  // found (slot, position) pairs, flushed when nearly full
+  uint16_t queue[kScanWarps][1024];
+  uint32_t gtab[kScanWarps][kGeneTab + 4];  // tg_off[g0 .. g0 + kGeneTab] of the current tile (g0 = target of its first block)
+  uint32_t pattern[1024];              // bloom_pattern(): the two low-half bits of a key
 };
 
 // Extract the W-mer that starts at base j (0..31) of the word pair (lo, hi).
@@ -75,11 +95,15 @@ __device__ __forceinline__ uint64_t window_at(uint64_t lo, uint64_t hi, unsigned
 template <int KW, int WN>
 __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel(const ScanArgs a) {
   pdl_enter();
-  __shared__ alignas(128) uint64_t tiles[kScanWarps][2][kWarpSmemWords];
-  __shared__ alignas(8) uint64_t bars[kScanWarps][2];
-  __shared__ uint16_t queue[kScanWarps][1024];
-  __shared__ uint2 stage[kScanWarps][kStageCap];  // found (slot, position) pairs, flushed when nearly full
-  __shared__ uint32_t pattern[1024];              // bloom_pattern(): the two low-half bits of a key
+  extern __shared__ __align__(128) unsigned char scan_smem[];
+  ScanSmem& sm = *reinterpret_cast<ScanSmem*>(scan_smem);
+  auto& tiles = sm.tiles;
+  auto& bars = sm.bars;
+  auto& queue = sm.queue;
+  auto& stage = sm.stage;
+  auto& stage_rec = sm.stage_rec;
+  auto& pattern = sm.pattern;
+  uint32_t* gt = sm.gtab[threadIdx.x >> 5];
   for (int i = threadIdx.x; i < 1024; i += kScanBlock) pattern[i] = bloom_pattern((uint32_t)i);
   __syncthreads();
   const int tid = threadIdx.x;
@@ -93,6 +117,7 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
   }
   __syncwarp();
 
+  const bool any_x = *a.targets_have_x != 0ull;
   constexpr bool K32 = KW == 0;
   constexpr bool WIDE = KW == 2;
   const uint64_t kmask = low_bases_mask(min(a.W, 32));
@@ -100,6 +125,7 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
   const uint32_t xr = a.geom.xr;
   const int gm = a.geom.m;
   const int lg_words = a.geom.lg_words;
+  const int lg_blk = a.geom.lg_blk;
   // Static, balanced split: the stream is cut into units of kProbeBatch words and every warp of
   // the grid gets a contiguous run of units whose length differs by at most one between warps;
   // the warp walks its run in tiles of up to 32 words (the last one may be shorter).
@@ -119,25 +145,54 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
   uint2* st = stage[warp];
   uint32_t n_st = 0;  // staged candidates of this warp (warp-uniform)
   // One global atomic per flush instead of one per drain round: same-address atomics serialise.
+  uint4* st_rec = stage_rec[warp];
+  // Flush: one global atomic reserves the run; every staged candidate is written as the pair kernel wants it --
+  // (slot, position), its key group's size, and ONE 32-byte record (two uint4):
+  //   (global position of the window, window start p inside its target, global end of the target, read record of item 0)
+  //   (item 0 of the key group, CSR start of the further items, target index, 0)
+  // so the expansion needs no pass over the candidates of its own.  The target of a position comes from the tile's
+  // slice of the offset table in shared memory (gt[]: loaded once per tile; the stage is flushed at the end of every
+  // tile, so all staged positions belong to the current one) -- per-candidate look-ups in global memory were measured
+  // to miss the L2 this kernel's random traffic keeps flushing.  A tile with more than kGeneTab target starts falls
+  // back to the global search.  A W-mer that straddles a target boundary is not a window of any target (processSeq
+  // only rolls inside one target, cmd/muscato_screen/main.go:319): size 0.
+  uint32_t g0 = 0;     // target that holds the first base of the tile's first 2^kGeneBlockShift block
+  bool gt_ok = false;  // gt[] covers the whole tile
   auto flush_stage = [&]() {
     unsigned long long out0 = 0;
     if (lane == 0) out0 = atomicAdd(a.n_cand, (unsigned long long)n_st);
     out0 = __shfl_sync(0xffffffffu, out0, 0);
-    // The slot's record travels with the candidate: it sits in the bucket line the look-up has just
-    // brought into the L2, so this is the ONE dependent access a candidate costs (the expansion
-    // reads no table memory at all).
-#pragma unroll 4
+#pragma unroll 2
     for (uint32_t i = lane; i < n_st; i += 32) {
       const uint2 e = st[i];
-      const uint4 rec = __ldg(slot_rec_ptr(a.tab, (uint64_t)e.x));
-      if (out0 + i < a.cand_cap) {
-        a.cand[out0 + i] = e;
-        a.cmeta[out0 + i] = rec;
+      const uint4 rec = st_rec[i];
+      uint32_t g, goff, gend;
+      if (gt_ok) {
+        // number of offsets gt[1..kGeneTab] <= position (ascending): branch-free binary search in shared memory
+        uint32_t c = 0;
+#pragma unroll
+        for (int step = kGeneTab / 2; step >= 1; step >>= 1) c += (gt[c + step] <= e.y) ? step : 0;
+        g = g0 + c;
+        goff = gt[c];
+        gend = gt[c + 1];
+      } else {
+        const uint64_t g_lo = __ldg(a.blk2gene + (e.y >> kGeneBlockShift)), g_hi = __ldg(a.blk2gene + (e.y >> kGeneBlockShift) + 1);
+        g = (uint32_t)(upper_bound_dev<uint32_t>(a.tg_off, g_lo + 1, g_hi + 1, e.y) - 1);
+        goff = __ldg(a.tg_off + g);
+        gend = __ldg(a.tg_off + g + 1);
+      }
+      const unsigned long long o = out0 + i;
+      if (o < a.cand_cap) {
+        a.cand[o] = e;
+        a.cinfo[2 * o] = make_uint4(e.y, e.y - goff, gend, rec.y);
+        a.cinfo[2 * o + 1] = make_uint4(rec.x, rec.z, g, 0u);
+        a.sizes[o] = ((uint64_t)e.y + (uint64_t)a.W <= (uint64_t)gend) ? 1u + rec.w : 0u;
       }
     }
     __syncwarp();
     n_st = 0;
   };
+  uint32_t g0_next = w0 < w_end ? __ldg(a.blk2gene + ((w0 * 32ull) >> kGeneBlockShift)) : 0u;
   for (; w0 < w_end; w0 += kWarpTileWords) {
     const uint64_t wn = w0 + kWarpTileWords;
     if (lane == 0 && wn < w_end) {
@@ -145,6 +200,13 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
       bulk_copy_g2s(tiles[warp][buf ^ 1], a.tg_words + wn, kBytes, &bar[buf ^ 1]);
     }
     const int tile_words = (int)min((uint64_t)kWarpTileWords, w_end - w0);  // multiple of kProbeBatch
+    // the tile's slice of the target offsets: requested now, consumed only when phase 2 starts (the loads overlap the
+    // tile's arrival and the whole of phase 1)
+    g0 = g0_next;
+    if (wn < w_end) g0_next = __ldg(a.blk2gene + ((wn * 32ull) >> kGeneBlockShift));  // for the next tile: no dependent wait
+    const uint32_t gt_o0 = __ldg(a.tg_off + min((uint64_t)g0 + lane, a.n_targets));
+    const uint32_t gt_o1 = __ldg(a.tg_off + min((uint64_t)g0 + 32u + lane, a.n_targets));
+    const uint32_t gt_o2 = __ldg(a.tg_off + min((uint64_t)g0 + 64u, a.n_targets));
     mbar_wait(&bar[buf], (phases >> buf) & 1u);
     phases ^= 1u << buf;
     const uint64_t* tile = tiles[warp][buf];
@@ -152,8 +214,8 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
     // lane i owns word i of the tile: its pass mask and its X flag
     uint32_t mask = 0;
     // X summary bits of word w and w+1 (xsum is padded): bit i of xwords = word i of the tile needs the X path
-    unsigned xwords;
-    {
+    unsigned xwords = 0;
+    if (any_x) {
       const uint64_t w = w0 + (uint64_t)lane;
       const uint32_t xs0 = __ldg(a.xsum + (w >> 5));
       const uint32_t xs1 = __ldg(a.xsum + ((w + 1) >> 5));
@@ -183,8 +245,8 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
             if (WIDE) h[i] = bloom_hash32<false>(prex, wide_khi(key, window_at(tile[wi + 1], tile[wi + 2], lane, kmask1)));
             else h[i] = bloom_hash32<false>(prex, (uint32_t)(key >> 32));
           }
-          const uint32_t sec = bloom_sector_of(bloom_min_mmer<WN>(prex, a.mul), gm, lg_words);
-          bw[i] = __ldg(a.bloom + __funnelshift_l(h[i], sec, 2));  // (sec << 2) | (h >> 30)
+          const uint32_t sec = bloom_sector_of(bloom_min_mmer<WN>(prex, a.mul), gm, lg_words, lg_blk);
+          bw[i] = __ldg(a.bloom + __funnelshift_l(h[i], sec, lg_blk));  // (block << lg_blk) | (h >> (32 - lg_blk))
         }
 #pragma unroll
         for (int i = 0; i < kProbeBatch; i++) {
@@ -230,6 +292,12 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
     }
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     if (total) {
+      gt[lane] = gt_o0;
+      gt[32 + lane] = gt_o1;
+      if (lane == 0) gt[kGeneTab] = gt_o2;
+      // covered when the offset after the table lies beyond the tile's last base (offsets past the last target repeat
+      // the total, which is beyond every position)
+      gt_ok = (uint64_t)gt_o2 > w0 * 32ull + (uint64_t)(32 * kWarpTileWords - 1);
       n_pass += cnt;
       uint32_t at = incl - cnt;
       uint32_t m = mask;
@@ -240,9 +308,26 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
       }
       __syncwarp();
       const uint64_t wbase = w0 * 32ull;  // first position of this warp tile
-      // kDrain table look-ups in flight per lane: the home bucket (four fingerprints, one 256-bit
-      // load) of each is fetched before any is resolved -- the look-ups are independent and a
-      // single one costs an L2 / HBM round trip.
+      // fingerprint of a queued position (e = word << 5 | base), as the table stores it
+      auto entry_fp = [&](uint32_t e) -> uint64_t {
+        const unsigned src = e >> 5, j = e & 31u;
+        uint64_t xm = 0, xm1 = 0;
+        const bool hasx = (xwords_all >> src) & 1u;
+        if (hasx) xm = window_at(__ldg(a.tg_x + w0 + src), __ldg(a.tg_x + w0 + src + 1), j, kmask);
+        if (WIDE) {
+          if (hasx) xm1 = window_at(__ldg(a.tg_x + w0 + src + 1), __ldg(a.tg_x + w0 + src + 2), j, kmask1);
+          return key_fp_wide(window_at(tile[src], tile[src + 1], j, kmask), window_at(tile[src + 1], tile[src + 2], j, kmask1), xm, xm1);
+        }
+        return key_fp(window_at(tile[src], tile[src + 1], j, kmask), xm);
+      };
+      // Pass A: the home bucket LINE of every queued position is requested into the L2 up front (prefetch: no
+      // register, no scoreboard) -- all of the tile's look-ups are in flight together, and the drain below, which
+      // can only keep kDrain per lane in registers, finds its lines in the L2 instead of waiting for HBM round by round.
+      if (a.prefetch)
+        for (uint32_t idx = lane; idx < total; idx += 32)
+          prefetch_l2(bucket_ptr(a.tab, table_home_bucket(entry_fp(q16[idx]), a.n_buckets)));
+      // Pass B: kDrain look-ups per lane and round: the home bucket (first four fingerprints, one 256-bit load) of
+      // each is fetched before any is resolved; then the group records of the hits (same line) are fetched together.
       constexpr int kDrain = 2;
       for (uint32_t base = 0; base < total; base += 32 * kDrain) {
         uint64_t fp[kDrain], bk[kDrain], q[kDrain][4];
@@ -255,47 +340,51 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
           bk[u] = 0;
           q[u][0] = q[u][1] = q[u][2] = q[u][3] = 0;
           if (e[u] != 0xffffffffu) {
-            const unsigned src = e[u] >> 5, j = e[u] & 31u;
-            uint64_t xm = 0, xm1 = 0;
-            const bool hasx = (xwords_all >> src) & 1u;
-            if (hasx) xm = window_at(__ldg(a.tg_x + w0 + src), __ldg(a.tg_x + w0 + src + 1), j, kmask);
-            if (WIDE) {
-              if (hasx) xm1 = window_at(__ldg(a.tg_x + w0 + src + 1), __ldg(a.tg_x + w0 + src + 2), j, kmask1);
-              fp[u] = key_fp_wide(window_at(tile[src], tile[src + 1], j, kmask), window_at(tile[src + 1], tile[src + 2], j, kmask1),
-                                  xm, xm1);
-            } else {
-              fp[u] = key_fp(window_at(tile[src], tile[src + 1], j, kmask), xm);
-            }
+            fp[u] = entry_fp(e[u]);
             bk[u] = table_home_bucket(fp[u], a.n_buckets);
             ldg256(bucket_ptr(a.tab, bk[u]), q[u][0], q[u][1], q[u][2], q[u][3]);  // the first four fingerprints of the home bucket
           }
         }
+        int r[kDrain];
 #pragma unroll
         for (int u = 0; u < kDrain; u++) {
-          if (base + 32 * u >= total) break;  // warp-uniform
           // slots fill in order, so the fifth fingerprint only matters when the first four are taken
           // by other keys (rare at the table's load factor): it is fetched on demand
-          int r = 5;  // 0..4 found, 5 = not in the table
+          r[u] = 5;  // 0..4 found, 5 = not in the table
           if (fp[u]) {
             while (true) {
-              if (q[u][0] == fp[u]) { r = 0; break; }
-              if (q[u][1] == fp[u]) { r = 1; break; }
-              if (q[u][2] == fp[u]) { r = 2; break; }
-              if (q[u][3] == fp[u]) { r = 3; break; }
+              if (q[u][0] == fp[u]) { r[u] = 0; break; }
+              if (q[u][1] == fp[u]) { r[u] = 1; break; }
+              if (q[u][2] == fp[u]) { r[u] = 2; break; }
+              if (q[u][3] == fp[u]) { r[u] = 3; break; }
               if ((q[u][0] == 0ull) | (q[u][1] == 0ull) | (q[u][2] == 0ull) | (q[u][3] == 0ull)) break;
               const uint64_t q4 = __ldg(reinterpret_cast<const unsigned long long*>(bucket_ptr(a.tab, bk[u]) + 32));
-              if (q4 == fp[u]) { r = 4; break; }
+              if (q4 == fp[u]) { r[u] = 4; break; }
               if (q4 == 0ull) break;
               bk[u] = bk[u] + 1 == a.n_buckets ? 0 : bk[u] + 1;  // bucket full of other keys: walk on
               ldg256(bucket_ptr(a.tab, bk[u]), q[u][0], q[u][1], q[u][2], q[u][3]);
             }
           }
-          const bool hit = r < kBucketSlots;
+        }
+        // the group records of the hits sit in the bucket lines the look-ups have just brought in: fetched NOW, while
+        // the lines are in the L2 for certain (fetched at flush time they were measured to come from HBM a second time)
+        uint4 rr[kDrain];
+#pragma unroll
+        for (int u = 0; u < kDrain; u++) {
+          rr[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (r[u] < kBucketSlots) rr[u] = __ldg(reinterpret_cast<const uint4*>(bucket_ptr(a.tab, bk[u]) + kBucketRecOff) + r[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kDrain; u++) {
+          if (base + 32 * u >= total) break;  // warp-uniform
+          const bool hit = r[u] < kBucketSlots;
           const unsigned found = __ballot_sync(0xffffffffu, hit);
           if (found) {
-            if (hit)
-              st[n_st + __popc(found & ((1u << lane) - 1u))] =
-                  make_uint2((uint32_t)(bk[u] * kBucketSlots + (uint64_t)r), (uint32_t)(wbase + e[u]));
+            if (hit) {
+              const uint32_t at = n_st + __popc(found & ((1u << lane) - 1u));
+              st[at] = make_uint2((uint32_t)(bk[u] * kBucketSlots + (uint64_t)r[u]), (uint32_t)(wbase + e[u]));
+              st_rec[at] = rr[u];
+            }
             n_st += __popc(found);
             __syncwarp();
             if (n_st > kStageCap - 32) flush_stage();
@@ -303,11 +392,11 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
         }
       }
       __syncwarp();
+      if (n_st) flush_stage();  // the stage never outlives its tile (gt[] is the tile's)
     }
     __syncwarp();  // all lanes are done with tile[buf] before lane 0 lets the TMA engine refill it
     buf ^= 1;
   }
-  if (n_st) flush_stage();
   n_pass = __reduce_add_sync(0xffffffffu, n_pass);
   if (lane == 0 && n_pass) atomicAdd(a.n_bloom_pass, (unsigned long long)n_pass);
 }
