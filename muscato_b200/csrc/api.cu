@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/muscato_b200.h"
@@ -579,6 +580,8 @@ int enqueue_scan(msc_ctx* ctx) {
     a.n_cand = ctx->ctr(C_NCAND);
     a.n_bloom_pass = ctx->ctr(C_BLOOMPASS);
     a.W = ctx->win.W;
+    a.alu_masks = ctx->lg_bloom > 23 ? 1 : 0;
+    if (const char* e = getenv("MSC_SCAN_ALU_MASKS")) a.alu_masks = atoi(e) != 0;
     a.prefetch = 0;  // measured slower at S2 (72 vs 60 ms): the memory system is saturated, more requests in flight only add queueing
     if (const char* e = getenv("MSC_SCAN_PREFETCH")) a.prefetch = atoi(e) != 0;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ctx->n_tiles, (uint64_t)ctx->scan_grid));

@@ -67,7 +67,7 @@ extern "C" {
 
 // Targets of block `block`: genes_per_block * (rev ? 2 : 1) sequences of gene_len bases, written
 // back to back into out (2i = forward, 2i+1 = reverse complement when rev).  period > 0 makes the
-// block low-complexity (S4): every gene is a tandem repeat of a random unit of 1..period bases with
+// block low-complexity (S4): every gene is a tandem repeat of a random unit of pmin..pmax bases (period = pmax | pmin << 8) with
 // sub256/256 of its bases substituted.
 void msc_gen_targets(uint64_t seed, uint64_t block, uint32_t genes_per_block, uint32_t gene_len, int rev, uint32_t period,
                      uint32_t sub256, uint8_t* out) {
@@ -79,7 +79,9 @@ void msc_gen_targets(uint64_t seed, uint64_t block, uint32_t genes_per_block, ui
       fill_random(g, fw, gene_len);
     } else {
       uint8_t unit[64];
-      const uint32_t p = 1 + (uint32_t)g.below(period < 64 ? period : 64);
+      // period = longest unit | shortest unit << 8 (0 = 1)
+      const uint32_t pmax = (period & 255u) < 64 ? (period & 255u) : 64, pmin = (period >> 8) ? (period >> 8) : 1;
+      const uint32_t p = pmin >= pmax ? pmax : pmin + (uint32_t)g.below(pmax - pmin + 1);
       fill_random(g, unit, p);
       for (uint32_t j = 0; j < gene_len; j++) fw[j] = unit[j % p];
       if (sub256) {

@@ -75,6 +75,8 @@ __device__ __forceinline__ uint64_t scan_count(const unsigned long long* n_ptr, 
 // (10^6..10^8 counters) that beats a decoupled look-back chain, whose per-tile hand-over latency
 // dominates below ~10^7 elements.
 // ---------------------------------------------------------------------------------------------
+constexpr int kBigItems = 16;  // elements per thread and round on the large-array path
+
 template <typename OutT>
 __global__ void __launch_bounds__(kScanThreads) scan_resident_kernel(const uint32_t* __restrict__ in,
                                                                      const unsigned long long* n_ptr, uint64_t n_host,
@@ -117,12 +119,17 @@ __global__ void __launch_bounds__(kScanThreads) scan_resident_kernel(const uint3
     }
     ex_in_block = block_exclusive_scan_u64(s, &s_total, warp_sums);
   } else {
-    for (uint64_t i = lo + (uint64_t)threadIdx.x * 4; i < hi; i += kScanTile) {
-      if (i + 4 <= hi) {
-        const uint4 v = *reinterpret_cast<const uint4*>(in + i);
-        s += (uint64_t)v.x + v.y + v.z + v.w;
+    // kBigItems contiguous elements per thread and round: four 16-byte loads in flight per thread (one block per
+    // SM has to keep HBM busy on its own)
+    for (uint64_t i0 = lo + (uint64_t)threadIdx.x * kBigItems; i0 < hi; i0 += (uint64_t)kScanThreads * kBigItems) {
+      if (i0 + kBigItems <= hi) {
+        uint4 v[kBigItems / 4];
+#pragma unroll
+        for (int q = 0; q < kBigItems / 4; q++) v[q] = *reinterpret_cast<const uint4*>(in + i0 + 4 * q);
+#pragma unroll
+        for (int q = 0; q < kBigItems / 4; q++) s += (uint64_t)v[q].x + v[q].y + v[q].z + v[q].w;
       } else {
-        for (uint64_t j = i; j < hi; j++) s += in[j];
+        for (uint64_t j = i0; j < hi; j++) s += in[j];
       }
     }
     (void)block_exclusive_scan_u64(s, &s_total, warp_sums);
@@ -161,22 +168,47 @@ __global__ void __launch_bounds__(kScanThreads) scan_resident_kernel(const uint3
     }
     return;
   }
-  for (uint64_t base = lo; base < hi; base += kScanTile) {
-    const uint64_t i = base + (uint64_t)threadIdx.x * 4;
-    uint32_t v[4] = {0u, 0u, 0u, 0u};
-    if (i + 4 <= hi) {
-      const uint4 q = *reinterpret_cast<const uint4*>(in + i);
-      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
-      for (int j = 0; j < 4; j++)
-        if (i + j < hi) v[j] = in[i + j];
-    }
-    const uint64_t t = (uint64_t)v[0] + v[1] + v[2] + v[3];
-    uint64_t run = run0 + block_exclusive_scan_u64(t, &s_total, warp_sums);
+  for (uint64_t base = lo; base < hi; base += (uint64_t)kScanThreads * kBigItems) {
+    const uint64_t i0 = base + (uint64_t)threadIdx.x * kBigItems;
+    uint32_t v[kBigItems];
+    const bool whole = i0 + kBigItems <= hi;
+    if (whole) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      if (i + j < hi) out[i + j] = (OutT)run;
-      run += v[j];
+      for (int q = 0; q < kBigItems / 4; q++) {
+        const uint4 w = *reinterpret_cast<const uint4*>(in + i0 + 4 * q);
+        v[4 * q] = w.x; v[4 * q + 1] = w.y; v[4 * q + 2] = w.z; v[4 * q + 3] = w.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < kBigItems; q++) v[q] = i0 + q < hi ? in[i0 + q] : 0u;
+    }
+    uint64_t t = 0;
+#pragma unroll
+    for (int q = 0; q < kBigItems; q++) t += v[q];
+    uint64_t run = run0 + block_exclusive_scan_u64(t, &s_total, warp_sums);
+    if (whole) {
+      // slices start at multiples of 4 elements and rounds at multiples of kBigItems: 16-byte aligned vector stores
+      if (sizeof(OutT) == 8) {
+#pragma unroll
+        for (int q = 0; q < kBigItems; q += 2) {
+          const uint64_t a0 = run, a1 = run + v[q];
+          run = a1 + v[q + 1];
+          *reinterpret_cast<ulonglong2*>(out + i0 + q) = make_ulonglong2(a0, a1);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < kBigItems; q += 4) {
+          const uint64_t a0 = run, a1 = a0 + v[q], a2 = a1 + v[q + 1], a3 = a2 + v[q + 2];
+          run = a3 + v[q + 3];
+          *reinterpret_cast<uint4*>(out + i0 + q) = make_uint4((uint32_t)a0, (uint32_t)a1, (uint32_t)a2, (uint32_t)a3);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < kBigItems; q++) {
+        if (i0 + q < hi) out[i0 + q] = (OutT)run;
+        run += v[q];
+      }
     }
     run0 += s_total;
     __syncthreads();  // s_total / warp_sums are reused by the next round

@@ -60,6 +60,7 @@ struct ScanArgs {
   unsigned long long* n_cand;
   unsigned long long* n_bloom_pass;
   int W;
+  int alu_masks;          // 1 = Bloom bit masks by arithmetic instead of the shared-memory pattern table (MSC_SCAN_ALU_MASKS)
   int prefetch;           // 1 = request every queued position's bucket line into the L2 before the drain (MSC_SCAN_PREFETCH)
 };
 
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
   // only rolls inside one target, cmd/muscato_screen/main.go:319): size 0.
   uint32_t g0 = 0;     // target that holds the first base of the tile's first 2^kGeneBlockShift block
   bool gt_ok = false;  // gt[] covers the whole tile
+  uint32_t gb0 = 0, gb1 = 0, gb2 = 0, gb3 = 0;  // tg_off[g0 .. g0 + 3] (warp-uniform copies of gt[0..3])
   auto flush_stage = [&]() {
     unsigned long long out0 = 0;
     if (lane == 0) out0 = atomicAdd(a.n_cand, (unsigned long long)n_st);
@@ -167,7 +169,13 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
       const uint2 e = st[i];
       const uint4 rec = st_rec[i];
       uint32_t g, goff, gend;
-      if (gt_ok) {
+      if (e.y < gb3) {
+        // the tile's first three targets, offsets in registers (a 1024-base tile rarely holds more starts)
+        const uint32_t c = (e.y >= gb1) + (e.y >= gb2);
+        g = g0 + c;
+        goff = c == 0 ? gb0 : (c == 1 ? gb1 : gb2);
+        gend = c == 0 ? gb1 : (c == 1 ? gb2 : gb3);
+      } else if (gt_ok) {
         // number of offsets gt[1..kGeneTab] <= position (ascending): branch-free binary search in shared memory
         uint32_t c = 0;
 #pragma unroll
@@ -251,7 +259,10 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
 #pragma unroll
         for (int i = 0; i < kProbeBatch; i++) {
           // same masks as bloom_masks32(): pattern table look-up + rotate
-          const uint32_t mlo = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pattern) + (h[i] & 0xFFCu));
+          // pattern table in shared memory (L2-resident regime: the ALU pipe is the limit) or two shifts (HBM regime:
+          // the shared-memory pipe's latency is on the warp's critical path, the ALU is idle)
+          const uint32_t mlo = a.alu_masks ? bloom_pattern((h[i] >> 2) & 1023u)
+                                           : *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pattern) + (h[i] & 0xFFCu));
           const uint32_t mhi = __funnelshift_l(mlo, mlo, h[i] >> 12);
           const unsigned b = __ballot_sync(0xffffffffu, ((~bw[i].x & mlo) | (~bw[i].y & mhi)) == 0u);
           if ((int)lane == ib + i) mask = b;
@@ -298,6 +309,10 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
       // covered when the offset after the table lies beyond the tile's last base (offsets past the last target repeat
       // the total, which is beyond every position)
       gt_ok = (uint64_t)gt_o2 > w0 * 32ull + (uint64_t)(32 * kWarpTileWords - 1);
+      gb0 = __shfl_sync(0xffffffffu, gt_o0, 0);
+      gb1 = __shfl_sync(0xffffffffu, gt_o0, 1);
+      gb2 = __shfl_sync(0xffffffffu, gt_o0, 2);
+      gb3 = __shfl_sync(0xffffffffu, gt_o0, 3);
       n_pass += cnt;
       uint32_t at = incl - cnt;
       uint32_t m = mask;

@@ -152,7 +152,8 @@ class BlockSpec:
     genes_per_block: int
     gene_len: int
     rev: bool = True
-    period: int = 0           # > 0: tandem-repeat targets with units of 1..period bases (S4)
+    period: int = 0           # > 0: tandem-repeat targets with units of period_min..period bases (S4)
+    period_min: int = 1
     target_sub256: int = 0    # substitutions inside tandem-repeat targets
 
     @property
@@ -229,7 +230,7 @@ def generate_blocks(spec: BlockSpec, blocks=None, reads_out: np.ndarray = None, 
         else:
             tv = np.empty(tbytes, dtype=np.uint8)
         if want_targets or want_reads:
-            lib.msc_gen_targets(spec.seed, b, spec.genes_per_block, spec.gene_len, int(spec.rev), spec.period,
+            lib.msc_gen_targets(spec.seed, b, spec.genes_per_block, spec.gene_len, int(spec.rev), spec.period | (spec.period_min << 8) if spec.period else 0,
                                 spec.target_sub256, tv.ctypes.data)
         if want_reads:
             rv = reads[i * rbytes:(i + 1) * rbytes]

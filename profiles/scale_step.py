@@ -25,6 +25,7 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--window-width", type=int, default=0)
 ap.add_argument("--max-matches", type=int, default=0)
 ap.add_argument("--trace", action="store_true")
+ap.add_argument("--bloom-bits", type=int, default=0, help="Bloom bits per key (0 = the library's own sizing)")
 args = ap.parse_args()
 spec, cfgd, w = bench.pick_workload(args)
 t0 = time.time()
@@ -33,7 +34,7 @@ gen_s = time.time() - t0
 ro = np.arange(spec.n_reads + 1, dtype=np.uint64) * np.uint64(spec.read_len)
 to = np.arange(spec.n_targets + 1, dtype=np.uint64) * np.uint64(spec.gene_len)
 cfg = Config(**cfgd).apply_defaults()
-with HotPath(cfg, device=0, keep_ascii=True) as hp:
+with HotPath(cfg, device=0, keep_ascii=True, bloom_bits_per_key=args.bloom_bits) as hp:
     hp.set_reads((reads, ro))
     hp.set_targets((targets, to))
     hp.run()                       # sizes the bounded buffers
@@ -48,4 +49,4 @@ K = max(1, args.steps)
 print(json.dumps({"workload": bench.workload_name(spec, cfgd, w), "gen_s": round(gen_s, 2), "ms_per_step": step_ms,
                   "stage_ms": {k: st[k] / K for k in st if k.startswith("ms_")},
                   "counts": {k: st[k] for k in ("n_reads", "n_keys", "table_slots", "bloom_bytes", "target_bases", "n_candidates",
-                                                "n_pairs", "n_pass", "n_matches_pre", "n_matches")}}))
+                                                "n_pairs", "n_pass", "n_matches_pre", "n_matches", "bloom_pass")}}))
