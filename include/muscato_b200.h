@@ -75,7 +75,8 @@ typedef struct msc_stats {
   uint64_t kernel_launches;           /* kernels launched by this library since msc_reset_stats */
   float ms_pack_reads, ms_build, ms_pack_targets, ms_scan, ms_expand, ms_confirm, ms_combine;
   float ms_scan_kernel;               /* the scan kernel alone (CUDA events on the launch stream) */
-  float reserved_f[8];                /* [0] positions that passed the Bloom front, [1] ms of msc_prep_reads on the device */
+  float reserved_f[8];                /* [0] positions that passed the Bloom front, [1] ms of msc_prep_reads on the device,
+                                         [2] exact front: launches of the scan per step (slices of the 4^W-bit map), 0 = Bloom front */
 } msc_stats;
 
 typedef struct msc_ctx msc_ctx;

@@ -64,6 +64,7 @@ class msc_stats(C.Structure):
         d = {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved_f"}
         d["bloom_pass"] = float(self.reserved_f[0])
         d["ms_prep"] = float(self.reserved_f[1])  # device time of msc_prep_reads (sort + collapse), H2D excluded
+        d["front_passes"] = int(self.reserved_f[2])  # exact front: scan launches per step; 0 = Bloom front
         return d
 
 

@@ -28,6 +28,7 @@
 #include "prefix.cuh"
 #include "readprep.cuh"
 #include "scan.cuh"
+#include "scan_direct.cuh"
 
 using namespace msc;
 
@@ -188,6 +189,14 @@ struct msc_ctx {
   // (every record is one more stream operation between two kernels)
   bool stage_events = true;
   bool pdl = true;  // MSC_PDL=0: plain stream-ordered launches
+  bool pdl_always = false;  // MSC_PDL=2
+  // Programmatic dependent launch hides ~1 us per kernel boundary -- 20 us of a 0.6 ms step on the small workload --
+  // but was measured to COST 7.6 ms per step at configs[2] size (key-table build 47.2 -> 39.6 ms without it: the
+  // early-launched CTAs of the next kernel take the places of the running kernel's later waves), so it is used only
+  // where launch latency matters.
+  bool pdl_on() const {
+    return pdl && (pdl_always || (n_reads * (uint64_t)std::max(1, win.nwin) <= (1ull << 24) && n_bases <= (1ull << 29)));
+  }
   bool trace = false;
   std::vector<std::pair<const char*, cudaEvent_t>> trace_ev;
   size_t trace_used = 0;
@@ -347,7 +356,7 @@ void add_combine_fills(msc_ctx* ctx, Filler& f) {
 int enqueue_fill(msc_ctx* ctx, const Filler& f) {
   if (f.overflow) return ctx->fail(MSC_ERR_STATE, "internal: more than %d fill jobs in one prologue", kMaxFillJobs);
   if (f.job.n == 0) return MSC_OK;
-  launch_k(ctx->pdl, fill_buffers_kernel, (unsigned)ctx->sm_count * 8, 256, 0, ctx->stream, f.job);
+  launch_k(ctx->pdl_on(), fill_buffers_kernel, (unsigned)ctx->sm_count * 8, 256, 0, ctx->stream, f.job);
   LAUNCH_CHECK();
   return MSC_OK;
 }
@@ -412,7 +421,7 @@ int enqueue_build_reads(msc_ctx* ctx) {
   if (U) {
     const int rpb = std::max(1, 256 / S);  // whole reads per block
     const size_t smem = (size_t)rpb * (size_t)ctx->win.MRL + 64;
-    launch_k(ctx->pdl, pack_reads_kernel, grid_for(U, rpb), 256, smem, ctx->stream, 
+    launch_k(ctx->pdl_on(), pack_reads_kernel, grid_for(U, rpb), 256, smem, ctx->stream, 
         ctx->rd_ascii.as<uint8_t>(), ctx->rd_offs.as<uint64_t>(), U, S, rpb, ctx->rd_words.as<uint64_t>(),
         ctx->rd_x.as<uint64_t>(), ctx->len_flags.as<uint32_t>());
     LAUNCH_CHECK();
@@ -442,27 +451,27 @@ int enqueue_build_reads(msc_ctx* ctx) {
     a.geom = ctx->geom;
     const unsigned g8 = (unsigned)ctx->sm_count * 8;
     const uint64_t n_items = U * (uint64_t)ctx->win.nwin;
-    launch_k(ctx->pdl, table_clear_kernel, (unsigned)std::min<uint64_t>(grid_for(ctx->tgeo.n_buckets * 4, 256), (uint64_t)ctx->sm_count * 32),
+    launch_k(ctx->pdl_on(), table_clear_kernel, (unsigned)std::min<uint64_t>(grid_for(ctx->tgeo.n_buckets * 4, 256), (uint64_t)ctx->sm_count * 32),
              256, 0, ctx->stream, ctx->tab.as<uint8_t>(), ctx->tgeo.n_buckets);
     LAUNCH_CHECK();
-    launch_k(ctx->pdl, build_windows_kernel, (unsigned)std::min<uint64_t>(grid_for(U, 256), g8), 256, 0, ctx->stream, ctx->win, a);
+    launch_k(ctx->pdl_on(), build_windows_kernel, (unsigned)std::min<uint64_t>(grid_for(U, 256), g8), 256, 0, ctx->stream, ctx->win, a);
     LAUNCH_CHECK();
-    launch_k(ctx->pdl, build_offsets_kernel, 1, kMaxParts, 0, ctx->stream, ctx->part_count.as<unsigned int>(), (int)ctx->tgeo.n_parts);
+    launch_k(ctx->pdl_on(), build_offsets_kernel, 1, kMaxParts, 0, ctx->stream, ctx->part_count.as<unsigned int>(), (int)ctx->tgeo.n_parts);
     LAUNCH_CHECK();
     if (!ctx->scatter_attr_set) {
       CK(cudaFuncSetAttribute((const void*)build_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
       ctx->scatter_attr_set = true;
     }
-    launch_k(ctx->pdl, build_scatter_kernel, (unsigned)std::min<uint64_t>(grid_for(n_items, kStageKeys), (uint64_t)ctx->sm_count * 2),
+    launch_k(ctx->pdl_on(), build_scatter_kernel, (unsigned)std::min<uint64_t>(grid_for(n_items, kStageKeys), (uint64_t)ctx->sm_count * 2),
              kScatterThreads, sizeof(ScatterSmem), ctx->stream, ctx->win, a);
     LAUNCH_CHECK();
-    launch_k(ctx->pdl, build_insert_kernel, (unsigned)std::min<uint64_t>(grid_for(n_items, 256), g8), 256, 0, ctx->stream, a);
+    launch_k(ctx->pdl_on(), build_insert_kernel, (unsigned)std::min<uint64_t>(grid_for(n_items, 256), g8), 256, 0, ctx->stream, a);
     LAUNCH_CHECK();
-    launch_k(ctx->pdl, build_dup_count_kernel, g8, 256, 0, ctx->stream, a);
+    launch_k(ctx->pdl_on(), build_dup_count_kernel, g8, 256, 0, ctx->stream, a);
     LAUNCH_CHECK();
-    launch_k(ctx->pdl, build_dup_alloc_kernel, g8, 256, 0, ctx->stream, a);
+    launch_k(ctx->pdl_on(), build_dup_alloc_kernel, g8, 256, 0, ctx->stream, a);
     LAUNCH_CHECK();
-    launch_k(ctx->pdl, build_dup_fill_kernel, g8, 256, 0, ctx->stream, a);
+    launch_k(ctx->pdl_on(), build_dup_fill_kernel, g8, 256, 0, ctx->stream, a);
     LAUNCH_CHECK();
   }
   if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_BUILD1], ctx->stream));
@@ -494,7 +503,7 @@ int enqueue_pack_targets(msc_ctx* ctx) {
     RC(enqueue_fill(ctx, f));
   }
   ctx->pro.targets = false;
-  launch_k(ctx->pdl, pack_targets_kernel, grid_for(ctx->n_words_alloc, 256), 256, 0, ctx->stream, 
+  launch_k(ctx->pdl_on(), pack_targets_kernel, grid_for(ctx->n_words_alloc, 256), 256, 0, ctx->stream, 
       ctx->tg_ascii.as<uint8_t>(), ctx->n_bases, ctx->tg_words.as<uint64_t>(), ctx->n_words_alloc,
       ctx->tg_x.as<uint64_t>(), ctx->xsum.as<uint32_t>(), ctx->ctr(C_TGX));
   LAUNCH_CHECK();
@@ -536,17 +545,19 @@ void (*pick_scan_wn(int wn))(const ScanArgs) {
   }
 }
 // W <= 16: 32-bit keys; W <= 32: one 64-bit key word; wider: two key words
-void (*pick_scan_kernel(int W, int wn))(const ScanArgs) {
+void (*pick_scan_kernel(int W, int wn, bool direct = false))(const ScanArgs) {
+  if (direct) return scan_direct_kernel;  // exact front (W <= 15), scan_direct.cuh
   return W <= 16 ? pick_scan_wn<0>(wn) : W <= 32 ? pick_scan_wn<1>(wn) : pick_scan_wn<2>(wn);
 }
 
 int enqueue_scan(msc_ctx* ctx) {
   if (ctx->cand.cap == 0) RC(reserve_cand(ctx, std::max<uint64_t>(1u << 20, ctx->n_bases / 16)));
-  void (*scan_fn)(const ScanArgs) = pick_scan_kernel(ctx->win.W, ctx->geom.wn);
+  void (*scan_fn)(const ScanArgs) = pick_scan_kernel(ctx->win.W, ctx->geom.wn, ctx->geom.direct != 0);
+  const size_t scan_smem = ctx->geom.direct ? sizeof(ScanDirectSmem) : sizeof(ScanSmem);
   if (ctx->scan_grid == 0 || ctx->scan_fn_sized != (const void*)scan_fn) {
     int blocks_per_sm = 0;
-    CK(cudaFuncSetAttribute((const void*)scan_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_fn, kScanBlock, sizeof(ScanSmem)));
+    CK(cudaFuncSetAttribute((const void*)scan_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_fn, kScanBlock, scan_smem));
     ctx->scan_grid = ctx->sm_count * std::max(1, blocks_per_sm);
     ctx->scan_fn_sized = (const void*)scan_fn;
   }
@@ -584,9 +595,19 @@ int enqueue_scan(msc_ctx* ctx) {
     if (const char* e = getenv("MSC_SCAN_ALU_MASKS")) a.alu_masks = atoi(e) != 0;
     a.prefetch = 0;  // measured slower at S2 (72 vs 60 ms): the memory system is saturated, more requests in flight only add queueing
     if (const char* e = getenv("MSC_SCAN_PREFETCH")) a.prefetch = atoi(e) != 0;
+    // table beyond the L2: its lines and the candidate records are touched once (evict-first), which leaves the L2 to
+    // the front's current slice
+    a.stream_tab = ctx->tgeo.n_buckets * (uint64_t)kBucketBytes > (64ull << 20) ? 1 : 0;
+    if (const char* e = getenv("MSC_SCAN_STREAM_TAB")) a.stream_tab = atoi(e) != 0;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ctx->n_tiles, (uint64_t)ctx->scan_grid));
-    launch_k(ctx->pdl, scan_fn, grid, kScanBlock, sizeof(ScanSmem), ctx->stream, a);
-    LAUNCH_CHECK();
+    // exact front: one launch per slice of the bitmap (every launch walks the whole database and tests the positions
+    // whose bit lies in its slice); the Bloom front is one launch
+    const int n_pass = ctx->geom.direct ? 1 << ctx->geom.lg_pass : 1;
+    for (int q = 0; q < n_pass; q++) {
+      a.pass = q;
+      launch_k(ctx->pdl_on(), scan_fn, grid, kScanBlock, scan_smem, ctx->stream, a);
+      LAUNCH_CHECK();
+    }
   }
   CK(cudaEventRecord(ctx->ev[EV_SCAN1], ctx->stream));
   return MSC_OK;
@@ -601,7 +622,7 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   const unsigned pgrid = (unsigned)ctx->sm_count * 8;
   RC(enqueue_exclusive_scan<uint64_t>(ctx, ctx->sizes.as<uint32_t>(), ctx->ctr(C_NCAND), ccap, ctx->pstart.as<uint64_t>(),
                                       true, ctx->ctr(C_NPAIRS)));
-  launch_k(ctx->pdl, pair_block_starts_kernel, pgrid, 256, 0, ctx->stream, ctx->pstart.as<uint64_t>(), ctx->ctr(C_NCAND), ccap,
+  launch_k(ctx->pdl_on(), pair_block_starts_kernel, pgrid, 256, 0, ctx->stream, ctx->pstart.as<uint64_t>(), ctx->ctr(C_NCAND), ccap,
                                                            ctx->ctr(C_NPAIRS), ctx->block_cap(),
                                                            ctx->block_first.as<uint32_t>());
   LAUNCH_CHECK();
@@ -654,9 +675,9 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
     ctx->confirm_grid = ctx->sm_count * std::max(1, per_sm);
   }
   const unsigned cgrid = (unsigned)ctx->confirm_grid;
-  if (mode == 0) launch_k(ctx->pdl, confirm_pairs_kernel<0>, cgrid, 256, 0, ctx->stream, ctx->win, a);
-  else if (mode == 1) launch_k(ctx->pdl, confirm_pairs_kernel<1>, cgrid, 256, 0, ctx->stream, ctx->win, a);
-  else launch_k(ctx->pdl, confirm_pairs_kernel<2>, cgrid, 256, 0, ctx->stream, ctx->win, a);
+  if (mode == 0) launch_k(ctx->pdl_on(), confirm_pairs_kernel<0>, cgrid, 256, 0, ctx->stream, ctx->win, a);
+  else if (mode == 1) launch_k(ctx->pdl_on(), confirm_pairs_kernel<1>, cgrid, 256, 0, ctx->stream, ctx->win, a);
+  else launch_k(ctx->pdl_on(), confirm_pairs_kernel<2>, cgrid, 256, 0, ctx->stream, ctx->win, a);
   LAUNCH_CHECK();
   if (mode == 0) {
     // MaxMatches pre-check (cmd/muscato_confirm/main.go:233-242, :424-448): truncation can only
@@ -664,7 +685,7 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
     const unsigned long long thr = ctx->n_shards > 1 ? (unsigned long long)ctx->cfg.max_matches / (unsigned long long)ctx->n_shards
                                                      : (unsigned long long)ctx->cfg.max_matches;
     // exact per-slot counts once they are kept, else the small hashed counters (upper bounds)
-    launch_k(ctx->pdl, overflow_count_kernel, (unsigned)ctx->sm_count * 8, 256, 0, ctx->stream,
+    launch_k(ctx->pdl_on(), overflow_count_kernel, (unsigned)ctx->sm_count * 8, 256, 0, ctx->stream,
         ctx->exact_counts ? ctx->pass_cnt.as<uint32_t>() : ctx->pass_small.as<uint32_t>(),
         ctx->exact_counts ? ctx->n_slots : (1ull << ctx->lg_small), thr, ctx->ctr(C_NPASS), ctx->ctr(C_NOVER),
         ctx->n_shards > 1 ? ctx->best.as<uint32_t>() + ctx->n_reads : (uint32_t*)nullptr);
@@ -691,27 +712,27 @@ int enqueue_combine(msc_ctx* ctx) {
   ctx->pro.combine = false;
   const unsigned g = (unsigned)ctx->sm_count * 8;
   if (ctx->n_shards > 1) {  // best[n_reads] after the MIN all-reduce: did ANY shard see a MaxMatches candidate group?
-    launch_k(ctx->pdl, shard_flag_kernel, 1, 32, 0, ctx->stream, ctx->best.as<uint32_t>() + ctx->n_reads, ctx->ctr(C_SHARDOVER));
+    launch_k(ctx->pdl_on(), shard_flag_kernel, 1, 32, 0, ctx->stream, ctx->best.as<uint32_t>() + ctx->n_reads, ctx->ctr(C_SHARDOVER));
     LAUNCH_CHECK();
   }
-  launch_k(ctx->pdl, combine_count_kernel, g, 256, 0, ctx->stream, ctx->match_pre.as<uint4>(), ctx->ctr(C_NMATCH), mcap,
+  launch_k(ctx->pdl_on(), combine_count_kernel, g, 256, 0, ctx->stream, ctx->match_pre.as<uint4>(), ctx->ctr(C_NMATCH), mcap,
                                                    ctx->best.as<uint32_t>(), (uint32_t)ctx->cfg.mmtol,
                                                    ctx->rcount.as<uint32_t>());
   LAUNCH_CHECK();
   RC(enqueue_exclusive_scan<uint32_t>(ctx, ctx->rcount.as<uint32_t>(), nullptr, U, ctx->rstart.as<uint32_t>(), true,
                                       ctx->ctr(C_NOUT)));
-  launch_k(ctx->pdl, combine_scatter_kernel, g, 256, 0, ctx->stream, ctx->match_pre.as<uint4>(), ctx->ctr(C_NMATCH), mcap,
+  launch_k(ctx->pdl_on(), combine_scatter_kernel, g, 256, 0, ctx->stream, ctx->match_pre.as<uint4>(), ctx->ctr(C_NMATCH), mcap,
                                                      ctx->best.as<uint32_t>(), (uint32_t)ctx->cfg.mmtol,
                                                      ctx->rstart.as<uint32_t>(), ctx->rfill.as<uint32_t>(),
                                                      ctx->match_out.as<uint4>());
   LAUNCH_CHECK();
   if (U) {
     // deterministic (gene, pos) order inside every read group; match_pre is dead and serves as scratch
-    launch_k(ctx->pdl, segment_sort_short_kernel, grid_for(U, 256), 256, 0, ctx->stream, 
+    launch_k(ctx->pdl_on(), segment_sort_short_kernel, grid_for(U, 256), 256, 0, ctx->stream, 
         ctx->match_out.as<uint4>(), ctx->rstart.as<uint32_t>(), U, ctx->long_list.as<uint32_t>(), ctx->ctr(C_NLONG),
         ctx->mid_list.as<uint32_t>(), ctx->ctr(C_PAD1));
     LAUNCH_CHECK();
-    launch_k(ctx->pdl, segment_rank_sort_kernel, g, kRankThreads, 0, ctx->stream, ctx->match_out.as<uint4>(), ctx->match_pre.as<uint4>(),
+    launch_k(ctx->pdl_on(), segment_rank_sort_kernel, g, kRankThreads, 0, ctx->stream, ctx->match_out.as<uint4>(), ctx->match_pre.as<uint4>(),
                                                          ctx->rstart.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
                                                          ctx->ctr(C_NLONG), ctx->mid_list.as<uint32_t>(), ctx->ctr(C_PAD1));
     LAUNCH_CHECK();
@@ -738,6 +759,7 @@ int finish_scan(msc_ctx* ctx) {
   ctx->st.n_candidates = ctx->n_cand;
   ctx->st.positions_probed = ctx->n_bases;
   ctx->st.reserved_f[0] = (float)ctx->h_counters[C_BLOOMPASS];
+  ctx->st.reserved_f[2] = ctx->geom.direct ? (float)(1 << ctx->geom.lg_pass) : 0.f;
   ctx->have_cand = true;
   ctx->have_confirm = ctx->have_combine = false;
   return MSC_OK;
@@ -959,7 +981,10 @@ msc_ctx* msc_create(const msc_config* config, char* errbuf, uint64_t errlen) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->trace = getenv("MSC_TRACE") && atoi(getenv("MSC_TRACE")) > 0;
   if (const char* e = getenv("MSC_STAGE_EVENTS")) ctx->stage_events = atoi(e) != 0;
-  if (const char* e = getenv("MSC_PDL")) ctx->pdl = atoi(e) != 0;
+  if (const char* e = getenv("MSC_PDL")) {
+    ctx->pdl = atoi(e) != 0;
+    ctx->pdl_always = atoi(e) == 2;
+  }
   ctx->win.nwin = c.n_windows;
   ctx->win.W = c.window_width;
   ctx->win.MRL = c.max_read_length;
@@ -1097,6 +1122,25 @@ static int reads_reserve(msc_ctx* ctx, uint64_t n_reads, uint64_t total) {
     if (lg > lg_l2) lg = std::max(lg_l2, ceil_log2((kmax * 12ull + 63) / 64));
     ctx->lg_bloom = lg;
   }
+  // Exact front (common.cuh, BloomGeom::direct): when one bit per POSSIBLE key (4^W bits) is no larger than the Bloom
+  // words would be, the front is that bitmap -- no hash, no false positives -- and the scan tests it slice by slice
+  // (<= 32 MB per pass, L2-resident).  W <= 15: 128 MB at most.  MSC_FRONT_DIRECT=0/1 forces the choice,
+  // MSC_FRONT_PASS_MB the slice size (tuning only: results do not depend on the front).
+  ctx->geom.direct = 0;
+  ctx->geom.lg_pass = 0;
+  if (ctx->win.W <= 15) {
+    const int lg_direct = std::max(10, 2 * ctx->win.W - 6);
+    bool direct = lg_direct <= ctx->lg_bloom;
+    if (const char* e = getenv("MSC_FRONT_DIRECT")) direct = atoi(e) != 0;
+    if (direct) {
+      int pass_mb = 32;
+      if (const char* e = getenv("MSC_FRONT_PASS_MB")) pass_mb = std::max(1, atoi(e));
+      const int lg_pass_words = ceil_log2(((uint64_t)pass_mb << 20) / 8);
+      ctx->geom.direct = 1;
+      ctx->geom.lg_pass = std::max(0, lg_direct - lg_pass_words);
+      ctx->lg_bloom = lg_direct;
+    }
+  }
   // Minimiser geometry of the Bloom addressing (common.cuh): m-mers of the key's first P bases.
   // 4^m is kept >= 4x the number of sectors so that the minimisers spread over all of them, and
   // at most 8 m-mers compete (ALU cost per probed position).  MSC_MINIMIZER_M overrides m.
@@ -1196,7 +1240,7 @@ int msc_set_reads_device(msc_ctx* ctx, const uint8_t* d_ascii, const uint64_t* d
     RC(enqueue_fill(ctx, f));
   }
   if (n_reads) {
-    launch_k(ctx->pdl, validate_read_offsets_kernel, grid_for(n_reads, 256), 256, 0, ctx->stream, 
+    launch_k(ctx->pdl_on(), validate_read_offsets_kernel, grid_for(n_reads, 256), 256, 0, ctx->stream, 
         ctx->rd_offs.as<uint64_t>(), n_reads, total_bytes, (uint64_t)ctx->win.MRL, ctx->ctr(C_PAD1));
     LAUNCH_CHECK();
   }
@@ -1286,7 +1330,7 @@ int msc_prep_reads(msc_ctx* ctx, const uint8_t* raw_ascii, const uint64_t* raw_o
   uint32_t* cur = idx_a.as<uint32_t>();
   uint32_t* nxt = idx_b.as<uint32_t>();
   if (n) {
-    launch_k(ctx->pdl, prep_encode_kernel, grid_for(n, 256), 256, 0, ctx->stream, d_raw.as<uint8_t>(), d_offs.as<uint64_t>(), n, MRL,
+    launch_k(ctx->pdl_on(), prep_encode_kernel, grid_for(n, 256), 256, 0, ctx->stream, d_raw.as<uint8_t>(), d_offs.as<uint64_t>(), n, MRL,
                                                                   (int)min_read_length, n_planes, planes.as<uint8_t>(),
                                                                   ctx->prep.key64.as<uint64_t>(), keep.as<uint32_t>(), ctx->ctr(C_PREP_KEPT));
     LAUNCH_CHECK();
@@ -1299,11 +1343,11 @@ int msc_prep_reads(msc_ctx* ctx, const uint8_t* raw_ascii, const uint64_t* raw_o
     auto radix_passes = [&](int first_plane_excl_hi) -> int {  // planes first_plane_excl_hi-1 .. 0
       for (int b = first_plane_excl_hi - 1; b >= 0; b--) {
         const uint8_t* plane = planes.as<uint8_t>() + (size_t)b * n;
-        launch_k(ctx->pdl, radix_hist_kernel, n_chunks, kRadixThreads, 0, ctx->stream, cur, plane, n, n_chunks, hist.as<uint32_t>());
+        launch_k(ctx->pdl_on(), radix_hist_kernel, n_chunks, kRadixThreads, 0, ctx->stream, cur, plane, n, n_chunks, hist.as<uint32_t>());
         LAUNCH_CHECK();
         RC(enqueue_exclusive_scan<uint32_t>(ctx, hist.as<uint32_t>(), nullptr, (uint64_t)256 * n_chunks, hoff.as<uint32_t>(),
                                             false, ctx->ctr(C_PAD3)));
-        launch_k(ctx->pdl, radix_scatter_kernel, n_chunks, kRadixThreads, 0, ctx->stream, cur, plane, n, n_chunks, hoff.as<uint32_t>(), nxt);
+        launch_k(ctx->pdl_on(), radix_scatter_kernel, n_chunks, kRadixThreads, 0, ctx->stream, cur, plane, n, n_chunks, hoff.as<uint32_t>(), nxt);
         LAUNCH_CHECK();
         std::swap(cur, nxt);
       }
@@ -1311,11 +1355,11 @@ int msc_prep_reads(msc_ctx* ctx, const uint8_t* raw_ascii, const uint64_t* raw_o
     };
     bool full_sort = n_planes <= kPrePlanes || (getenv("MSC_PREP_FULL_SORT") && atoi(getenv("MSC_PREP_FULL_SORT")) > 0);
     for (int attempt = 0; attempt < 2; attempt++) {
-      launch_k(ctx->pdl, iota_kernel, grid_for(n, 256), 256, 0, ctx->stream, cur, n);
+      launch_k(ctx->pdl_on(), iota_kernel, grid_for(n, 256), 256, 0, ctx->stream, cur, n);
       LAUNCH_CHECK();
       PRC(radix_passes(full_sort ? n_planes : kPrePlanes));
       if (full_sort) break;
-      launch_k(ctx->pdl, prep_tiefix_kernel, grid_for(n, 256), 256, 0, ctx->stream, cur, planes.as<uint8_t>(),
+      launch_k(ctx->pdl_on(), prep_tiefix_kernel, grid_for(n, 256), 256, 0, ctx->stream, cur, planes.as<uint8_t>(),
                ctx->prep.key64.as<uint64_t>(), n,
                ctx->ctr(C_PREP_KEPT), kPrePlanes, n_planes, ctx->ctr(C_PREP_TIE));
       LAUNCH_CHECK();
@@ -1323,13 +1367,13 @@ int msc_prep_reads(msc_ctx* ctx, const uint8_t* raw_ascii, const uint64_t* raw_o
       if (ctx->h_counters[C_PREP_TIE] == 0) break;
       full_sort = true;
     }
-    launch_k(ctx->pdl, prep_heads_kernel, grid_for(n, 256), 256, 0, ctx->stream, cur, planes.as<uint8_t>(),
+    launch_k(ctx->pdl_on(), prep_heads_kernel, grid_for(n, 256), 256, 0, ctx->stream, cur, planes.as<uint8_t>(),
              ctx->prep.key64.as<uint64_t>(), n, ctx->ctr(C_PREP_KEPT), n_planes,
                                                                  head.as<uint32_t>());
     LAUNCH_CHECK();
     PRC(enqueue_exclusive_scan<uint32_t>(ctx, head.as<uint32_t>(), ctx->ctr(C_PREP_KEPT), n, head_scan.as<uint32_t>(), true,
                                          ctx->ctr(C_PREP_UNIQ)));
-    launch_k(ctx->pdl, prep_groups_kernel, grid_for(n, 256), 256, 0, ctx->stream, cur, head.as<uint32_t>(), head_scan.as<uint32_t>(),
+    launch_k(ctx->pdl_on(), prep_groups_kernel, grid_for(n, 256), 256, 0, ctx->stream, cur, head.as<uint32_t>(), head_scan.as<uint32_t>(),
                                                                   ctx->ctr(C_PREP_KEPT), d_offs.as<uint64_t>(), MRL,
                                                                   ctx->ctr(C_PREP_UNIQ), ctx->prep_gstart.as<uint32_t>(),
                                                                   ulen.as<uint32_t>());
@@ -1346,7 +1390,7 @@ int msc_prep_reads(msc_ctx* ctx, const uint8_t* raw_ascii, const uint64_t* raw_o
   if (!n || !ctx->prep_kept) PCK(cudaMemsetAsync(ctx->prep_gstart.p, 0, 2 * sizeof(uint32_t), ctx->stream));
   PRC(reads_reserve(ctx, U, ctx->prep_bytes));
   if (U) {
-    launch_k(ctx->pdl, prep_gather_kernel, grid_for(U * 32, 256), 256, 0, ctx->stream, d_raw.as<uint8_t>(), d_offs.as<uint64_t>(), ctx->prep_perm.as<uint32_t>(),
+    launch_k(ctx->pdl_on(), prep_gather_kernel, grid_for(U * 32, 256), 256, 0, ctx->stream, d_raw.as<uint8_t>(), d_offs.as<uint64_t>(), ctx->prep_perm.as<uint32_t>(),
                                                                      ctx->prep_gstart.as<uint32_t>(), uoffs.as<uint64_t>(),
                                                                      ctx->ctr(C_PREP_UNIQ), ctx->rd_ascii.as<uint8_t>());
     LAUNCH_CHECK();
@@ -1510,7 +1554,7 @@ int msc_set_targets_packed(msc_ctx* ctx, const uint64_t* words, const uint64_t* 
     f.add(ctx->ctr(C_TGX), 2 * sizeof(unsigned long long));
     RC(enqueue_fill(ctx, f));
   }
-  launch_k(ctx->pdl, packed_targets_finish_kernel, grid_for(ctx->n_words_alloc, 256), 256, 0, ctx->stream, ctx->tg_words.as<uint64_t>(),
+  launch_k(ctx->pdl_on(), packed_targets_finish_kernel, grid_for(ctx->n_words_alloc, 256), 256, 0, ctx->stream, ctx->tg_words.as<uint64_t>(),
            ctx->tg_x.as<uint64_t>(), ctx->n_bases, ctx->n_words_alloc, ctx->xsum.as<uint32_t>(), ctx->ctr(C_TGX));
   LAUNCH_CHECK();
   CK(cudaEventRecord(ctx->ev_tg_free, ctx->stream));
@@ -1691,12 +1735,12 @@ int msc_fetch_nonmatch(msc_ctx* ctx, uint32_t* ids, uint64_t capacity, uint64_t*
   CK(ctx->nm_flag.reserve((U + 4) * sizeof(uint32_t)));
   CK(ctx->nm_pos.reserve((U + 4) * sizeof(uint32_t)));
   CK(ctx->nm_list.reserve((U + 4) * sizeof(uint32_t)));
-  launch_k(ctx->pdl, nonmatch_flag_kernel, grid_for(U, 256), 256, 0, ctx->stream, ctx->best.as<uint32_t>(), U, MSC_NO_MATCH,
+  launch_k(ctx->pdl_on(), nonmatch_flag_kernel, grid_for(U, 256), 256, 0, ctx->stream, ctx->best.as<uint32_t>(), U, MSC_NO_MATCH,
                                                                    ctx->nm_flag.as<uint32_t>());
   LAUNCH_CHECK();
   RC(enqueue_exclusive_scan<uint32_t>(ctx, ctx->nm_flag.as<uint32_t>(), nullptr, U, ctx->nm_pos.as<uint32_t>(), true,
                                       ctx->ctr(C_PAD2)));
-  launch_k(ctx->pdl, nonmatch_scatter_kernel, grid_for(U, 256), 256, 0, ctx->stream, ctx->nm_flag.as<uint32_t>(), ctx->nm_pos.as<uint32_t>(), U,
+  launch_k(ctx->pdl_on(), nonmatch_scatter_kernel, grid_for(U, 256), 256, 0, ctx->stream, ctx->nm_flag.as<uint32_t>(), ctx->nm_pos.as<uint32_t>(), U,
                                                                       ctx->nm_list.as<uint32_t>());
   LAUNCH_CHECK();
   RC(sync_counters(ctx));

@@ -88,6 +88,13 @@ struct BloomGeom {
   int m;           // minimiser length in bases, 1..16
   int wn;          // m-mers per key that compete: P - m + 1, 1..8
   uint32_t xr;     // alphabet relabelling of the key's low 32 bits: 0x55555555 cut to W bases
+  // EXACT front (round 2): for W <= 15 and a key set so large that the Bloom words would take more room than one bit
+  // per POSSIBLE key (4^W bits: 128 MB at W = 15), the front is that bitmap -- bit x = the key itself, no hash, no
+  // false positives (a window with X sets/tests a hashed bit: false positives only).  The scan walks the database
+  // 2^lg_pass times; pass q tests only the positions whose bit lies in slice q of the bitmap (x >> (lg_words + 6 -
+  // lg_pass) == q), so the bits a pass touches (<= 32 MB) stay in the L2 while the table lines stream past them.
+  int direct;      // 1 = exact bitmap over the key space
+  int lg_pass;     // log2(passes of the scan), direct only
 };
 
 // Fingerprint-addressed variant (keys with X).
@@ -152,6 +159,14 @@ __host__ __device__ __forceinline__ uint32_t bloom_sector_rt(uint32_t prex, int 
 __host__ __device__ __forceinline__ void bloom_locate(uint64_t key, uint64_t xm, uint64_t fp, int W,
                                                       const BloomGeom& g, uint64_t& widx, uint32_t& mlo,
                                                       uint32_t& mhi, uint64_t key1 = 0ull) {
+  if (g.direct) {
+    // bit index in [0, 2^(lg_words + 6)): the key (4^W <= 2^(lg_words + 6)), or a hash of the fingerprint for an X window
+    const uint64_t x = xm == 0 ? key : fp >> (64 - (g.lg_words + 6));
+    widx = x >> 6;
+    mlo = (x & 32u) ? 0u : 1u << (unsigned)(x & 31u);
+    mhi = (x & 32u) ? 1u << (unsigned)(x & 31u) : 0u;
+    return;
+  }
   if (xm == 0) {
     const uint32_t prex = (uint32_t)key ^ g.xr;
     const uint32_t h = W <= 16 ? bloom_hash32<true>(prex, 0u)
@@ -211,6 +226,42 @@ __device__ __forceinline__ uint64_t ldcg64(const void* p) {
   uint64_t v;
   asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+
+// L2 eviction priorities (createpolicy; SASS: the policy travels in the memory descriptor).  evict_last: the slice of
+// the exact front a scan pass keeps probing; evict_first: table lines and candidate records that are touched once.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint32_t ldg32_hint(const uint32_t* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+// 256-bit read-only load of a line that will not be needed again (LDG.E.NA.EFL2.256)
+__device__ __forceinline__ void ldg256_stream(const void* p, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+__device__ __forceinline__ uint4 ldg128_last_use(const uint4* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg128_hint(void* p, uint4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg64_hint(void* p, uint2 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg32_hint(void* p, uint32_t v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
 
 // Request a line into the L2 without a destination register.

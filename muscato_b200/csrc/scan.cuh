@@ -62,6 +62,8 @@ struct ScanArgs {
   int W;
   int alu_masks;          // 1 = Bloom bit masks by arithmetic instead of the shared-memory pattern table (MSC_SCAN_ALU_MASKS)
   int prefetch;           // 1 = request every queued position's bucket line into the L2 before the drain (MSC_SCAN_PREFETCH)
+  int pass;               // exact front (geom.direct): the slice of the bitmap this launch tests, 0 .. 2^lg_pass - 1
+  int stream_tab;         // 1 = table beyond the L2: bucket lines and candidate records carry the evict-first L2 policy
 };
 
 // Shared memory of one scan CTA (dynamic: 50 KB, above the 48 KB static limit).
@@ -70,6 +72,7 @@ struct ScanSmem {
   alignas(16) uint4 stage_rec[kScanWarps][kStageCap];  // the key group record of every staged candidate
   alignas(8) uint64_t bars[kScanWarps][2];
   uint2 stage[kScanWarps][kStageCap];  // found (slot, position) pairs, flushed when nearly full
+  uint32_t stage_g[kScanWarps][kStageCap];  // the target that holds each staged position
   uint16_t queue[kScanWarps][1024];
   uint32_t gtab[kScanWarps][kGeneTab + 4];  // tg_off[g0 .. g0 + kGeneTab] of the current tile (g0 = target of its first block)
   uint32_t pattern[1024];              // bloom_pattern(): the two low-half bits of a key
@@ -92,7 +95,8 @@ __device__ __forceinline__ uint64_t window_at(uint64_t lo, uint64_t hi, unsigned
 //            lane i re-derives the key of queued position i with two shuffles, looks it up in the
 //            exact table, and the warp appends the found (slot, position) pairs with ONE atomic.
 // KW: 0 = W <= 16 (the key arithmetic of phase 1 is 32 bit), 1 = W <= 32, 2 = wide window
-// (32 < W <= 64, two key words).  WN: number of competing m-mers.
+// (32 < W <= 64, two key words).  WN: number of competing m-mers.  (The exact front of BloomGeom::direct has its own
+// kernel, scan_direct.cuh.)
 template <int KW, int WN>
 __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel(const ScanArgs a) {
   pdl_enter();
@@ -121,6 +125,8 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
   const bool any_x = *a.targets_have_x != 0ull;
   constexpr bool K32 = KW == 0;
   constexpr bool WIDE = KW == 2;
+  const uint64_t pol_once = l2_policy_evict_first();
+  const bool stream_tab = a.stream_tab != 0;
   const uint64_t kmask = low_bases_mask(min(a.W, 32));
   const uint64_t kmask1 = WIDE ? low_bases_mask(a.W - 32) : 0ull;  // bases 32..W-1 of a wide window
   const uint32_t xr = a.geom.xr;
@@ -147,6 +153,7 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
   uint32_t n_st = 0;  // staged candidates of this warp (warp-uniform)
   // One global atomic per flush instead of one per drain round: same-address atomics serialise.
   uint4* st_rec = stage_rec[warp];
+  uint32_t* st_g = sm.stage_g[warp];
   // Flush: one global atomic reserves the run; every staged candidate is written as the pair kernel wants it --
   // (slot, position), its key group's size, and ONE 32-byte record (two uint4):
   //   (global position of the window, window start p inside its target, global end of the target, read record of item 0)
@@ -159,7 +166,7 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
   // only rolls inside one target, cmd/muscato_screen/main.go:319): size 0.
   uint32_t g0 = 0;     // target that holds the first base of the tile's first 2^kGeneBlockShift block
   bool gt_ok = false;  // gt[] covers the whole tile
-  uint32_t gb0 = 0, gb1 = 0, gb2 = 0, gb3 = 0;  // tg_off[g0 .. g0 + 3] (warp-uniform copies of gt[0..3])
+  uint32_t gb1 = 0, gb2 = 0, gb3 = 0;  // tg_off[g0 + 1 .. g0 + 3] (warp-uniform copies of gt[1..3])
   auto flush_stage = [&]() {
     unsigned long long out0 = 0;
     if (lane == 0) out0 = atomicAdd(a.n_cand, (unsigned long long)n_st);
@@ -168,37 +175,43 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
     for (uint32_t i = lane; i < n_st; i += 32) {
       const uint2 e = st[i];
       const uint4 rec = st_rec[i];
-      uint32_t g, goff, gend;
-      if (e.y < gb3) {
-        // the tile's first three targets, offsets in registers (a 1024-base tile rarely holds more starts)
-        const uint32_t c = (e.y >= gb1) + (e.y >= gb2);
-        g = g0 + c;
-        goff = c == 0 ? gb0 : (c == 1 ? gb1 : gb2);
-        gend = c == 0 ? gb1 : (c == 1 ? gb2 : gb3);
-      } else if (gt_ok) {
-        // number of offsets gt[1..kGeneTab] <= position (ascending): branch-free binary search in shared memory
-        uint32_t c = 0;
-#pragma unroll
-        for (int step = kGeneTab / 2; step >= 1; step >>= 1) c += (gt[c + step] <= e.y) ? step : 0;
-        g = g0 + c;
-        goff = gt[c];
-        gend = gt[c + 1];
-      } else {
-        const uint64_t g_lo = __ldg(a.blk2gene + (e.y >> kGeneBlockShift)), g_hi = __ldg(a.blk2gene + (e.y >> kGeneBlockShift) + 1);
-        g = (uint32_t)(upper_bound_dev<uint32_t>(a.tg_off, g_lo + 1, g_hi + 1, e.y) - 1);
-        goff = __ldg(a.tg_off + g);
-        gend = __ldg(a.tg_off + g + 1);
-      }
+      // the target was resolved when the candidate was staged (target_of below: the tile's slice of the offset table);
+      // its two offsets come through the L1 (neighbouring candidates share them)
+      const uint32_t g = st_g[i];
+      const uint32_t goff = __ldg(a.tg_off + g), gend = __ldg(a.tg_off + g + 1);
       const unsigned long long o = out0 + i;
       if (o < a.cand_cap) {
-        a.cand[o] = e;
-        a.cinfo[2 * o] = make_uint4(e.y, e.y - goff, gend, rec.y);
-        a.cinfo[2 * o + 1] = make_uint4(rec.x, rec.z, g, 0u);
-        a.sizes[o] = ((uint64_t)e.y + (uint64_t)a.W <= (uint64_t)gend) ? 1u + rec.w : 0u;
+        const uint32_t sz = ((uint64_t)e.y + (uint64_t)a.W <= (uint64_t)gend) ? 1u + rec.w : 0u;
+        if (stream_tab) {
+          // written once, read once by the expansion long after the L2 has turned over: first out
+          stg64_hint(a.cand + o, e, pol_once);
+          stg128_hint(a.cinfo + 2 * o, make_uint4(e.y, e.y - goff, gend, rec.y), pol_once);
+          stg128_hint(a.cinfo + 2 * o + 1, make_uint4(rec.x, rec.z, g, 0u), pol_once);
+          stg32_hint(a.sizes + o, sz, pol_once);
+        } else {
+          a.cand[o] = e;
+          a.cinfo[2 * o] = make_uint4(e.y, e.y - goff, gend, rec.y);
+          a.cinfo[2 * o + 1] = make_uint4(rec.x, rec.z, g, 0u);
+          a.sizes[o] = sz;
+        }
       }
     }
     __syncwarp();
     n_st = 0;
+  };
+  // Target that holds position `pos` of the current tile: the tile's first three targets from registers, its first
+  // kGeneTab from the warp's shared-memory slice of the offset table, anything beyond by a search in global memory.
+  auto target_of = [&](uint32_t pos) -> uint32_t {
+    if (pos < gb3) return g0 + (pos >= gb1) + (pos >= gb2);
+    if (gt_ok) {
+      // number of offsets gt[1..kGeneTab] <= position (ascending): branch-free binary search in shared memory
+      uint32_t c = 0;
+#pragma unroll
+      for (int step = kGeneTab / 2; step >= 1; step >>= 1) c += (gt[c + step] <= pos) ? step : 0;
+      return g0 + c;
+    }
+    const uint64_t g_lo = __ldg(a.blk2gene + (pos >> kGeneBlockShift)), g_hi = __ldg(a.blk2gene + (pos >> kGeneBlockShift) + 1);
+    return (uint32_t)(upper_bound_dev<uint32_t>(a.tg_off, g_lo + 1, g_hi + 1, pos) - 1);
   };
   uint32_t g0_next = w0 < w_end ? __ldg(a.blk2gene + ((w0 * 32ull) >> kGeneBlockShift)) : 0u;
   for (; w0 < w_end; w0 += kWarpTileWords) {
@@ -309,7 +322,6 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
       // covered when the offset after the table lies beyond the tile's last base (offsets past the last target repeat
       // the total, which is beyond every position)
       gt_ok = (uint64_t)gt_o2 > w0 * 32ull + (uint64_t)(32 * kWarpTileWords - 1);
-      gb0 = __shfl_sync(0xffffffffu, gt_o0, 0);
       gb1 = __shfl_sync(0xffffffffu, gt_o0, 1);
       gb2 = __shfl_sync(0xffffffffu, gt_o0, 2);
       gb3 = __shfl_sync(0xffffffffu, gt_o0, 3);
@@ -387,7 +399,10 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
 #pragma unroll
         for (int u = 0; u < kDrain; u++) {
           rr[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (r[u] < kBucketSlots) rr[u] = __ldg(reinterpret_cast<const uint4*>(bucket_ptr(a.tab, bk[u]) + kBucketRecOff) + r[u]);
+          if (r[u] < kBucketSlots) {
+            const uint4* rp = reinterpret_cast<const uint4*>(bucket_ptr(a.tab, bk[u]) + kBucketRecOff) + r[u];
+            rr[u] = stream_tab ? ldg128_last_use(rp, pol_once) : __ldg(rp);  // the line's last use: first out of the L2
+          }
         }
 #pragma unroll
         for (int u = 0; u < kDrain; u++) {
@@ -399,6 +414,7 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
               const uint32_t at = n_st + __popc(found & ((1u << lane) - 1u));
               st[at] = make_uint2((uint32_t)(bk[u] * kBucketSlots + (uint64_t)r[u]), (uint32_t)(wbase + e[u]));
               st_rec[at] = rr[u];
+              st_g[at] = target_of((uint32_t)(wbase + e[u]));
             }
             n_st += __popc(found);
             __syncwarp();
@@ -406,12 +422,12 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
           }
         }
       }
-      __syncwarp();
-      if (n_st) flush_stage();  // the stage never outlives its tile (gt[] is the tile's)
+      __syncwarp();  // (the stage outlives the tile: every entry carries its target)
     }
     __syncwarp();  // all lanes are done with tile[buf] before lane 0 lets the TMA engine refill it
     buf ^= 1;
   }
+  if (n_st) flush_stage();
   n_pass = __reduce_add_sync(0xffffffffu, n_pass);
   if (lane == 0 && n_pass) atomicAdd(a.n_bloom_pass, (unsigned long long)n_pass);
 }

@@ -159,9 +159,19 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_random_cases_vs_oracle(case, tmp_path, oracle_bin):
+# every case with the front the library picks; the W <= 15 ones also with the Bloom front forced and with the exact
+# front forced in 16 MB slices (W = 15: 8 passes of the scan over a 128 MB bitmap) -- the front never changes results
+FRONT_CASES = [(c, "auto") for c in CASES] + [(c, f) for c in CASES if c[1] <= 15 for f in ("bloom", "direct")]
+
+
+@pytest.mark.parametrize("case,front", FRONT_CASES, ids=[f"{c[0]}-{f}" for c, f in FRONT_CASES])
+def test_random_cases_vs_oracle(case, front, tmp_path, oracle_bin, monkeypatch):
     name, W, wins, mrl, pm, mind, mmtol, rlens, glen, sub, xr = case
+    if front == "bloom":
+        monkeypatch.setenv("MSC_FRONT_DIRECT", "0")
+    elif front == "direct":
+        monkeypatch.setenv("MSC_FRONT_DIRECT", "1")
+        monkeypatch.setenv("MSC_FRONT_PASS_MB", "16")
     rng = np.random.default_rng(zlib.crc32(name.encode()))
     alphabet = b"AC" if name == "w7_lowcomplex" else b"ACG" if "lowcomplex" in name else b"ACGT"
     n_genes = 30
