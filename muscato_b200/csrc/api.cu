@@ -396,6 +396,10 @@ int wait_upload(msc_ctx* ctx) {
   CK(cudaEventSynchronize(ctx->ev_copy));
   return MSC_OK;
 }
+int wait_upload_all(msc_ctx* ctx) {  // error paths: nothing of the caller's buffers may still be in flight
+  CK(cudaStreamSynchronize(ctx->copy_stream));
+  return MSC_OK;
+}
 
 float elapsed(msc_ctx* ctx, int a, int b) {
   float ms = 0;
@@ -407,9 +411,43 @@ float elapsed(msc_ctx* ctx, int a, int b) {
 }
 
 // ---- enqueue: reads pack + key table build (from the resident ASCII copy) ------------------
-int enqueue_build_reads(msc_ctx* ctx) {
-  const uint64_t U = ctx->n_reads;
-  const int S = ctx->win.S;
+// Three parts, so that msc_set_reads can run the per-read work chunk by chunk behind a chunked upload:
+//   begin   zero-fills (+ the table clear when uploading: it then runs under the first chunk's copy)
+//   chunk   2-bit pack + window pass (validity, read records, front bits, keys per partition) of reads [r0, r1)
+//   end     partition offsets -> scatter -> insert -> CSR of the further group members
+static BuildArgs build_args(msc_ctx* ctx) {
+  BuildArgs a{};
+  a.rd_words = ctx->rd_words.as<uint64_t>();
+  a.rd_x = ctx->rd_x.as<uint64_t>();
+  a.len_flags = ctx->len_flags.as<uint32_t>();
+  a.n_reads = ctx->n_reads;
+  a.w_begin = 0;
+  a.w_end = ctx->n_reads;
+  a.nmiss = ctx->nmiss.as<int32_t>();
+  a.validmask = ctx->validmask.as<uint32_t>();
+  a.rmeta = ctx->rmeta.as<uint2>();
+  a.n_keys = ctx->ctr(C_NKEYS);
+  a.tab = ctx->tab.as<uint8_t>();
+  a.tg = ctx->tgeo;
+  a.part_count = ctx->part_count.as<unsigned int>();
+  a.recs = ctx->recs.as<uint4>();
+  a.dups = ctx->dups.as<uint4>();
+  a.n_dup = ctx->ctr(C_NDUP);
+  a.n_alloc = ctx->ctr(C_SCRATCH);
+  a.items = ctx->items.as<uint2>();
+  a.bloom = ctx->bloom.as<unsigned long long>();
+  a.geom = ctx->geom;
+  return a;
+}
+
+static int enqueue_table_clear(msc_ctx* ctx) {
+  launch_k(ctx->pdl_on(), table_clear_kernel, (unsigned)std::min<uint64_t>(grid_for(ctx->tgeo.n_buckets * 4, 256), (uint64_t)ctx->sm_count * 32),
+           256, 0, ctx->stream, ctx->tab.as<uint8_t>(), ctx->tgeo.n_buckets);
+  LAUNCH_CHECK();
+  return MSC_OK;
+}
+
+int enqueue_build_begin(msc_ctx* ctx, bool clear_now) {
   if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_PACKR0], ctx->stream));
   if (ctx->trace) ctx->trace_mark("start build_reads");
   if (!ctx->pro.reads) {
@@ -418,44 +456,40 @@ int enqueue_build_reads(msc_ctx* ctx) {
     RC(enqueue_fill(ctx, f));
   }
   ctx->pro.reads = false;
-  if (U) {
-    const int rpb = std::max(1, 256 / S);  // whole reads per block
-    const size_t smem = (size_t)rpb * (size_t)ctx->win.MRL + 64;
-    launch_k(ctx->pdl_on(), pack_reads_kernel, grid_for(U, rpb), 256, smem, ctx->stream, 
-        ctx->rd_ascii.as<uint8_t>(), ctx->rd_offs.as<uint64_t>(), U, S, rpb, ctx->rd_words.as<uint64_t>(),
-        ctx->rd_x.as<uint64_t>(), ctx->len_flags.as<uint32_t>());
-    LAUNCH_CHECK();
-  }
-  CK(cudaEventRecord(ctx->ev_rd_free, ctx->stream));
-  if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_PACKR1], ctx->stream));
+  if (clear_now && ctx->n_reads) RC(enqueue_table_clear(ctx));
+  return MSC_OK;
+}
 
+int enqueue_pack_reads_range(msc_ctx* ctx, uint64_t r0, uint64_t r1) {
+  if (r1 <= r0) return MSC_OK;
+  const int S = ctx->win.S;
+  const int rpb = std::max(1, 256 / S);  // whole reads per block
+  const size_t smem = (size_t)rpb * (size_t)ctx->win.MRL + 64;
+  launch_k(ctx->pdl_on(), pack_reads_kernel, grid_for(r1 - r0, rpb), 256, smem, ctx->stream,
+      ctx->rd_ascii.as<uint8_t>(), ctx->rd_offs.as<uint64_t>() + r0, r1 - r0, S, rpb, ctx->rd_words.as<uint64_t>() + r0 * (uint64_t)S,
+      ctx->rd_x.as<uint64_t>() + r0 * (uint64_t)S, ctx->len_flags.as<uint32_t>() + r0);
+  LAUNCH_CHECK();
+  return MSC_OK;
+}
+
+int enqueue_windows_range(msc_ctx* ctx, uint64_t r0, uint64_t r1) {
+  if (r1 <= r0) return MSC_OK;
+  BuildArgs a = build_args(ctx);
+  a.w_begin = r0;
+  a.w_end = r1;
+  const unsigned g8 = (unsigned)ctx->sm_count * 8;
+  launch_k(ctx->pdl_on(), build_windows_kernel, (unsigned)std::min<uint64_t>(grid_for(r1 - r0, 256), g8), 256, 0, ctx->stream, ctx->win, a);
+  LAUNCH_CHECK();
+  return MSC_OK;
+}
+
+int enqueue_build_end(msc_ctx* ctx, bool clear_now) {
+  const uint64_t U = ctx->n_reads;
   if (U) {
-    BuildArgs a{};
-    a.rd_words = ctx->rd_words.as<uint64_t>();
-    a.rd_x = ctx->rd_x.as<uint64_t>();
-    a.len_flags = ctx->len_flags.as<uint32_t>();
-    a.n_reads = U;
-    a.nmiss = ctx->nmiss.as<int32_t>();
-    a.validmask = ctx->validmask.as<uint32_t>();
-    a.rmeta = ctx->rmeta.as<uint2>();
-    a.n_keys = ctx->ctr(C_NKEYS);
-    a.tab = ctx->tab.as<uint8_t>();
-    a.tg = ctx->tgeo;
-    a.part_count = ctx->part_count.as<unsigned int>();
-    a.recs = ctx->recs.as<uint4>();
-    a.dups = ctx->dups.as<uint4>();
-    a.n_dup = ctx->ctr(C_NDUP);
-    a.n_alloc = ctx->ctr(C_SCRATCH);
-    a.items = ctx->items.as<uint2>();
-    a.bloom = ctx->bloom.as<unsigned long long>();
-    a.geom = ctx->geom;
+    const BuildArgs a = build_args(ctx);
     const unsigned g8 = (unsigned)ctx->sm_count * 8;
     const uint64_t n_items = U * (uint64_t)ctx->win.nwin;
-    launch_k(ctx->pdl_on(), table_clear_kernel, (unsigned)std::min<uint64_t>(grid_for(ctx->tgeo.n_buckets * 4, 256), (uint64_t)ctx->sm_count * 32),
-             256, 0, ctx->stream, ctx->tab.as<uint8_t>(), ctx->tgeo.n_buckets);
-    LAUNCH_CHECK();
-    launch_k(ctx->pdl_on(), build_windows_kernel, (unsigned)std::min<uint64_t>(grid_for(U, 256), g8), 256, 0, ctx->stream, ctx->win, a);
-    LAUNCH_CHECK();
+    if (clear_now) RC(enqueue_table_clear(ctx));
     launch_k(ctx->pdl_on(), build_offsets_kernel, 1, kMaxParts, 0, ctx->stream, ctx->part_count.as<unsigned int>(), (int)ctx->tgeo.n_parts);
     LAUNCH_CHECK();
     if (!ctx->scatter_attr_set) {
@@ -478,6 +512,16 @@ int enqueue_build_reads(msc_ctx* ctx) {
   ctx->have_cand = ctx->have_confirm = ctx->have_combine = false;
   ctx->pend_reads = true;
   return MSC_OK;
+}
+
+// The whole build from the resident ASCII copy (msc_rebuild, device-side inputs).
+int enqueue_build_reads(msc_ctx* ctx) {
+  RC(enqueue_build_begin(ctx, false));
+  RC(enqueue_pack_reads_range(ctx, 0, ctx->n_reads));
+  CK(cudaEventRecord(ctx->ev_rd_free, ctx->stream));
+  if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_PACKR1], ctx->stream));
+  RC(enqueue_windows_range(ctx, 0, ctx->n_reads));
+  return enqueue_build_end(ctx, true);
 }
 
 void account_build_reads(msc_ctx* ctx) {
@@ -1191,30 +1235,48 @@ int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint
   RC(reads_reserve(ctx, n_reads, total));
   ctx->have_reads = false;
   ctx->have_prep = false;
+  // Chunked upload: the reads go over in chunks of kUploadReads; the pack and the window pass of a chunk run while the
+  // next chunk is on the PCIe link, so that only the partitioned insert is left when the last byte has arrived (the
+  // 44 ms pack + build of configs[2] used to start after the whole 10.8 GB copy).  The offsets of a chunk are
+  // validated on the host before anything that indexes the ASCII buffer through them is enqueued.
   RC(begin_upload(ctx, ctx->ev_rd_free));
-  if (total) CK(cudaMemcpyAsync(ctx->rd_ascii.p, ascii, total, cudaMemcpyHostToDevice, ctx->copy_stream));
-  if (n_reads) CK(cudaMemcpyAsync(ctx->rd_offs.p, offs, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->copy_stream));
-  else CK(cudaMemsetAsync(ctx->rd_offs.p, 0, sizeof(uint64_t), ctx->copy_stream));
-  RC(end_upload(ctx));
   ctx->st.h2d_bytes += total + (n_reads + 1) * sizeof(uint64_t);
-  // The offsets are validated while the copy is in flight; no kernel that indexes the ASCII
-  // buffer through them is enqueued before they are known to be sane.
-  {
-    const uint64_t mrl = (uint64_t)ctx->win.MRL;
+  RC(enqueue_build_begin(ctx, true));
+  if (!n_reads) CK(cudaMemsetAsync(ctx->rd_offs.p, 0, sizeof(uint64_t), ctx->copy_stream));
+  constexpr uint64_t kUploadReads = 1ull << 22;
+  const uint64_t mrl = (uint64_t)ctx->win.MRL;
+  for (uint64_t r0 = 0; r0 < n_reads; r0 += kUploadReads) {
+    const uint64_t r1 = std::min(n_reads, r0 + kUploadReads);
     uint64_t bad = 0;
-    for (uint64_t i = 0; i < n_reads; i++) bad |= (uint64_t)(offs[i + 1] < offs[i]) | (uint64_t)(offs[i + 1] - offs[i] > mrl);
+    for (uint64_t i = r0; i < r1; i++) bad |= (uint64_t)(offs[i + 1] < offs[i]) | (uint64_t)(offs[i + 1] - offs[i] > mrl);
+    bad |= (uint64_t)(offs[r1] > total);
     if (bad) {
-      RC(wait_upload(ctx));
-      for (uint64_t i = 0; i < n_reads; i++) {
+      RC(wait_upload_all(ctx));
+      for (uint64_t i = r0; i < r1; i++) {
         if (offs[i + 1] < offs[i]) return ctx->fail(MSC_ERR_INPUT, "reads: offsets not monotone at %llu", (unsigned long long)i);
         if (offs[i + 1] - offs[i] > mrl)
           return ctx->fail(MSC_ERR_INPUT, "reads: read %llu is longer than MaxReadLength (prep_reads truncates, "
                            "cmd/muscato_prep_reads/main.go:67-69)", (unsigned long long)i);
       }
+      return ctx->fail(MSC_ERR_INPUT, "reads: offsets run past offs[n_reads]");
     }
+    // (entry r0 of a later chunk went over as the last entry of the chunk before: the pack kernels may be reading it)
+    const uint64_t o0 = r0 ? r0 + 1 : 0;
+    CK(cudaMemcpyAsync(ctx->rd_offs.as<uint64_t>() + o0, offs + o0, (r1 - o0 + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (offs[r1] > offs[r0])
+      CK(cudaMemcpyAsync(ctx->rd_ascii.as<uint8_t>() + offs[r0], ascii + offs[r0], offs[r1] - offs[r0], cudaMemcpyHostToDevice, ctx->copy_stream));
+    RC(end_upload(ctx));  // the compute stream waits for this chunk only
+    RC(enqueue_pack_reads_range(ctx, r0, r1));
+    if (r1 == n_reads) CK(cudaEventRecord(ctx->ev_rd_free, ctx->stream));
+    RC(enqueue_windows_range(ctx, r0, r1));
   }
+  if (!n_reads) {
+    RC(end_upload(ctx));
+    CK(cudaEventRecord(ctx->ev_rd_free, ctx->stream));
+  }
+  if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_PACKR1], ctx->stream));
   ctx->have_reads = true;
-  RC(enqueue_build_reads(ctx));  // runs behind the copy; its counters are booked at the next sync
+  RC(enqueue_build_end(ctx, false));  // runs behind the copy; its counters are booked at the next sync
   RC(wait_upload(ctx));          // the caller's buffers are only borrowed for the call
   if (!ctx->cfg.keep_ascii) {
     RC(sync_counters(ctx));

@@ -94,6 +94,7 @@ struct BuildArgs {
   const uint64_t* rd_x;
   const uint32_t* len_flags;
   uint64_t n_reads;
+  uint64_t w_begin, w_end;      // build_windows_kernel: the reads of this launch (a chunk of a chunked upload)
   const int32_t* nmiss;  // [MRL + 1], host-computed float64 table (cmd/muscato_confirm/main.go:198)
   // per read outputs
   uint32_t* validmask;
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(256) build_windows_kernel(const WinCfg cfg, co
   for (int p = threadIdx.x; p < P; p += blockDim.x) s_hist[p] = 0u;
   __syncthreads();
   uint32_t nk = 0;
-  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += (uint64_t)gridDim.x * blockDim.x) {
+  for (uint64_t r = a.w_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.w_end; r += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t lf = a.len_flags[r];
     const int L = (int)(lf & 0x7fffffffu);
     const bool hasx = lf >> 31;
