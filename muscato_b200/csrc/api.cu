@@ -91,7 +91,7 @@ struct ScopedDevBuf : DevBuf {
 // Device counter block (unsigned long long each).
 enum Counter {
   C_NKEYS = 0, C_NGROUPS, C_NDUP, C_SCRATCH, C_NCAND, C_BLOOMPASS, C_NMATCH, C_NPASS, C_NOVER, C_NOUT, C_NPAIRS,
-  C_PAD0, C_NLONG, C_PAD1, C_TGX,  // C_NLONG, C_TGX at even indices; C_TGX = "some target word has X"
+  C_NDUMMY, C_NLONG, C_PAD1, C_TGX,  // C_NLONG, C_TGX at even indices; C_TGX = "some target word has X"
   C_PAD2, C_PREP_KEPT, C_PREP_UNIQ, C_PREP_BYTES, C_PAD3,  // C_PREP_KEPT at an even index (16)
   C_PREP_TIE, C_SHARDOVER,                                 // C_PREP_TIE (20): longest unsorted run of prep_tiefix_kernel;
                                                            // C_SHARDOVER: some target shard flagged a MaxMatches candidate group
@@ -150,7 +150,7 @@ struct msc_ctx {
   // candidates / pairs
   uint64_t n_cand = 0, n_pairs = 0;
   bool have_cand = false;
-  DevBuf cand, cinfo, sizes, pstart, block_first;
+  DevBuf cinfo, sizes, pstart, block_first;
   // matches
   uint64_t n_match_pre = 0, n_match = 0;
   bool have_confirm = false, have_combine = false;
@@ -230,7 +230,7 @@ struct msc_ctx {
     return code;
   }
   unsigned long long* ctr(int which) const { return counters.as<unsigned long long>() + which; }
-  uint64_t cand_cap() const { return cand.cap / sizeof(uint2); }
+  uint64_t cand_cap() const { return sizes.cap >= sizeof(uint32_t) ? sizes.cap / sizeof(uint32_t) - 1 : 0; }
   uint64_t match_cap() const { return match_pre.cap / sizeof(uint4); }
   uint64_t block_cap() const {
     const uint64_t n = block_first.cap / sizeof(uint32_t);
@@ -340,6 +340,7 @@ void add_targets_fills(msc_ctx* ctx, Filler& f) {
 }
 void add_scan_fills(msc_ctx* ctx, Filler& f) {
   f.add(ctx->ctr(C_NCAND), 2 * sizeof(unsigned long long));  // C_NCAND, C_BLOOMPASS
+  f.add(ctx->ctr(C_NPAIRS), 2 * sizeof(unsigned long long));  // C_NPAIRS (rewritten by every expansion), C_NDUMMY
 }
 void add_pairs_fills(msc_ctx* ctx, Filler& f) {
   f.add(ctx->ctr(C_NMATCH), 4 * sizeof(unsigned long long));  // C_NMATCH, C_NPASS, C_NOVER, C_NOUT
@@ -566,10 +567,9 @@ void account_pack_targets(msc_ctx* ctx) {
 
 // The candidate list is two parallel arrays: (slot, position) and the slot's record.
 int reserve_cand(msc_ctx* ctx, uint64_t n) {
-  CK(ctx->cand.reserve(n * sizeof(uint2)));
-  // the scan kernel writes the pair kernel's per-candidate record and the group size next to (slot, position)
-  const uint64_t ccap = ctx->cand.cap / sizeof(uint2);
-  CK(ctx->sizes.reserve((ccap + 1) * sizeof(uint32_t)));
+  // per candidate: the pair kernel's 32-byte record (position, slot, group record ...) and the key group's size
+  CK(ctx->sizes.reserve((n + 1) * sizeof(uint32_t)));
+  const uint64_t ccap = ctx->sizes.cap / sizeof(uint32_t) - 1;
   CK(ctx->cinfo.reserve((ccap + 1) * 2 * sizeof(uint4)));
   return MSC_OK;
 }
@@ -595,7 +595,11 @@ void (*pick_scan_kernel(int W, int wn, bool direct = false))(const ScanArgs) {
 }
 
 int enqueue_scan(msc_ctx* ctx) {
-  if (ctx->cand.cap == 0) RC(reserve_cand(ctx, std::max<uint64_t>(1u << 20, ctx->n_bases / 16)));
+  if (ctx->sizes.cap == 0) {
+    // (exact front: every warp of every launch may leave most of one kSlotBlock of reserved slots empty)
+    const uint64_t slack = ctx->geom.direct ? (uint64_t)ctx->sm_count * MSC_DIRECT_CTAS * kScanWarps * kSlotBlock << ctx->geom.lg_pass : 0;
+    RC(reserve_cand(ctx, std::max<uint64_t>(1u << 20, ctx->n_bases / 16) + slack));
+  }
   void (*scan_fn)(const ScanArgs) = pick_scan_kernel(ctx->win.W, ctx->geom.wn, ctx->geom.direct != 0);
   const size_t scan_smem = ctx->geom.direct ? sizeof(ScanDirectSmem) : sizeof(ScanSmem);
   if (ctx->scan_grid == 0 || ctx->scan_fn_sized != (const void*)scan_fn) {
@@ -625,7 +629,6 @@ int enqueue_scan(msc_ctx* ctx) {
     for (int j = 0; j < 8; j++) a.mul[j] = j < ctx->geom.wn ? 1u << (32 - 2 * ctx->geom.m - 2 * j) : 0u;
     a.tab = ctx->tab.as<uint8_t>();
     a.n_buckets = ctx->tgeo.n_buckets;
-    a.cand = ctx->cand.as<uint2>();
     a.cinfo = ctx->cinfo.as<uint4>();
     a.sizes = ctx->sizes.as<uint32_t>();
     a.tg_off = ctx->tg_off.as<uint32_t>();
@@ -634,11 +637,14 @@ int enqueue_scan(msc_ctx* ctx) {
     a.cand_cap = ctx->cand_cap();
     a.n_cand = ctx->ctr(C_NCAND);
     a.n_bloom_pass = ctx->ctr(C_BLOOMPASS);
+    a.n_dummy = ctx->ctr(C_NDUMMY);
     a.W = ctx->win.W;
     a.alu_masks = ctx->lg_bloom > 23 ? 1 : 0;
     if (const char* e = getenv("MSC_SCAN_ALU_MASKS")) a.alu_masks = atoi(e) != 0;
-    a.prefetch = 0;  // measured slower at S2 (72 vs 60 ms): the memory system is saturated, more requests in flight only add queueing
-    if (const char* e = getenv("MSC_SCAN_PREFETCH")) a.prefetch = atoi(e) != 0;
+    // Bloom front: measured slower at S2 (72 vs 60 ms: the memory system is saturated by the filter's own misses, more
+    // requests in flight only add queueing); exact front: the survivor's line is requested when it is queued
+    a.prefetch = 0;
+    if (const char* e = getenv("MSC_SCAN_PREFETCH")) a.prefetch = atoi(e);
     // table beyond the L2: its lines and the candidate records are touched once (evict-first), which leaves the L2 to
     // the front's current slice
     a.stream_tab = ctx->tgeo.n_buckets * (uint64_t)kBucketBytes > (64ull << 20) ? 1 : 0;
@@ -686,7 +692,6 @@ int enqueue_pairs(msc_ctx* ctx, int mode, DevBuf& outbuf) {
   a.block_cap = ctx->block_cap();
   a.items = ctx->items.as<uint2>();
   a.validmask = ctx->validmask.as<uint32_t>();
-  a.cand = ctx->cand.as<uint2>();
   a.pass_small = ctx->pass_small.as<uint32_t>();
   a.lg_small = ctx->lg_small;
   a.pass_cnt = ctx->exact_counts ? ctx->pass_cnt.as<uint32_t>() : nullptr;
@@ -800,7 +805,7 @@ int finish_scan(msc_ctx* ctx) {
     ctx->have_cand = false;
     return NEED_RETRY;
   }
-  ctx->st.n_candidates = ctx->n_cand;
+  ctx->st.n_candidates = ctx->n_cand - std::min<uint64_t>(ctx->n_cand, ctx->h_counters[C_NDUMMY]);  // without the empty slots of the exact front
   ctx->st.positions_probed = ctx->n_bases;
   ctx->st.reserved_f[0] = (float)ctx->h_counters[C_BLOOMPASS];
   ctx->st.reserved_f[2] = ctx->geom.direct ? (float)(1 << ctx->geom.lg_pass) : 0.f;
@@ -1086,7 +1091,7 @@ void msc_destroy(msc_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->rd_ascii,    &ctx->rd_offs,   &ctx->rd_words, &ctx->rd_x,      &ctx->len_flags, &ctx->validmask, &ctx->rmeta,
                     &ctx->tab,         &ctx->recs,      &ctx->dups,     &ctx->part_count, &ctx->pass_small, &ctx->pass_cnt, &ctx->bloom,
                     &ctx->items,       &ctx->tg_ascii,  &ctx->tg_off,    &ctx->tg_words,
-                    &ctx->tg_x,        &ctx->xsum,      &ctx->blk2gene,  &ctx->prep_perm, &ctx->prep_gstart, &ctx->nm_flag, &ctx->nm_pos, &ctx->nm_list, &ctx->cand,     &ctx->cinfo,     &ctx->sizes,     &ctx->pstart,
+                    &ctx->tg_x,        &ctx->xsum,      &ctx->blk2gene,  &ctx->prep_perm, &ctx->prep_gstart, &ctx->nm_flag, &ctx->nm_pos, &ctx->nm_list, &ctx->cinfo,     &ctx->sizes,     &ctx->pstart,
                     &ctx->block_first, &ctx->match_pre, &ctx->best,     &ctx->rcount,    &ctx->rstart,    &ctx->rfill,
                     &ctx->match_out,   &ctx->long_list, &ctx->mid_list, &ctx->counters,  &ctx->tile_sums, &ctx->scan_state, &ctx->nmiss};
   for (DevBuf* b : bufs) b->release();
@@ -1174,7 +1179,9 @@ static int reads_reserve(msc_ctx* ctx, uint64_t n_reads, uint64_t total) {
   ctx->geom.lg_pass = 0;
   if (ctx->win.W <= 15) {
     const int lg_direct = std::max(10, 2 * ctx->win.W - 6);
-    bool direct = lg_direct <= ctx->lg_bloom;
+    // (measured, profiles/r02/call23_summary.txt: 3.7e7 keys: Bloom 64 MB 3.54 ms vs exact 1.99 ms per 2.5e8 bases;
+    // 1.5e7 keys: 1.23 vs 0.79; 6e6 keys, Bloom 32 MB: 0.31 vs 0.36 -- the map pays from a 64 MB Bloom front on)
+    bool direct = lg_direct <= ctx->lg_bloom + 1;
     if (const char* e = getenv("MSC_FRONT_DIRECT")) direct = atoi(e) != 0;
     if (direct) {
       int pass_mb = 32;

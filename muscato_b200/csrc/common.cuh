@@ -14,6 +14,16 @@ namespace msc {
 // ---------------------------------------------------------------------------
 constexpr uint64_t kEvenBits = 0x5555555555555555ull;
 
+// Bits 0, 2, 4, ... 30 of x packed into the low 16 bits.
+__host__ __device__ __forceinline__ uint32_t compress_even32(uint32_t x) {
+  x &= 0x55555555u;
+  x = (x | (x >> 1)) & 0x33333333u;
+  x = (x | (x >> 2)) & 0x0f0f0f0fu;
+  x = (x | (x >> 4)) & 0x00ff00ffu;
+  x = (x | (x >> 8)) & 0x0000ffffu;
+  return x;
+}
+
 __host__ __device__ __forceinline__ uint64_t low_bases_mask(int n) {  // n in [0,32]
   return n >= 32 ? ~0ull : ((1ull << (2 * n)) - 1ull);
 }
@@ -266,6 +276,11 @@ __device__ __forceinline__ void stg32_hint(void* p, uint32_t v, uint64_t pol) {
 
 // Request a line into the L2 without a destination register.
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// The same through the TMA engine: `bytes` (multiple of 16) from a 16-byte aligned address, no register, no LSU slot.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 __device__ __forceinline__ const uint8_t* bucket_ptr(const uint8_t* tab, uint64_t b) { return tab + b * (uint64_t)kBucketBytes; }
 __device__ __forceinline__ uint8_t* bucket_ptr(uint8_t* tab, uint64_t b) { return tab + b * (uint64_t)kBucketBytes; }

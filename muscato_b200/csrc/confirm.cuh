@@ -56,7 +56,6 @@ __global__ void __launch_bounds__(256) pair_block_starts_kernel(const uint64_t* 
 struct ConfirmArgs {
   // candidates and their pair prefix
   const uint4* cinfo;          // two per candidate, written by the scan kernel
-  const uint2* cand;           // (slot, position): the slot is only needed by pairs that pass
   const uint32_t* block_first; // first candidate of each kPairBlock-pair block (+1 sentinel entry)
   const uint64_t* pstart;  // n_cand + 1
   const unsigned long long* n_pairs_ptr;  // device-side pair count (grand total of the size scan)
@@ -309,7 +308,7 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
   }
 
   // The pair passes through window k.
-  const uint32_t slot = __ldg(a.cand + c).x;
+  const uint32_t slot = cj.w;
   atomicAdd(a.pass_small + ((slot * 0x9E3779B1u) >> (32 - a.lg_small)), 1u);
   if (a.pass_cnt) atomicAdd(a.pass_cnt + slot, 1u);
   n_pass++;

@@ -49,7 +49,6 @@ struct ScanArgs {
   uint32_t mul[8];        // mul[j] = 1 << (32 - 2m - 2j): m-mer j of a key to the top of a word
   const uint8_t* tab;     // key table: 128-byte buckets (common.cuh)
   uint64_t n_buckets;
-  uint2* cand;            // (slot, global target position)
   // the candidate's 32-byte record for the pair kernel (two uint4, see flush_stage) and its key group's size
   uint4* cinfo;
   uint32_t* sizes;
@@ -59,6 +58,7 @@ struct ScanArgs {
   unsigned long long cand_cap;
   unsigned long long* n_cand;
   unsigned long long* n_bloom_pass;
+  unsigned long long* n_dummy;  // exact front: candidate slots that were reserved and stayed empty (size 0)
   int W;
   int alu_masks;          // 1 = Bloom bit masks by arithmetic instead of the shared-memory pattern table (MSC_SCAN_ALU_MASKS)
   int prefetch;           // 1 = request every queued position's bucket line into the L2 before the drain (MSC_SCAN_PREFETCH)
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
   // Flush: one global atomic reserves the run; every staged candidate is written as the pair kernel wants it --
   // (slot, position), its key group's size, and ONE 32-byte record (two uint4):
   //   (global position of the window, window start p inside its target, global end of the target, read record of item 0)
-  //   (item 0 of the key group, CSR start of the further items, target index, 0)
+  //   (item 0 of the key group, CSR start of the further items, target index, table slot)
   // so the expansion needs no pass over the candidates of its own.  The target of a position comes from the tile's
   // slice of the offset table in shared memory (gt[]: loaded once per tile; the stage is flushed at the end of every
   // tile, so all staged positions belong to the current one) -- per-candidate look-ups in global memory were measured
@@ -184,14 +184,12 @@ __global__ void __launch_bounds__(kScanBlock, MSC_SCAN_CTAS) scan_targets_kernel
         const uint32_t sz = ((uint64_t)e.y + (uint64_t)a.W <= (uint64_t)gend) ? 1u + rec.w : 0u;
         if (stream_tab) {
           // written once, read once by the expansion long after the L2 has turned over: first out
-          stg64_hint(a.cand + o, e, pol_once);
           stg128_hint(a.cinfo + 2 * o, make_uint4(e.y, e.y - goff, gend, rec.y), pol_once);
-          stg128_hint(a.cinfo + 2 * o + 1, make_uint4(rec.x, rec.z, g, 0u), pol_once);
+          stg128_hint(a.cinfo + 2 * o + 1, make_uint4(rec.x, rec.z, g, e.x), pol_once);
           stg32_hint(a.sizes + o, sz, pol_once);
         } else {
-          a.cand[o] = e;
           a.cinfo[2 * o] = make_uint4(e.y, e.y - goff, gend, rec.y);
-          a.cinfo[2 * o + 1] = make_uint4(rec.x, rec.z, g, 0u);
+          a.cinfo[2 * o + 1] = make_uint4(rec.x, rec.z, g, e.x);
           a.sizes[o] = sz;
         }
       }
