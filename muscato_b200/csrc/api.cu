@@ -435,6 +435,7 @@ static BuildArgs build_args(msc_ctx* ctx) {
   a.dups = ctx->dups.as<uint4>();
   a.n_dup = ctx->ctr(C_NDUP);
   a.n_alloc = ctx->ctr(C_SCRATCH);
+  a.insert_cursor = ctx->ctr(C_NGROUPS);  // (the host derives the group count from keys - further members)
   a.items = ctx->items.as<uint2>();
   a.bloom = ctx->bloom.as<unsigned long long>();
   a.geom = ctx->geom;

@@ -110,6 +110,7 @@ struct BuildArgs {
   uint4* dups;                  // {slot, item, rmx, ordinal}
   unsigned long long* n_dup;
   unsigned long long* n_alloc;  // bump allocator of the CSR
+  unsigned long long* insert_cursor;  // build_insert_kernel: next record to hand out
   uint2* items;
   // Bloom front
   unsigned long long* bloom;
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(256) build_windows_kernel(const WinCfg cfg, co
   for (int p = threadIdx.x; p < P; p += blockDim.x) s_hist[p] = 0u;
   __syncthreads();
   uint32_t nk = 0;
+  const uint64_t pol_keep = l2_policy_evict_last();
   for (uint64_t r = a.w_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.w_end; r += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t lf = a.len_flags[r];
     const int L = (int)(lf & 0x7fffffffu);
@@ -186,13 +188,15 @@ __global__ void __launch_bounds__(256) build_windows_kernel(const WinCfg cfg, co
       uint64_t widx;
       uint32_t mlo, mhi;
       bloom_locate(key, xm, fp, cfg.W, a.geom, widx, mlo, mhi, key1);
-      atomicOr(a.bloom + widx, (unsigned long long)mlo | ((unsigned long long)mhi << 32));
+      // the front's words are the one structure this pass re-uses: last out of the L2 (every RED that misses costs a
+      // sector read and a sector write in HBM: ncu, 1.6 sectors of each per key with a 128 MB map and default priority)
+      red_or64_hint(a.bloom + widx, (unsigned long long)mlo | ((unsigned long long)mhi << 32), pol_keep);
       atomicAdd(&s_hist[key_partition(fp, a.tg)], 1u);
     }
-    a.validmask[r] = vm;
+    __stcs(a.validmask + r, vm);  // (streaming stores: written once, read by later kernels from HBM anyway)
     // what the confirm kernel needs of a read: length, mismatch budget nmiss(L), has-X flag (WinCfg);
     // .y = valid-window mask
-    a.rmeta[r] = make_uint2((uint32_t)L | ((uint32_t)__ldg(a.nmiss + L) << cfg.lbits) | (lf & 0x80000000u), vm);
+    __stcs(a.rmeta + r, make_uint2((uint32_t)L | ((uint32_t)__ldg(a.nmiss + L) << cfg.lbits) | (lf & 0x80000000u), vm));
   }
   __syncthreads();
   for (int p = threadIdx.x; p < P; p += blockDim.x) {
@@ -306,40 +310,97 @@ __global__ void __launch_bounds__(kScatterThreads, 2) build_scatter_kernel(const
 // group claims a slot with one CAS on the first slot it saw free in the bucket (the CAS returns what
 // is there now if another thread was faster) and writes the slot's record; further members are
 // appended to the dups list (their CSR position is settled by passes D-F, after every claim is done).
+//
+// The records are handed out in ORDER, one block-sized chunk per grab of a global cursor (insert_cursor, zero-filled with
+// the other counters), so that the whole grid works on one front of ~3e5 consecutive records = one partition = 16 MB of
+// table at any time: with a static grid-stride split the warps drift several partitions apart and the bucket lines of a
+// partition left the L2 between the ~2 keys that touch each of them (ncu: one line read from HBM per KEY, not per bucket).
+constexpr int kInsPerThread = 1;  // records per thread and round (2 was measured slower: 11.3 vs 10.5 ms at configs[2])
+
 __global__ void __launch_bounds__(256) build_insert_kernel(const BuildArgs a) {
   pdl_enter();
+  __shared__ unsigned long long s_chunk, s_dup_base;
+  __shared__ uint32_t s_wcnt[8];
   const uint64_t n = *a.n_keys;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint4 rc = a.recs[i];
-    const uint64_t fp = (uint64_t)rc.x | ((uint64_t)rc.y << 32);
-    uint64_t bk = table_home_bucket(fp, a.tg.n_buckets);
-    int64_t slot = -1;
-    bool first = false;
-    while (slot < 0) {
-      uint8_t* bp = bucket_ptr(a.tab, bk);
-      uint64_t q[kBucketSlots];
-      ldcg256(bp, q[0], q[1], q[2], q[3]);  // the bucket as it stands (L2: other SMs are claiming slots)
-      q[4] = ldcg64(bp + 32);
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  while (true) {
+    if (threadIdx.x == 0) s_chunk = atomicAdd(a.insert_cursor, (unsigned long long)(blockDim.x * kInsPerThread));
+    __syncthreads();
+    if (s_chunk >= n) break;  // block-uniform
+    uint4 rc[kInsPerThread];
+    uint64_t fp[kInsPerThread], bk[kInsPerThread];
+    int64_t slot[kInsPerThread];
+    bool first[kInsPerThread], valid[kInsPerThread];
+    uint64_t q[kInsPerThread][kBucketSlots];
 #pragma unroll
-      for (int s = 0; s < kBucketSlots; s++) {
-        if (slot >= 0) break;
-        uint64_t v = q[s];
-        if (v == 0ull) v = atomicCAS(reinterpret_cast<unsigned long long*>(bp) + s, 0ull, (unsigned long long)fp);
-        if (v == 0ull) {
-          slot = (int64_t)(bk * kBucketSlots + s);
-          first = true;
-        } else if (v == fp) {
-          slot = (int64_t)(bk * kBucketSlots + s);
-        }
+    for (int u = 0; u < kInsPerThread; u++) {
+      const uint64_t i = s_chunk + (uint64_t)u * blockDim.x + threadIdx.x;
+      valid[u] = i < n;
+      rc[u] = valid[u] ? a.recs[i] : make_uint4(0u, 0u, 0u, 0u);
+      fp[u] = (uint64_t)rc[u].x | ((uint64_t)rc[u].y << 32);
+      bk[u] = table_home_bucket(fp[u], a.tg.n_buckets);
+      slot[u] = -1;
+      first[u] = false;
+      if (valid[u]) {
+        // the bucket as it stands (L2: other SMs are claiming slots); both records' buckets are requested before either is used
+        ldcg256(bucket_ptr(a.tab, bk[u]), q[u][0], q[u][1], q[u][2], q[u][3]);
+        q[u][4] = ldcg64(bucket_ptr(a.tab, bk[u]) + 32);
       }
-      if (slot < 0) bk = bk + 1 == a.tg.n_buckets ? 0 : bk + 1;  // bucket full of other keys: next bucket
     }
-    if (first) {
-      *slot_rec_ptr(a.tab, (uint64_t)slot) = make_uint4(rc.z, rc.w, 0u, 0u);
-    } else {
-      const unsigned long long at = warp_agg_inc(a.n_dup);
-      a.dups[at] = make_uint4((uint32_t)slot, rc.z, rc.w, 0u);
+#pragma unroll
+    for (int u = 0; u < kInsPerThread; u++) {
+      if (!valid[u]) continue;
+      while (true) {
+        uint8_t* bp = bucket_ptr(a.tab, bk[u]);
+#pragma unroll
+        for (int s = 0; s < kBucketSlots; s++) {
+          if (slot[u] >= 0) break;
+          uint64_t v = q[u][s];
+          if (v == 0ull) v = atomicCAS(reinterpret_cast<unsigned long long*>(bp) + s, 0ull, (unsigned long long)fp[u]);
+          if (v == 0ull) {
+            slot[u] = (int64_t)(bk[u] * kBucketSlots + s);
+            first[u] = true;
+          } else if (v == fp[u]) {
+            slot[u] = (int64_t)(bk[u] * kBucketSlots + s);
+          }
+        }
+        if (slot[u] >= 0) break;
+        bk[u] = bk[u] + 1 == a.tg.n_buckets ? 0 : bk[u] + 1;  // bucket full of other keys: next bucket
+        ldcg256(bucket_ptr(a.tab, bk[u]), q[u][0], q[u][1], q[u][2], q[u][3]);
+        q[u][4] = ldcg64(bucket_ptr(a.tab, bk[u]) + 32);
+      }
+      if (first[u]) *slot_rec_ptr(a.tab, (uint64_t)slot[u]) = make_uint4(rc[u].z, rc[u].w, 0u, 0u);
     }
+    // further members: ONE bump of the global list cursor per block and round (a returning atomic per warp on one
+    // address -- 9.4e6 of them at configs[2] -- was what bounded this kernel, not its HBM traffic)
+    unsigned bal[kInsPerThread];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int u = 0; u < kInsPerThread; u++) {
+      bal[u] = __ballot_sync(0xffffffffu, valid[u] && !first[u]);
+      mine += __popc(bal[u]);
+    }
+    if (lane == 0) s_wcnt[warp] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t t = 0;
+      for (int w = 0; w < 8; w++) {
+        const uint32_t c = s_wcnt[w];
+        s_wcnt[w] = t;
+        t += c;
+      }
+      s_dup_base = t ? atomicAdd(a.n_dup, (unsigned long long)t) : 0ull;
+    }
+    __syncthreads();
+    {
+      unsigned long long at = s_dup_base + s_wcnt[warp];
+#pragma unroll
+      for (int u = 0; u < kInsPerThread; u++) {
+        if (valid[u] && !first[u]) a.dups[at + __popc(bal[u] & ((1u << lane) - 1u))] = make_uint4((uint32_t)slot[u], rc[u].z, rc[u].w, 0u);
+        at += __popc(bal[u]);
+      }
+    }
+    __syncthreads();  // s_chunk, s_wcnt, s_dup_base are rewritten by the next round
   }
 }
 

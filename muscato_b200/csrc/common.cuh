@@ -259,6 +259,10 @@ __device__ __forceinline__ uint32_t ldg32_hint(const uint32_t* p, uint64_t pol) 
 __device__ __forceinline__ void ldg256_stream(const void* p, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d) {
   asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
+// 64-bit OR without a return value whose line keeps the given L2 priority (REDG.E.OR.64 with a policy descriptor).
+__device__ __forceinline__ void red_or64_hint(unsigned long long* p, unsigned long long v, uint64_t pol) {
+  asm volatile("red.global.or.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
 __device__ __forceinline__ uint4 ldg128_last_use(const uint4* p, uint64_t pol) {
   uint4 v;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
