@@ -329,7 +329,7 @@ struct Filler {
 void add_reads_fills(msc_ctx* ctx, Filler& f) {
   f.add(ctx->len_flags.p, (ctx->n_reads + 1) * sizeof(uint32_t));
   f.add(ctx->ctr(C_NKEYS), 4 * sizeof(unsigned long long));  // C_NKEYS, C_NGROUPS, C_NDUP, C_SCRATCH
-  f.add(ctx->part_count.p, kMaxParts * sizeof(unsigned int));
+  f.add(ctx->part_count.p, (size_t)kMaxParts * kPartStride * sizeof(unsigned int));
   f.add(ctx->bloom.p, (1ull << ctx->lg_bloom) * sizeof(uint64_t));  // build_windows_kernel sets the bits
   // (the table's fingerprints are cleared by table_clear_kernel: 64 of every 128 bytes)
 }
@@ -1214,7 +1214,7 @@ static int reads_reserve(msc_ctx* ctx, uint64_t n_reads, uint64_t total) {
     ctx->geom.xr = 0x55555555u & (uint32_t)low_bases_mask(ctx->win.W);
   }
   CK(ctx->tab.reserve(ctx->tgeo.n_buckets * (uint64_t)kBucketBytes));
-  CK(ctx->part_count.reserve((size_t)kMaxParts * sizeof(unsigned int)));
+  CK(ctx->part_count.reserve((size_t)kMaxParts * kPartStride * sizeof(unsigned int)));
   CK(ctx->pass_small.reserve((1ull << ctx->lg_small) * sizeof(uint32_t)));
   CK(ctx->bloom.reserve((1ull << ctx->lg_bloom) * sizeof(uint64_t)));
   CK(ctx->recs.reserve((n_reads * nwin + 1) * sizeof(uint4)));

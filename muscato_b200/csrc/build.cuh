@@ -118,6 +118,10 @@ struct BuildArgs {
 };
 
 constexpr int kMaxParts = 1024;
+// The per-partition counters / write cursors sit one per 128-byte line (kPartStride words apart): every block of the
+// window pass and of the scatter bumps all of them, and atomics on one line serialise in its L2 slice (packed, the 1024
+// counters are 32 lines).
+constexpr int kPartStride = 32;
 
 __device__ __forceinline__ uint32_t key_partition(uint64_t fp, const TableGeom& tg) {
   return (uint32_t)(table_home_bucket(fp, tg.n_buckets) >> tg.lg_bpp);
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(256) build_windows_kernel(const WinCfg cfg, co
   __syncthreads();
   for (int p = threadIdx.x; p < P; p += blockDim.x) {
     const unsigned int c = s_hist[p];
-    if (c) atomicAdd(a.part_count + p, c);
+    if (c) atomicAdd(a.part_count + (size_t)p * kPartStride, c);
   }
   // one counter atomic per block (same-address atomics serialise)
   __shared__ uint32_t s_nk[8];
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(kMaxParts) build_offsets_kernel(unsigned int* 
   pdl_enter();
   __shared__ unsigned int s[kMaxParts];
   const int t = threadIdx.x;
-  const unsigned int v = t < P ? part_count[t] : 0u;
+  const unsigned int v = t < P ? part_count[(size_t)t * kPartStride] : 0u;
   s[t] = v;
   __syncthreads();
   for (int o = 1; o < kMaxParts; o <<= 1) {
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(kMaxParts) build_offsets_kernel(unsigned int* 
     s[t] += add;
     __syncthreads();
   }
-  if (t < P) part_count[t] = s[t] - v;
+  if (t < P) part_count[(size_t)t * kPartStride] = s[t] - v;
 }
 
 // Pass B: distribute the key records into partition order.  One thread per (read, window) item; a
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(kScatterThreads, 2) build_scatter_kernel(const
     __syncthreads();
     for (int p = threadIdx.x; p < P; p += kScatterThreads) {
       const unsigned int c = s_cnt[p];
-      if (c) s_base[p] = atomicAdd(a.part_count + p, c);
+      if (c) s_base[p] = atomicAdd(a.part_count + (size_t)p * kPartStride, c);
       s_cnt[p] = 0u;
     }
     __syncthreads();
