@@ -419,6 +419,7 @@ float elapsed(msc_ctx* ctx, int a, int b) {
 static BuildArgs build_args(msc_ctx* ctx) {
   BuildArgs a{};
   a.rd_words = ctx->rd_words.as<uint64_t>();
+  a.rd_words_rw = ctx->rd_words.as<uint64_t>();
   a.rd_x = ctx->rd_x.as<uint64_t>();
   a.len_flags = ctx->len_flags.as<uint32_t>();
   a.n_reads = ctx->n_reads;
@@ -1065,6 +1066,8 @@ msc_ctx* msc_create(const msc_config* config, char* errbuf, uint64_t errlen) {
     int sk = std::min(12, (31 - ctx->win.lbits - ctx->win.nbits) / 2);
     if (const char* e = getenv("MSC_SKETCH")) sk = std::min(sk, atoi(e));
     ctx->win.sk = sk >= 4 ? sk : 0;
+    ctx->win.vm_in_row = 2 * (32 * ctx->win.S - ctx->win.MRL) >= ctx->win.nwin ? 1 : 0;
+    if (const char* e = getenv("MSC_VM_IN_ROW")) ctx->win.vm_in_row = ctx->win.vm_in_row && atoi(e) != 0;
   }
   ok = ok && ctx->nmiss.reserve(nm.size() * sizeof(int32_t)) == cudaSuccess;
   ok = ok && cudaMemcpy(ctx->nmiss.p, nm.data(), nm.size() * sizeof(int32_t), cudaMemcpyHostToDevice) == cudaSuccess;

@@ -18,6 +18,10 @@ struct WinCfg {
   //   bits [0, lbits) read length, [lbits, lbits + nbits) mismatch budget nmiss(L), then 2 * sk bits of SKETCH
   //   (sk read bases next to the window, see item_sketch), bit 31 = the read contains X
   int lbits, nbits, sk;
+  // 1 = the read's valid-window mask also sits in the top nwin bits of the LAST word of its packed row (bases the
+  // row does not use: 2 * (32 * S - MRL) >= nwin), so that confirm finds it in the row line it has just fetched
+  // instead of in a second random line (measured: 10 % of the confirm kernel's stall samples, 8.5 GB at configs[2])
+  int vm_in_row;
   int windows[32];
 };
 
@@ -94,6 +98,7 @@ struct BuildArgs {
   const uint64_t* rd_x;
   const uint32_t* len_flags;
   uint64_t n_reads;
+  uint64_t* rd_words_rw;        // = rd_words (build_windows_kernel adds the valid-window mask to the row's spare bits)
   uint64_t w_begin, w_end;      // build_windows_kernel: the reads of this launch (a chunk of a chunked upload)
   const int32_t* nmiss;  // [MRL + 1], host-computed float64 table (cmd/muscato_confirm/main.go:198)
   // per read outputs
@@ -198,6 +203,7 @@ __global__ void __launch_bounds__(256) build_windows_kernel(const WinCfg cfg, co
       atomicAdd(&s_hist[key_partition(fp, a.tg)], 1u);
     }
     __stcs(a.validmask + r, vm);  // (streaming stores: written once, read by later kernels from HBM anyway)
+    if (cfg.vm_in_row && vm) a.rd_words_rw[r * (uint64_t)cfg.S + (uint64_t)(cfg.S - 1)] |= (uint64_t)vm << (64 - cfg.nwin);
     // what the confirm kernel needs of a read: length, mismatch budget nmiss(L), has-X flag (WinCfg);
     // .y = valid-window mask
     __stcs(a.rmeta + r, make_uint2((uint32_t)L | ((uint32_t)__ldg(a.nmiss + L) << cfg.lbits) | (lf & 0x80000000u), vm));

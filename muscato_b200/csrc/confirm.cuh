@@ -321,7 +321,10 @@ __device__ __forceinline__ bool confirm_one_pair(const WinCfg& cfg, const Confir
   // Cross-window de-duplication: emit only through the lowest window index that delivers
   // this (read, gene, pos).  Window k' delivers it iff it is valid for the read, its k-mer
   // matches exactly, and -- when it would sit at target position 0 -- the literal-100 rule holds.
-  uint32_t vm = k ? (__ldg(a.validmask + r) & ((1u << k) - 1u)) : 0u;
+  // (the valid-window mask of the read: from the spare bits of its row's last word -- the line is in the L1 -- when
+  // the row has them, WinCfg::vm_in_row; else from the per-read array)
+  uint32_t vm = 0u;
+  if (k) vm = (cfg.vm_in_row ? (uint32_t)(__ldg(row + (cfg.S - 1)) >> (64 - cfg.nwin)) : __ldg(a.validmask + r)) & ((1u << k) - 1u);
   while (vm) {
     const int k2 = __ffs(vm) - 1;
     vm &= vm - 1;
