@@ -350,7 +350,6 @@ void add_pairs_fills(msc_ctx* ctx, Filler& f) {
 }
 void add_combine_fills(msc_ctx* ctx, Filler& f) {
   f.add(ctx->rcount.p, (ctx->n_reads + 1) * sizeof(uint32_t));
-  f.add(ctx->rfill.p, (ctx->n_reads + 1) * sizeof(uint32_t));
   f.add(ctx->ctr(C_NLONG), 2 * sizeof(unsigned long long));
 }
 
@@ -772,10 +771,11 @@ int enqueue_combine(msc_ctx* ctx) {
   LAUNCH_CHECK();
   RC(enqueue_exclusive_scan<uint32_t>(ctx, ctx->rcount.as<uint32_t>(), nullptr, U, ctx->rstart.as<uint32_t>(), true,
                                       ctx->ctr(C_NOUT)));
+  // the per-read output cursors start at the reads' first slots
+  CK(cudaMemcpyAsync(ctx->rfill.p, ctx->rstart.p, (U + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   launch_k(ctx->pdl_on(), combine_scatter_kernel, g, 256, 0, ctx->stream, ctx->match_pre.as<uint4>(), ctx->ctr(C_NMATCH), mcap,
                                                      ctx->best.as<uint32_t>(), (uint32_t)ctx->cfg.mmtol,
-                                                     ctx->rstart.as<uint32_t>(), ctx->rfill.as<uint32_t>(),
-                                                     ctx->match_out.as<uint4>());
+                                                     ctx->rfill.as<uint32_t>(), ctx->match_out.as<uint4>());
   LAUNCH_CHECK();
   if (U) {
     // deterministic (gene, pos) order inside every read group; match_pre is dead and serves as scratch

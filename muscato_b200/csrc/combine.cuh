@@ -23,13 +23,14 @@ __global__ void __launch_bounds__(256) combine_count_kernel(const uint4* __restr
 __global__ void __launch_bounds__(256) combine_scatter_kernel(const uint4* __restrict__ m,
                                                               const unsigned long long* __restrict__ n_ptr, uint64_t cap,
                                                               const uint32_t* __restrict__ best, uint32_t mmtol,
-                                                              const uint32_t* __restrict__ rstart,
-                                                              uint32_t* __restrict__ rfill, uint4* __restrict__ out) {
+                                                              uint32_t* __restrict__ rcursor, uint4* __restrict__ out) {
   pdl_enter();
+  // rcursor[r] starts as a copy of the read's first output slot (rstart[r]) and is bumped per match: ONE random line
+  // per kept match next to best[r], where a separate fill counter cost a second one
   const uint64_t n = min((uint64_t)*n_ptr, cap);
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint4 v = m[i];
-    if (v.w <= __ldg(best + v.x) + mmtol) out[__ldg(rstart + v.x) + atomicAdd(rfill + v.x, 1u)] = v;
+    if (v.w <= __ldg(best + v.x) + mmtol) out[atomicAdd(rcursor + v.x, 1u)] = v;
   }
 }
 
