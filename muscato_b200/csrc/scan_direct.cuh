@@ -8,9 +8,9 @@
 // 77 GB of table lines stream through, and a probe that misses costs a whole HBM line.  So the scan runs in
 // 2^lg_pass LAUNCHES; launch q walks the whole packed database (0.5 GB: nothing) and tests only the positions whose
 // key falls into slice q of the bitmap (the key's top lg_pass bits = the window's last bases), so that the slice
-// (16 MB) is L2-resident (createpolicy evict_last on the probes, evict_first on the table lines' last use and on the
-// candidate records).  Measured at configs[2] on one B200: Bloom front 59.3 ms -> exact front 42.7 ms with the first
-// version of this kernel (profiles/r02/call18_summary.txt).
+// (32 MB) is L2-resident (createpolicy evict_last on the probes, evict_first on the table lines' last use and on the
+// candidate records).  Measured at configs[2] on one B200: Bloom front 59.3 ms -> exact front 36.5 ms
+// (profiles/r02/call16..19, call24, call34 summaries; what bounds it now: call26..29, call38).
 //
 // Per warp and 32-word tile (1024 positions, staged by the TMA engine as in scan.cuh):
 //   members   lane i finds the positions of word i that belong to slice q with a few 64-bit operations on the word
@@ -43,7 +43,7 @@ constexpr int kDrainEntries = MSC_DRAIN_ENTRIES;  // look-ups per drain (32 per 
 constexpr int kQB = kDrainEntries + 32 * kFrontBatch;  // survivor queue entries per warp: < one drain carried over + one front round
 constexpr int kSlotBlock = 256;  // candidate slots a warp reserves per atomic
 constexpr int kDBufs = 4;        // tile buffers per warp: three TMA copies in flight (a tile-pass with few members is
-                                 // shorter than one HBM round trip; with two buffers every tile waited for its copy)
+                                 // shorter than one HBM round trip)
 constexpr int kDGeneTab = 32;    // target offsets a warp keeps in shared memory per tile
 
 struct ScanDirectSmem {
@@ -52,7 +52,7 @@ struct ScanDirectSmem {
   uint32_t qb_pos[kScanWarps][kQB];  // survivors of the front: global position,
   uint32_t qb_key[kScanWarps][kQB];  //   key,
   uint32_t qb_g[kScanWarps][kQB];    //   target index,
-  uint32_t qb_bk[kScanWarps][kQB];   //   home bucket in the key table (its line is already on its way into the L2)
+  uint32_t qb_bk[kScanWarps][kQB];   //   home bucket in the key table
   uint32_t gtab[kScanWarps][kDGeneTab + 4];
 };
 
