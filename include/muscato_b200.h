@@ -148,6 +148,12 @@ int msc_set_targets(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, ui
 int msc_set_targets_packed(msc_ctx* ctx, const uint64_t* words, const uint64_t* xplane, const uint64_t* offs,
                            uint64_t n_targets);
 
+/* The targets of ANOTHER context on the same device, copied device to device (no host traffic).  Read parts are
+ * independent of each other (every rule of the path is per read), so a second context can screen another part of
+ * the reads against the same database while the first one is still uploading or computing: its read upload runs
+ * under the other context's scan + confirm.  src must have targets; it may replace them once this call has returned. */
+int msc_set_targets_from(msc_ctx* ctx, msc_ctx* src);
+
 /* The packed form of the current targets (after msc_set_targets), to write such a cache: words and
  * xplane need msc_packed_target_words() entries each; *has_x receives whether any base is X. */
 uint64_t msc_packed_target_words(const msc_ctx* ctx);

@@ -84,6 +84,7 @@ _SIGS = [
     ("msc_fetch_unique_reads", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("msc_set_targets", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     ("msc_set_targets_packed", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    ("msc_set_targets_from", C.c_int, [C.c_void_p, C.c_void_p]),
     ("msc_packed_target_words", C.c_uint64, [C.c_void_p]),
     ("msc_fetch_packed_targets", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     ("msc_rebuild", C.c_int, [C.c_void_p, C.c_int]),

@@ -1638,6 +1638,48 @@ int msc_set_targets_packed(msc_ctx* ctx, const uint64_t* words, const uint64_t* 
   return MSC_OK;
 }
 
+// The packed targets of another context on the same device, copied device to device (no host traffic): a second
+// context that screens ANOTHER part of the reads against the same database -- read parts are independent of each
+// other, so two contexts let the upload of one part run under the scan + confirm of the other (bench.py e2e,
+// engine.run_read_parts).
+int msc_set_targets_from(msc_ctx* ctx, msc_ctx* src) {
+  if (!ctx || !src) return MSC_ERR_STATE;
+  if (ctx == src) return MSC_OK;
+  if (!src->have_targets) return ctx->fail(MSC_ERR_STATE, "msc_set_targets_from: the source context has no targets");
+  if (ctx->device != src->device) return ctx->fail(MSC_ERR_INPUT, "msc_set_targets_from: the contexts are on different devices");
+  CK(cudaSetDevice(ctx->device));
+  RC(drop_deferred(ctx));
+  ctx->n_targets = src->n_targets;
+  ctx->n_bases = src->n_bases;
+  ctx->n_tiles = src->n_tiles;
+  ctx->n_words_alloc = src->n_words_alloc;
+  const uint64_t n_blk = (ctx->n_bases >> kGeneBlockShift) + 2;
+  const size_t xsum_bytes = (ctx->n_words_alloc / 32 + 4) * sizeof(uint32_t);
+  CK(ctx->tg_off.reserve((ctx->n_targets + 2) * sizeof(uint32_t)));
+  CK(ctx->tg_words.reserve(ctx->n_words_alloc * sizeof(uint64_t)));
+  CK(ctx->tg_x.reserve(ctx->n_words_alloc * sizeof(uint64_t)));
+  CK(ctx->xsum.reserve(xsum_bytes));
+  CK(ctx->blk2gene.reserve(n_blk * sizeof(uint32_t)));
+  ctx->tg_ascii.release();  // as for msc_set_targets_packed: msc_rebuild(2) has nothing to redo
+  // the source's pack kernel has finished when its "ASCII buffer is free" event has
+  CK(cudaStreamWaitEvent(ctx->stream, src->ev_tg_free, 0));
+  if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_PACKT0], ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tg_off.p, src->tg_off.p, (ctx->n_targets + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tg_words.p, src->tg_words.p, ctx->n_words_alloc * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tg_x.p, src->tg_x.p, ctx->n_words_alloc * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->xsum.p, src->xsum.p, xsum_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->blk2gene.p, src->blk2gene.p, n_blk * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->ctr(C_TGX), src->ctr(C_TGX), 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->ev_tg_free, ctx->stream));
+  if (ctx->stage_events) CK(cudaEventRecord(ctx->ev[EV_PACKT1], ctx->stream));
+  ctx->have_targets = true;
+  ctx->targets_packed = true;
+  ctx->have_cand = ctx->have_confirm = ctx->have_combine = false;
+  ctx->pend_targets = true;
+  CK(cudaStreamSynchronize(ctx->stream));  // the source may replace its targets as soon as this call has returned
+  return MSC_OK;
+}
+
 uint64_t msc_packed_target_words(const msc_ctx* ctx) { return (ctx && ctx->have_targets) ? (ctx->n_bases + 31) / 32 : 0; }
 
 int msc_fetch_packed_targets(msc_ctx* ctx, uint64_t* words, uint64_t* xplane, int32_t* has_x) {

@@ -3,6 +3,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Iterable, Sequence, Tuple, Union
 
 import numpy as np
@@ -156,6 +157,11 @@ class HotPath:
     def set_targets_ptr(self, ascii_ptr: int, offs_ptr: int, n: int):
         self.n_targets = n
         self._check(self._lib.msc_set_targets(self._ctx, ascii_ptr, offs_ptr, n))
+
+    def set_targets_from(self, other: "HotPath"):
+        """The packed targets of another context on the same device, copied device to device (msc_set_targets_from)."""
+        self.n_targets = other.n_targets
+        self._check(self._lib.msc_set_targets_from(self._ctx, other._ctx))
 
     def rebuild(self, what: int = 3):
         self._check(self._lib.msc_rebuild(self._ctx, what))
@@ -415,3 +421,77 @@ def run_tiled(hp: "HotPath", reads, targets, max_items: int = MAX_ITEMS_PER_READ
             hp.set_shards(1)
     out = [p for p in out if len(p)]
     return np.concatenate(out) if out else np.zeros(0, dtype=MATCH_DTYPE)
+
+
+# ---------------------------------------------------------------------------------------------
+# Read parts on ONE GPU: upload / compute overlap.
+#
+# Every rule of the path is per read (window validity, confirm, MMTol, the result order), so a read
+# set can be screened as independent parts, each with its own key table.  With the parts in separate
+# contexts (separate streams) the upload of part i+1 runs under the scan + confirm + combine of part
+# i: the end-to-end step of BASELINE configs[2] is PCIe time + the LAST part's pipeline instead of
+# PCIe time + the whole pipeline.  Only the first context uploads the targets; the others copy the
+# packed form device to device (msc_set_targets_from).  MaxMatches bounds a (window, k-mer) group
+# over ALL its reads: the parts run in sharded mode (groups above MaxMatches / parts are flagged)
+# and a flagged step raises, so that the caller falls back to one context.
+# ---------------------------------------------------------------------------------------------
+class ReadParts:
+    def __init__(self, cfg: Config, parts: int = 2, device: int = 0, keep_ascii: bool = True):
+        self.parts = int(parts)
+        self.ctx = [HotPath(cfg, device=device, keep_ascii=keep_ascii) for _ in range(self.parts)]
+        if self.parts > 1:
+            for hp in self.ctx:
+                hp.set_shards(self.parts)
+
+    def close(self):
+        for hp in self.ctx:
+            hp.close()
+        self.ctx = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def step(self, reads_ptrs, targets_ptr, out_ptrs):
+        """reads_ptrs[i] = (ascii_ptr, offs_ptr, n_reads) of part i (offsets relative to the part), targets_ptr =
+        (ascii_ptr, offs_ptr, n_targets), out_ptrs[i] = (dst_ptr, capacity in 16-byte records): host (pinned)
+        buffers.  Returns the number of matches of every part; read ids are relative to the part."""
+        res = [0] * self.parts
+        err = []
+
+        def finish(i):
+            try:
+                hp = self.ctx[i]
+                hp.run_stages(0, 1 | 2 | 4)
+                if self.parts > 1 and hp.shard_overflow():
+                    raise MuscatoError(_capi.MSC_ERR_STATE, "a key group may exceed MaxMatches across read parts: run the "
+                                       "reads through one context")
+                res[i] = hp.fetch_into(*out_ptrs[i])
+            except Exception as e:  # surfaced by the caller's thread
+                err.append(e)
+
+        threads = []
+        for i, hp in enumerate(self.ctx):
+            if i == 0:
+                hp.set_reads_ptr(*reads_ptrs[0])
+                hp.set_targets_ptr(*targets_ptr)   # the target upload runs under part 0's table build
+            else:
+                hp.set_targets_from(self.ctx[0])
+                hp.set_reads_ptr(*reads_ptrs[i])   # ... and this upload under part i-1's scan + confirm + combine
+            t = threading.Thread(target=finish, args=(i,))
+            t.start()
+            threads.append(t)
+        for t in threads:
+            t.join()
+        if err:
+            raise err[0]
+        return res
+
+    def stats(self):
+        return [hp.stats() for hp in self.ctx]
+
+    def reset_stats(self):
+        for hp in self.ctx:
+            hp.reset_stats()
