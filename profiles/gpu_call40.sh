@@ -1,10 +1,10 @@
 #!/bin/bash
-# round 2, call 41: more read parts for the e2e step
+# round 2, call 40: read parts on one GPU (upload of part i+1 under the compute of part i): parity + e2e with 1/2/3 parts
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 O=gpurun_out
-
-
+timeout 1200 python -m pytest tests/test_gpu_readparts.py -m gpu -x -q > $O/pytest_parts.log 2>&1; echo "pytest rc=$?"
+tail -5 $O/pytest_parts.log
 brief() { python - "$1" <<'PY'
 import json,sys
 try:
@@ -14,6 +14,6 @@ except Exception as e:
     print("   no JSON line:", e)
 PY
 }
-for p in 4 6 8; do
+for p in 2 1 3; do
 timeout 900 python bench.py --steps 5 --e2e-parts $p --no-cpu-baseline > $O/bench_parts$p.log 2> $O/bench_parts$p.err; echo "== bench e2e parts $p rc=$?"; brief $O/bench_parts$p.log; tail -3 $O/bench_parts$p.err
 done
