@@ -296,11 +296,15 @@ def test_cli_files_drop_in(case, tmp_path, oracle_bin):
 MM_CASES = [("best", 1), ("best", 3), ("best", 7), ("best", 40), ("first", 1), ("first", 5), ("first", 40)]
 
 
+@pytest.mark.parametrize("front", ["auto", "direct"])
 @pytest.mark.parametrize("mode,mm", MM_CASES, ids=[f"{m}{k}" for m, k in MM_CASES])
-def test_maxmatches_truncation_vs_oracle(mode, mm, tmp_path, oracle_bin):
+def test_maxmatches_truncation_vs_oracle(mode, mm, front, tmp_path, oracle_bin, monkeypatch):
     """Q7: per (window, k-mer) group the reference keeps at most MaxMatches pairs through an
     order-dependent heap ("best", cmd/muscato_confirm/main.go:424-448) or the first MaxMatches+1
-    ("first", :233-238).  Repetitive targets + many near-identical reads overflow small limits."""
+    ("first", :233-238).  Repetitive targets + many near-identical reads overflow small limits.
+    Both fronts of the scan (the exact one writes its candidates in another order and with empty slots)."""
+    if front == "direct":
+        monkeypatch.setenv("MSC_FRONT_DIRECT", "1")
     rng = np.random.default_rng(100 + mm)
     unit = helpers.random_dna(rng, 37)
     genes = []
@@ -435,10 +439,13 @@ def _repeat_case(rng, n_genes, n_reads, read_len):
     return reads, genes
 
 
+@pytest.mark.parametrize("front", ["auto", "direct"])
 @pytest.mark.parametrize("mm,mode,mindinuc", [(1000000, "best", 1), (1000, "best", 2), (300, "first", 3)])
-def test_high_multiplicity_stress_vs_oracle(mm, mode, mindinuc, tmp_path, oracle_bin):
+def test_high_multiplicity_stress_vs_oracle(mm, mode, mindinuc, front, tmp_path, oracle_bin, monkeypatch):
     """Hit explosion: thousands of candidates x dozens of reads per k-mer group, 5 mismatches at 100 bp
     (PMatch=0.95), default and small MaxMatches (the latter forces the order-dependent truncation)."""
+    if front == "direct":
+        monkeypatch.setenv("MSC_FRONT_DIRECT", "1")
     rng = np.random.default_rng(1234 + mm % 97)
     reads, genes = _repeat_case(rng, 30, 400, 100)
     cfgd = dict(Windows=[0, 30, 60], WindowWidth=12, MaxReadLength=100, PMatch=0.95, MinDinuc=mindinuc, MMTol=2,
