@@ -101,7 +101,11 @@ const char* msc_last_error(const msc_ctx* ctx);
  * table: replaces buildBloom (cmd/muscato_screen/main.go:116-207), muscato_window_reads
  * (cmd/muscato_window_reads/main.go:94-141) and sortWindows (cmd/muscato/main.go:237-304).
  * n_reads * n_windows <= 2^30 per call; larger read sets are fed in batches (reads are independent
- * of each other: every rule of the path, MMTol included, is per read). */
+ * of each other: every rule of the path, MMTol included, is per read).
+ * The upload is chunked (2^22 reads per chunk): a chunk's offsets are validated on the host, its
+ * copy is queued, and its 2-bit pack + window pass run on the device under the next chunk's copy.
+ * The call returns when the caller's buffers are no longer needed; the table build is stream
+ * ordered behind it and its counters are booked by the next synchronising call. */
 int msc_set_reads(msc_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint64_t n_reads);
 
 /* Same as msc_set_reads for buffers that are already in the memory of ctx's device (e.g. the
